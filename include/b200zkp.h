@@ -1,0 +1,155 @@
+/* b200zkp — C ABI of the B200-native polynomial-commitment path.
+ *
+ * Drop-in boundary for the one hot path of intmax-zkp-core's prover: plonky2's
+ *   PolynomialBatch::from_values / from_coeffs   (plonky2/src/fri/oracle.rs)
+ *   MerkleTree::new / prove                      (plonky2/src/hash/merkle_tree.rs)
+ *   PoseidonHash::{hash_no_pad, two_to_one}, PoseidonPermutation::permute   (plonky2/src/hash/*.rs)
+ *   fft / ifft / coset LDE                       (plonky2_field: field/src/fft.rs, polynomial/mod.rs)
+ * at InternetMaximalism/plonky2 @ f99ed9c — the git dependency pinned by
+ * /root/reference/Cargo.toml:12 and Cargo.lock:333-335 (its source is not vendored in the reference).
+ * The reference reaches these through CircuitBuilder::build and CircuitData::prove, e.g.
+ * /root/reference/src/transaction/circuits/mod.rs:158,453, src/zkdsa/circuits/mod.rs:37,326,
+ * src/rollup/circuits/mod.rs:605,1247.  The Rust binding a maintainer adds is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every field element is a uint64_t (GoldilocksField is #[repr(transparent)] over u64), host
+ *     little-endian; inputs may be non-canonical (>= p), every output is canonical.
+ *   - polynomial batches are column-major: k columns of n = 2^n_log elements, column c at c*n.
+ *   - leaves are rows of the LDE in bit-reversed order: leaf j = LDE row bitrev(j, n_log+rate_bits);
+ *     exported row-major, N = n << rate_bits rows of (k + salt) elements.
+ *   - digests use plonky2's MerkleTree.digests layout (2*(N - 2^cap_height) entries of 4 elements);
+ *     the cap has 2^cap_height entries of 4 elements.
+ *   - all functions return 0 on success, a negative b200zkp_status otherwise; nothing throws or
+ *     aborts across this boundary.  b200zkp_last_error(ctx) describes the last failure on ctx.
+ *   - a ctx owns one device, one stream and its twiddle caches; calls on one ctx are serialised by an
+ *     internal mutex, distinct ctxs are independent.  There is NO CPU fallback: without a CUDA
+ *     device every compute entry point fails with B200ZKP_ERR_CUDA.
+ *   - "_dev" entry points take device pointers (caller-owned, e.g. torch tensors) and enqueue on the
+ *     ctx stream without synchronising; the others take host pointers and return when the result is
+ *     in the caller's buffer.
+ */
+#ifndef B200ZKP_H
+#define B200ZKP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B200ZKP_OK = 0,
+    B200ZKP_ERR_BAD_ARG = -1, /* plonky2's asserts: power-of-two sizes, cap_height <= log2(N), ... */
+    B200ZKP_ERR_OOM = -2,
+    B200ZKP_ERR_CUDA = -3,
+    B200ZKP_ERR_UNSUPPORTED = -4
+} b200zkp_status;
+
+typedef struct b200zkp_ctx b200zkp_ctx;
+typedef struct b200zkp_batch b200zkp_batch; /* plonky2 PolynomialBatch */
+typedef struct b200zkp_tree b200zkp_tree;   /* plonky2 MerkleTree */
+
+#define B200ZKP_SALT_SIZE 4 /* plonky2 fri/oracle.rs SALT_SIZE */
+
+/* ---- library / context ------------------------------------------------------------------- */
+const char* b200zkp_version(void);
+/* number of CUDA devices visible, or a negative status */
+int b200zkp_device_count(void);
+/* stream == NULL: the ctx creates its own non-blocking stream; otherwise a cudaStream_t to share */
+int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out);
+void b200zkp_ctx_destroy(b200zkp_ctx* ctx);
+const char* b200zkp_last_error(const b200zkp_ctx* ctx);
+int b200zkp_ctx_synchronize(b200zkp_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx);
+/* pinned host memory for callers that want full-speed H2D/D2H */
+int b200zkp_host_alloc(size_t bytes, void** out);
+void b200zkp_host_free(void* p);
+
+/* ---- PolynomialBatch::from_values / from_coeffs (host buffers) ---------------------------- */
+/* values: k*n column-major evaluations on the size-n subgroup.  salt: NULL (blinding = false, every
+ * config the reference uses) or 4*N column-major elements in natural LDE order (the F::rand_vec
+ * columns plonky2 appends when blinding).  The batch keeps coefficients, LDE, digests and cap on the
+ * device; nothing but the cap is copied back until an accessor asks. */
+int b200zkp_commit_from_values(b200zkp_ctx* ctx, const uint64_t* values, uint32_t n_log, uint32_t k,
+                               uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                               b200zkp_batch** out);
+int b200zkp_commit_from_coeffs(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,
+                               uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                               b200zkp_batch** out);
+void b200zkp_batch_free(b200zkp_batch* b);
+/* shape: n_log, k, rate_bits, cap_height, salt_size */
+int b200zkp_batch_shape(const b200zkp_batch* b, uint32_t shape[5]);
+int b200zkp_batch_cap(b200zkp_batch* b, uint64_t* out /* 4 * 2^cap_height */);
+int b200zkp_batch_coeffs(b200zkp_batch* b, uint64_t* out /* k * n column-major */);
+int b200zkp_batch_leaves(b200zkp_batch* b, uint64_t* out /* N * (k+salt) row-major */);
+int b200zkp_batch_digests(b200zkp_batch* b, uint64_t* out /* 4 * 2*(N - 2^cap_height) */);
+/* MerkleTree::get + MerkleTree::prove for a list of leaf indices:
+ * rows: n_idx * (k+salt); siblings: n_idx * (log2 N - cap_height) * 4 (bottom-up); either may be NULL */
+int b200zkp_batch_rows(b200zkp_batch* b, const uint64_t* idx, uint64_t n_idx, uint64_t* rows,
+                       uint64_t* siblings);
+/* PolynomialBatch::get_lde_values(index, step): leaf bitrev(index*step) without the salt, k elements */
+int b200zkp_batch_lde_values(b200zkp_batch* b, uint64_t index, uint64_t step, uint64_t* out);
+/* device views of a batch, valid until b200zkp_batch_free: coefficients [k][n], LDE
+ * [(k+salt)][N] column-major in leaf (bit-reversed) row order, digests, cap */
+int b200zkp_batch_device_ptrs(b200zkp_batch* b, const uint64_t** coeffs, const uint64_t** lde,
+                              const uint64_t** digests, const uint64_t** cap);
+
+/* ---- MerkleTree::new (host buffers) -------------------------------------------------------- */
+/* leaves: n_leaves rows of leaf_len elements, row-major.  hash_or_noop: leaf_len <= 4 is not hashed. */
+int b200zkp_merkle_new(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len,
+                       uint32_t cap_height, b200zkp_tree** out);
+void b200zkp_tree_free(b200zkp_tree* t);
+int b200zkp_tree_cap(b200zkp_tree* t, uint64_t* out);
+int b200zkp_tree_digests(b200zkp_tree* t, uint64_t* out);
+int b200zkp_tree_prove(b200zkp_tree* t, const uint64_t* idx, uint64_t n_idx, uint64_t* siblings);
+
+/* ---- Hasher / field helpers (host buffers, batched) --------------------------------------- */
+int b200zkp_poseidon_permute(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint64_t* out); /* 12 each */
+int b200zkp_hash_no_pad(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, uint64_t* out);
+int b200zkp_hash_or_noop(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, uint64_t* out);
+int b200zkp_two_to_one(b200zkp_ctx* ctx, const uint64_t* left, const uint64_t* right, uint64_t count,
+                       uint64_t* out);
+/* in-place transforms of k columns of 2^n_log elements (natural order in and out) */
+int b200zkp_ntt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k);
+int b200zkp_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k);
+/* coset LDE: coeffs k*n -> out k*N, out[c][i] = p_c(7 * w_N^i), natural order (A4) */
+int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,
+                      uint32_t rate_bits, uint64_t* out);
+
+/* ---- device-resident stages (caller-owned device buffers; async on the ctx stream) --------- */
+/* values [k][in_stride] -> coeffs [k][out_stride], natural order.  scratch: k*n elements, may alias
+ * nothing; needed when n_log > 8 (may be NULL otherwise). */
+int b200zkp_dev_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
+                     uint64_t out_stride, uint64_t* scratch, uint32_t n_log, uint32_t k);
+/* coeffs [k][coeff_stride] -> lde [k][lde_stride] in leaf order, only leaf blocks
+ * [block_begin, block_end) of the 2^rate_bits coset blocks (block b = leaves [b*n, (b+1)*n), i.e. the
+ * coset 7*w_N^bitrev(b)); block b is written at column offset (b - block_begin)*n. */
+int b200zkp_dev_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,
+                    uint64_t lde_stride, uint32_t n_log, uint32_t k, uint32_t rate_bits,
+                    uint32_t block_begin, uint32_t block_end);
+/* salt [4][N] natural order -> rows of lde columns in leaf order for blocks [block_begin, block_end) */
+int b200zkp_dev_salt(b200zkp_ctx* ctx, const uint64_t* salt, uint64_t* lde_salt_cols, uint64_t lde_stride,
+                     uint32_t n_log, uint32_t rate_bits, uint32_t block_begin, uint32_t block_end);
+/* Merkle forest over n_leaves leaves, element (row, c) at leaves[row*row_stride + c*col_stride]:
+ * digests 4*2*(n_leaves - 2^cap_height), cap 4*2^cap_height (both device). */
+int b200zkp_dev_merkle(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t row_stride, uint64_t col_stride,
+                       uint32_t leaf_len, uint64_t n_leaves, uint32_t cap_height, uint64_t* digests,
+                       uint64_t* cap);
+/* whole commitment on caller-owned device buffers (what bench.py times with inputs resident in HBM):
+ * in [k][n] -> coeffs [k][n], lde [(k+salt)][N], digests, cap.  is_coeffs selects from_coeffs. */
+int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,
+                       uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, uint64_t* coeffs,
+                       uint64_t* lde, uint64_t* digests, uint64_t* cap);
+/* column-major [cols][col_stride] rows [row0,row0+n_rows) -> row-major [n_rows][cols] (device) */
+int b200zkp_dev_transpose_to_rows(b200zkp_ctx* ctx, const uint64_t* cm, uint64_t col_stride, uint32_t cols,
+                                  uint64_t row0, uint64_t n_rows, uint64_t* rm);
+/* integer-pipe micro-benchmark: runs `iters` dependent-chain rounds of the chosen
+ * instruction mix on every SM and returns giga thread-instructions per second in *out_gips.
+ * kind: 0 IMAD.WIDE.U32, 1 IADD3, 2 IMAD (32-bit), 3 alternating IMAD.WIDE/IADD3, 4 LOP3 */
+int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZKP_H */

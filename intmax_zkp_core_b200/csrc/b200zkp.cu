@@ -1,0 +1,898 @@
+// C ABI implementation (include/b200zkp.h): contexts, twiddle caches, pass scheduling, handles.
+// Product code: no CPU fallback, nothing from oracle/ is included, linked or executed here.
+#include "../../include/b200zkp.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "merkle_kernels.cuh"
+#include "ntt_kernels.cuh"
+#include "host_plan.hpp"
+
+using gl::u32;
+using gl::u64;
+
+// ------------------------------------------------------------------------------------------------
+struct TwoLevel {
+    u64* lo = nullptr;
+    u64* hi = nullptr;
+    u32 lo_bits = 0;
+};
+
+struct b200zkp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::mutex mu;
+    std::string err;
+    u64 launches = 0;
+    u64* wtab[2][9] = {};                               // [dir][B] w_{2^B}^(+-e)
+    std::map<u32, TwoLevel> tw[2];                      // [dir][n_log] -> w_n^(+-e)
+    std::map<u64, std::vector<TwoLevel>> coset;         // (n_log<<8 | rate_bits) -> per leaf block
+    std::map<u32, TwoLevel> shift7;                     // N_log -> 7^i (natural-order coset_lde helper)
+    std::multimap<size_t, void*> pool;                  // cached device allocations
+    std::vector<void*> table_allocs;
+};
+
+struct b200zkp_batch {
+    b200zkp_ctx* ctx;
+    u32 n_log, k, rate_bits, cap_height, salt;
+    u64 *coeffs, *lde, *digests, *cap;
+    size_t coeffs_b, lde_b, digests_b, cap_b;
+};
+
+struct b200zkp_tree {
+    b200zkp_ctx* ctx;
+    u64 n_leaves;
+    u32 leaf_len, cap_height;
+    u64 *digests, *cap;
+    size_t digests_b, cap_b;
+};
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                 \
+            return e__ == cudaErrorMemoryAllocation ? B200ZKP_ERR_OOM : B200ZKP_ERR_CUDA;     \
+        }                                                                                     \
+    } while (0)
+#define TRY(expr) do { int rc__ = (expr); if (rc__ != 0) return rc__; } while (0)
+#define BAD(ctx, msg) do { (ctx)->err = (msg); return B200ZKP_ERR_BAD_ARG; } while (0)
+#define LAUNCH_CHECK(ctx) do { (ctx)->launches++; CUDA_TRY(ctx, cudaGetLastError()); } while (0)
+
+static int dev_alloc(b200zkp_ctx* ctx, size_t bytes, void** out) {
+    *out = nullptr;
+    if (bytes == 0) return 0;
+    auto it = ctx->pool.find(bytes);
+    if (it != ctx->pool.end()) { *out = it->second; ctx->pool.erase(it); return 0; }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        // drop the cache and retry once
+        (void)cudaGetLastError();
+        for (auto& kv : ctx->pool) cudaFree(kv.second);
+        ctx->pool.clear();
+        e = cudaMalloc(out, bytes);
+    }
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? B200ZKP_ERR_OOM : B200ZKP_ERR_CUDA;
+    }
+    return 0;
+}
+static void dev_release(b200zkp_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    // keep at most ~16 cached blocks; stream order makes reuse on the same ctx safe
+    if (ctx->pool.size() < 16) ctx->pool.emplace(bytes, p);
+    else cudaFree(p);
+}
+
+static int upload(b200zkp_ctx* ctx, const std::vector<u64>& h, u64** d) {
+    CUDA_TRY(ctx, cudaMalloc((void**)d, h.size() * sizeof(u64)));
+    ctx->table_allocs.push_back(*d);
+    CUDA_TRY(ctx, cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int make_two_level(b200zkp_ctx* ctx, u64 base, u32 bits, TwoLevel* t) {
+    std::vector<u64> lo, hi;
+    t->lo_bits = hostgl::two_level_powers(base, bits, &lo, &hi);
+    TRY(upload(ctx, lo, &t->lo));
+    TRY(upload(ctx, hi, &t->hi));
+    return 0;
+}
+
+static int get_tw(b200zkp_ctx* ctx, int dir, u32 n_log, TwoLevel* out) {
+    auto it = ctx->tw[dir].find(n_log);
+    if (it == ctx->tw[dir].end()) {
+        u64 w = hostgl::root(n_log);
+        if (dir) w = hostgl::inv(w);
+        TwoLevel t;
+        TRY(make_two_level(ctx, w, n_log, &t));
+        it = ctx->tw[dir].emplace(n_log, t).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// per leaf block b of the LDE: powers of s_b = 7 * w_N^bitrev(b, rate_bits)
+static int get_coset(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const std::vector<TwoLevel>** out) {
+    u64 key = ((u64)n_log << 8) | rate_bits;
+    auto it = ctx->coset.find(key);
+    if (it == ctx->coset.end()) {
+        std::vector<TwoLevel> v((size_t)1 << rate_bits);
+        for (u32 b = 0; b < (1u << rate_bits); b++) {
+            u64 s = hostgl::coset_shift_of_block(n_log, rate_bits, b);
+            TRY(make_two_level(ctx, s, n_log, &v[b]));
+        }
+        it = ctx->coset.emplace(key, std::move(v)).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+template <int B>
+static void launch_pass_b(const ntt::PassParams& p, u64 blocks, cudaStream_t s) {
+    ntt::ntt_pass_kernel<B><<<(unsigned)blocks, ntt::THREADS, 0, s>>>(p);
+}
+static int launch_pass(b200zkp_ctx* ctx, const ntt::PassParams& p, u32 B) {
+    u64 T = ntt::TILE_ELEMS >> B;
+    u64 total_batches = (u64)p.ncols << (p.n_log - B);
+    u64 blocks = (total_batches + T - 1) / T;
+    if (blocks == 0) return 0;
+    if (blocks > 0x7fffffffull) BAD(ctx, "transform too large for one launch");
+    switch (B) {
+        case 1: launch_pass_b<1>(p, blocks, ctx->stream); break;
+        case 2: launch_pass_b<2>(p, blocks, ctx->stream); break;
+        case 3: launch_pass_b<3>(p, blocks, ctx->stream); break;
+        case 4: launch_pass_b<4>(p, blocks, ctx->stream); break;
+        case 5: launch_pass_b<5>(p, blocks, ctx->stream); break;
+        case 6: launch_pass_b<6>(p, blocks, ctx->stream); break;
+        case 7: launch_pass_b<7>(p, blocks, ctx->stream); break;
+        case 8: launch_pass_b<8>(p, blocks, ctx->stream); break;
+        default: BAD(ctx, "internal: bad pass width");
+    }
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int launch_canon_copy(b200zkp_ctx* ctx, const u64* src, u64* dst, u64 count) {
+    if (!count) return 0;
+    ntt::canon_copy_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(src, dst, count);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// One multi-pass transform over `ncols` columns.
+//   bitrev_out: in-place DIF order (LDE leaf order); else natural order (needs scratch when P > 1)
+static int run_transform(b200zkp_ctx* ctx, const u64* in, u64 in_stride, u64* out, u64 out_stride,
+                         u64* scratch, u32 n_log, u32 ncols, int dir, bool bitrev_out,
+                         const TwoLevel* scale, u64 out_scale, bool canon_in) {
+    if (ncols == 0) return 0;
+    if (n_log == 0) {
+        // single point: the transform is the identity (scale^0 = 1)
+        for (u32 c = 0; c < ncols; c++) {
+            // rare path (n = 1): one tiny launch per column keeps strides general
+            TRY(launch_canon_copy(ctx, in + c * in_stride, out + c * out_stride, 1));
+        }
+        return 0;
+    }
+    if (n_log > 32) BAD(ctx, "n_log exceeds the field's two-adicity (32)");
+    TwoLevel tw{};
+    if (n_log > 8) TRY(get_tw(ctx, dir, n_log, &tw));
+    if (!bitrev_out && n_log > 8 && !scratch) BAD(ctx, "scratch buffer required for n_log > 8");
+    ntt::TwoLevelPtr twp{tw.lo, tw.hi, tw.lo_bits};
+    ntt::TwoLevelPtr scp{};
+    if (scale) scp = ntt::TwoLevelPtr{scale->lo, scale->hi, scale->lo_bits};
+    ntt::Plan plan;
+    ntt::make_plan(&plan, in, in_stride, out, out_stride, scratch, n_log, ncols, ctx->wtab[dir], twp, bitrev_out,
+                   scale ? &scp : nullptr, out_scale, canon_in);
+    for (u32 pi = 0; pi < plan.n_passes; pi++) TRY(launch_pass(ctx, plan.pass[pi], plan.bits[pi]));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* b200zkp_version(void) { return "b200zkp 0.1 (sm_100a)"; }
+
+extern "C" int b200zkp_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return B200ZKP_ERR_CUDA; }
+    return n;
+}
+
+static int ctx_init_tables(b200zkp_ctx* ctx) {
+    for (int dir = 0; dir < 2; dir++)
+        for (u32 B = 1; B <= 8; B++) TRY(upload(ctx, hostgl::small_root_table(B, dir), &ctx->wtab[dir][B]));
+    return 0;
+}
+
+extern "C" int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out) {
+    if (!out) return B200ZKP_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return B200ZKP_ERR_CUDA; }
+    if (device < 0 || device >= n) return B200ZKP_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return B200ZKP_ERR_CUDA; }
+    b200zkp_ctx* ctx = new (std::nothrow) b200zkp_ctx();
+    if (!ctx) return B200ZKP_ERR_OOM;
+    ctx->device = device;
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            (void)cudaGetLastError(); delete ctx; return B200ZKP_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    int rc = ctx_init_tables(ctx);
+    if (rc != 0) { b200zkp_ctx_destroy(ctx); return rc; }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void b200zkp_ctx_destroy(b200zkp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->pool) cudaFree(kv.second);
+    for (void* p : ctx->table_allocs) cudaFree(p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* b200zkp_last_error(const b200zkp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int b200zkp_ctx_synchronize(b200zkp_ctx* ctx) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b200zkp_host_alloc(size_t bytes, void** out) {
+    if (!out) return B200ZKP_ERR_BAD_ARG;
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); *out = nullptr; return e == cudaErrorMemoryAllocation ? B200ZKP_ERR_OOM : B200ZKP_ERR_CUDA; }
+    return 0;
+}
+extern "C" void b200zkp_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------------------------------------ device stages
+struct Guard {
+    b200zkp_ctx* c;
+    explicit Guard(b200zkp_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
+    ~Guard() { c->mu.unlock(); }
+};
+
+static int dev_intt_locked(b200zkp_ctx* ctx, const u64* values, u64 in_stride, u64* coeffs, u64 out_stride,
+                           u64* scratch, u32 n_log, u32 k) {
+    u64 n_inv = hostgl::inv(((u64)1 << n_log) % hostgl::P);
+    return run_transform(ctx, values, in_stride, coeffs, out_stride, scratch, n_log, k, /*dir=*/1,
+                         /*bitrev_out=*/false, nullptr, n_log ? n_inv : 0, /*canon_in=*/true);
+}
+
+extern "C" int b200zkp_dev_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
+                                uint64_t out_stride, uint64_t* scratch, uint32_t n_log, uint32_t k) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!values || !coeffs) BAD(ctx, "null buffer");
+    return dev_intt_locked(ctx, (const u64*)values, in_stride, (u64*)coeffs, out_stride, (u64*)scratch, n_log, k);
+}
+
+static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride, u64* lde, u64 lde_stride,
+                          u32 n_log, u32 k, u32 rate_bits, u32 b0, u32 b1) {
+    if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "rate_bits / n_log out of range");
+    if (b0 > b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
+    const std::vector<TwoLevel>* cs;
+    TRY(get_coset(ctx, n_log, rate_bits, &cs));
+    for (u32 b = b0; b < b1; b++) {
+        u64* dst = lde + ((u64)(b - b0) << n_log);
+        TRY(run_transform(ctx, coeffs, coeff_stride, dst, lde_stride, nullptr, n_log, k, /*dir=*/0,
+                          /*bitrev_out=*/true, &(*cs)[b], 0, /*canon_in=*/true));
+    }
+    return 0;
+}
+
+extern "C" int b200zkp_dev_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,
+                               uint64_t lde_stride, uint32_t n_log, uint32_t k, uint32_t rate_bits,
+                               uint32_t block_begin, uint32_t block_end) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!coeffs || !lde) BAD(ctx, "null buffer");
+    return dev_lde_locked(ctx, (const u64*)coeffs, coeff_stride, (u64*)lde, lde_stride, n_log, k, rate_bits,
+                          block_begin, block_end);
+}
+
+static int dev_salt_locked(b200zkp_ctx* ctx, const u64* salt, u64* lde_salt, u64 lde_stride, u32 n_log,
+                           u32 rate_bits, u32 b0, u32 b1) {
+    // leaf j = natural row bitrev(j, N_log); leaf block b covers j in [b*n, (b+1)*n):
+    // natural index = bitrev(jl, n_log) * 2^r + bitrev(b, r).  One strided bit-reversed copy per block.
+    u32 N_log = n_log + rate_bits;
+    if (b0 == 0 && b1 == (1u << rate_bits)) {
+        u64 cnt = (u64)B200ZKP_SALT_SIZE << N_log;
+        ntt::bitrev_copy_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(
+            salt, lde_salt, N_log, B200ZKP_SALT_SIZE, (u64)1 << N_log, lde_stride);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    ctx->err = "salted commitments are only supported unsharded";
+    return B200ZKP_ERR_UNSUPPORTED;
+}
+
+extern "C" int b200zkp_dev_salt(b200zkp_ctx* ctx, const uint64_t* salt, uint64_t* lde_salt_cols,
+                                uint64_t lde_stride, uint32_t n_log, uint32_t rate_bits, uint32_t block_begin,
+                                uint32_t block_end) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!salt || !lde_salt_cols) BAD(ctx, "null buffer");
+    return dev_salt_locked(ctx, (const u64*)salt, (u64*)lde_salt_cols, lde_stride, n_log, rate_bits, block_begin, block_end);
+}
+
+static int dev_merkle_locked(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride, u64 col_stride, u32 leaf_len,
+                             u64 n_leaves, u32 cap_height, u64* digests, u64* cap) {
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) BAD(ctx, "number of leaves must be a power of two");
+    u32 lg = 0;
+    while (((u64)1 << lg) < n_leaves) lg++;
+    if (cap_height > lg) BAD(ctx, "cap_height exceeds log2(number of leaves)");
+    if (!leaves || !cap) BAD(ctx, "null buffer");
+    merkle::TreeShape shape;
+    shape.sub_log = lg - cap_height;
+    shape.sub_digests = 2 * (((u64)1 << shape.sub_log) - 1);
+    if (shape.sub_log > 0 && !digests) BAD(ctx, "null digests buffer");
+    {
+        u64 blocks = (n_leaves + 127) / 128;
+        merkle::leaf_hash_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(leaves, row_stride, col_stride,
+                                                                            leaf_len, n_leaves, shape, digests, cap, 1u);
+        LAUNCH_CHECK(ctx);
+    }
+    for (u32 layer = 0; layer < shape.sub_log; layer++) {
+        u64 n_parents = n_leaves >> (layer + 1);
+        u64 blocks = (n_parents + 127) / 128;
+        merkle::merkle_level_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
+        LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+extern "C" int b200zkp_dev_merkle(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t row_stride,
+                                  uint64_t col_stride, uint32_t leaf_len, uint64_t n_leaves, uint32_t cap_height,
+                                  uint64_t* digests, uint64_t* cap) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return dev_merkle_locked(ctx, (const u64*)leaves, row_stride, col_stride, leaf_len, n_leaves, cap_height,
+                             (u64*)digests, (u64*)cap);
+}
+
+static int dev_commit_locked(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log, u32 k, u32 rate_bits,
+                             u32 cap_height, const u64* salt, u64* coeffs, u64* lde, u64* digests, u64* cap) {
+    if (k == 0) BAD(ctx, "empty polynomial batch");
+    if (n_log + rate_bits > 32 || rate_bits > 8) BAD(ctx, "n_log + rate_bits exceeds two-adicity");
+    if (cap_height > n_log + rate_bits) BAD(ctx, "cap_height exceeds log2(LDE size)");
+    if (!in || !coeffs || !lde || !cap) BAD(ctx, "null buffer");
+    u64 n = (u64)1 << n_log, N = n << rate_bits;
+    u32 row = k + (salt ? B200ZKP_SALT_SIZE : 0);
+    if (is_coeffs) TRY(launch_canon_copy(ctx, in, coeffs, (u64)k * n));
+    else TRY(dev_intt_locked(ctx, in, n, coeffs, n, /*scratch=*/lde, n_log, k));   // the LDE buffer is free until step 2
+    TRY(dev_lde_locked(ctx, coeffs, n, lde, N, n_log, k, rate_bits, 0, 1u << rate_bits));
+    if (salt) TRY(dev_salt_locked(ctx, salt, lde + (u64)k * N, N, n_log, rate_bits, 0, 1u << rate_bits));
+    return dev_merkle_locked(ctx, lde, /*row_stride=*/1, /*col_stride=*/N, row, N, cap_height, digests, cap);
+}
+
+extern "C" int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,
+                                  uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, uint64_t* coeffs,
+                                  uint64_t* lde, uint64_t* digests, uint64_t* cap) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return dev_commit_locked(ctx, (const u64*)in, is_coeffs, n_log, k, rate_bits, cap_height, (const u64*)salt,
+                             (u64*)coeffs, (u64*)lde, (u64*)digests, (u64*)cap);
+}
+
+static int dev_transpose_rows_locked(b200zkp_ctx* ctx, const u64* cm, u64 col_stride, u32 cols, u64 row0,
+                                     u64 n_rows, u64* rm) {
+    if (!n_rows || !cols) return 0;
+    dim3 grid((unsigned)((n_rows + 31) / 32), (cols + 31) / 32), block(32, 8);
+    merkle::transpose_to_rows_kernel<<<grid, block, 0, ctx->stream>>>(cm, col_stride, cols, row0, n_rows, rm);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int b200zkp_dev_transpose_to_rows(b200zkp_ctx* ctx, const uint64_t* cm, uint64_t col_stride,
+                                             uint32_t cols, uint64_t row0, uint64_t n_rows, uint64_t* rm) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!cm || !rm) BAD(ctx, "null buffer");
+    return dev_transpose_rows_locked(ctx, (const u64*)cm, col_stride, cols, row0, n_rows, (u64*)rm);
+}
+
+// ------------------------------------------------------------------------------------------------ PolynomialBatch
+static void batch_release(b200zkp_batch* b) {
+    dev_release(b->ctx, b->coeffs, b->coeffs_b);
+    dev_release(b->ctx, b->lde, b->lde_b);
+    dev_release(b->ctx, b->digests, b->digests_b);
+    dev_release(b->ctx, b->cap, b->cap_b);
+    delete b;
+}
+
+static int commit_host(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log, u32 k, u32 rate_bits,
+                       u32 cap_height, const u64* salt, b200zkp_batch** out) {
+    if (!out) BAD(ctx, "null out");
+    *out = nullptr;
+    if (k == 0) BAD(ctx, "empty polynomial batch");
+    if (n_log + rate_bits > 32 || rate_bits > 8) BAD(ctx, "n_log + rate_bits exceeds two-adicity");
+    if (cap_height > n_log + rate_bits) BAD(ctx, "cap_height exceeds log2(LDE size)");
+    if (!in) BAD(ctx, "null input");
+    u64 n = (u64)1 << n_log, N = n << rate_bits;
+    u32 row = k + (salt ? B200ZKP_SALT_SIZE : 0);
+    b200zkp_batch* b = new (std::nothrow) b200zkp_batch();
+    if (!b) return B200ZKP_ERR_OOM;
+    b->ctx = ctx; b->n_log = n_log; b->k = k; b->rate_bits = rate_bits; b->cap_height = cap_height;
+    b->salt = salt ? B200ZKP_SALT_SIZE : 0;
+    b->coeffs_b = (size_t)k * n * 8;
+    b->lde_b = (size_t)row * N * 8;
+    b->digests_b = (size_t)2 * (N - ((u64)1 << cap_height)) * 32;
+    b->cap_b = ((size_t)32) << cap_height;
+    int rc = 0;
+    void* d_in = nullptr; size_t in_b = (size_t)k * n * 8;
+    void* d_salt = nullptr; size_t salt_b = salt ? (size_t)B200ZKP_SALT_SIZE * N * 8 : 0;
+    if ((rc = dev_alloc(ctx, b->coeffs_b, (void**)&b->coeffs)) || (rc = dev_alloc(ctx, b->lde_b, (void**)&b->lde)) ||
+        (rc = dev_alloc(ctx, b->digests_b, (void**)&b->digests)) || (rc = dev_alloc(ctx, b->cap_b, (void**)&b->cap)) ||
+        (rc = dev_alloc(ctx, in_b, &d_in)) || (rc = dev_alloc(ctx, salt_b, &d_salt))) {
+        dev_release(ctx, d_in, in_b); dev_release(ctx, d_salt, salt_b);
+        batch_release(b);
+        return rc;
+    }
+    auto fail = [&](int code) { dev_release(ctx, d_in, in_b); dev_release(ctx, d_salt, salt_b); batch_release(b); return code; };
+    cudaError_t e = cudaMemcpyAsync(d_in, in, in_b, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && salt) e = cudaMemcpyAsync(d_salt, salt, salt_b, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("H2D: ") + cudaGetErrorString(e); return fail(B200ZKP_ERR_CUDA); }
+    rc = dev_commit_locked(ctx, (const u64*)d_in, is_coeffs, n_log, k, rate_bits, cap_height, (const u64*)d_salt,
+                           b->coeffs, b->lde, b->digests, b->cap);
+    if (rc) return fail(rc);
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("commit: ") + cudaGetErrorString(e); return fail(B200ZKP_ERR_CUDA); }
+    dev_release(ctx, d_in, in_b);
+    dev_release(ctx, d_salt, salt_b);
+    *out = b;
+    return 0;
+}
+
+extern "C" int b200zkp_commit_from_values(b200zkp_ctx* ctx, const uint64_t* values, uint32_t n_log, uint32_t k,
+                                          uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                                          b200zkp_batch** out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return commit_host(ctx, (const u64*)values, 0, n_log, k, rate_bits, cap_height, (const u64*)salt, out);
+}
+extern "C" int b200zkp_commit_from_coeffs(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,
+                                          uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                                          b200zkp_batch** out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return commit_host(ctx, (const u64*)coeffs, 1, n_log, k, rate_bits, cap_height, (const u64*)salt, out);
+}
+
+extern "C" void b200zkp_batch_free(b200zkp_batch* b) {
+    if (!b) return;
+    Guard g(b->ctx);
+    cudaStreamSynchronize(b->ctx->stream);
+    batch_release(b);
+}
+
+extern "C" int b200zkp_batch_shape(const b200zkp_batch* b, uint32_t shape[5]) {
+    if (!b || !shape) return B200ZKP_ERR_BAD_ARG;
+    shape[0] = b->n_log; shape[1] = b->k; shape[2] = b->rate_bits; shape[3] = b->cap_height; shape[4] = b->salt;
+    return 0;
+}
+
+static int d2h(b200zkp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+static int h2d(b200zkp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int b200zkp_batch_cap(b200zkp_batch* b, uint64_t* out) {
+    if (!b || !out) return B200ZKP_ERR_BAD_ARG;
+    Guard g(b->ctx);
+    return d2h(b->ctx, out, b->cap, b->cap_b);
+}
+extern "C" int b200zkp_batch_coeffs(b200zkp_batch* b, uint64_t* out) {
+    if (!b || !out) return B200ZKP_ERR_BAD_ARG;
+    Guard g(b->ctx);
+    return d2h(b->ctx, out, b->coeffs, b->coeffs_b);
+}
+extern "C" int b200zkp_batch_digests(b200zkp_batch* b, uint64_t* out) {
+    if (!b) return B200ZKP_ERR_BAD_ARG;
+    Guard g(b->ctx);
+    if (b->digests_b && !out) BAD(b->ctx, "null out");
+    return d2h(b->ctx, out, b->digests, b->digests_b);
+}
+
+// leaves leave the device row-major: transpose in chunks through a bounded staging buffer
+extern "C" int b200zkp_batch_leaves(b200zkp_batch* b, uint64_t* out) {
+    if (!b || !out) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_ctx* ctx = b->ctx;
+    Guard g(ctx);
+    u64 N = (u64)1 << (b->n_log + b->rate_bits);
+    u32 row = b->k + b->salt;
+    u64 chunk_rows = std::min<u64>(N, std::max<u64>(1, ((u64)256 << 20) / ((u64)row * 8)));
+    void* stage = nullptr; size_t stage_b = (size_t)chunk_rows * row * 8;
+    TRY(dev_alloc(ctx, stage_b, &stage));
+    int rc = 0;
+    for (u64 r0 = 0; r0 < N && !rc; r0 += chunk_rows) {
+        u64 nr = std::min(chunk_rows, N - r0);
+        rc = dev_transpose_rows_locked(ctx, b->lde, N, row, r0, nr, (u64*)stage);
+        if (!rc) rc = d2h(ctx, out + r0 * row, stage, (size_t)nr * row * 8);
+    }
+    dev_release(ctx, stage, stage_b);
+    return rc;
+}
+
+static int gather_locked(b200zkp_ctx* ctx, const u64* lde, u64 N, u32 row, const u64* digests, u32 sub_log,
+                         const u64* idx, u64 n_idx, u64* rows, u64* siblings) {
+    if (!n_idx) return 0;
+    for (u64 i = 0; i < n_idx; i++) if (idx[i] >= N) BAD(ctx, "leaf index out of range");
+    void *d_idx = nullptr, *d_rows = nullptr, *d_sib = nullptr;
+    size_t idx_b = n_idx * 8, rows_b = rows ? n_idx * row * 8 : 0, sib_b = siblings ? n_idx * sub_log * 32 : 0;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, idx_b, &d_idx)) || (rc = dev_alloc(ctx, rows_b, &d_rows)) || (rc = dev_alloc(ctx, sib_b, &d_sib))) {
+        dev_release(ctx, d_idx, idx_b); dev_release(ctx, d_rows, rows_b); dev_release(ctx, d_sib, sib_b);
+        return rc;
+    }
+    auto done = [&](int code) { dev_release(ctx, d_idx, idx_b); dev_release(ctx, d_rows, rows_b); dev_release(ctx, d_sib, sib_b); return code; };
+    if ((rc = h2d(ctx, d_idx, idx, idx_b))) return done(rc);
+    if (rows_b) {
+        u64 cnt = n_idx * row;
+        merkle::gather_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(lde, N, row, (const u64*)d_idx, n_idx, (u64*)d_rows);
+        ctx->launches++;
+        if ((rc = d2h(ctx, rows, d_rows, rows_b))) return done(rc);
+    }
+    if (sib_b) {
+        merkle::TreeShape shape; shape.sub_log = sub_log; shape.sub_digests = 2 * (((u64)1 << sub_log) - 1);
+        u64 cnt = n_idx * sub_log;
+        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(digests, shape, (const u64*)d_idx, n_idx, (u64*)d_sib);
+        ctx->launches++;
+        if ((rc = d2h(ctx, siblings, d_sib, sib_b))) return done(rc);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return done(B200ZKP_ERR_CUDA); }
+    return done(0);
+}
+
+extern "C" int b200zkp_batch_rows(b200zkp_batch* b, const uint64_t* idx, uint64_t n_idx, uint64_t* rows,
+                                  uint64_t* siblings) {
+    if (!b || (!idx && n_idx)) return B200ZKP_ERR_BAD_ARG;
+    Guard g(b->ctx);
+    u32 N_log = b->n_log + b->rate_bits;
+    return gather_locked(b->ctx, b->lde, (u64)1 << N_log, b->k + b->salt, b->digests, N_log - b->cap_height,
+                         (const u64*)idx, n_idx, (u64*)rows, (u64*)siblings);
+}
+
+extern "C" int b200zkp_batch_lde_values(b200zkp_batch* b, uint64_t index, uint64_t step, uint64_t* out) {
+    if (!b || !out) return B200ZKP_ERR_BAD_ARG;
+    Guard g(b->ctx);
+    u32 N_log = b->n_log + b->rate_bits;
+    u64 N = (u64)1 << N_log;
+    u64 nat = index * step;
+    if (nat >= N) BAD(b->ctx, "index * step out of range");
+    u64 leaf = 0;
+    for (u32 i = 0; i < N_log; i++) leaf |= ((nat >> i) & 1) << (N_log - 1 - i);
+    // salt columns are last, so the first k entries of the row are the polynomial values
+    return gather_locked(b->ctx, b->lde, N, b->k, b->digests, 0, &leaf, 1, (u64*)out, nullptr);
+}
+
+extern "C" int b200zkp_batch_device_ptrs(b200zkp_batch* b, const uint64_t** coeffs, const uint64_t** lde,
+                                         const uint64_t** digests, const uint64_t** cap) {
+    if (!b) return B200ZKP_ERR_BAD_ARG;
+    if (coeffs) *coeffs = (const uint64_t*)b->coeffs;
+    if (lde) *lde = (const uint64_t*)b->lde;
+    if (digests) *digests = (const uint64_t*)b->digests;
+    if (cap) *cap = (const uint64_t*)b->cap;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ MerkleTree
+extern "C" int b200zkp_merkle_new(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len,
+                                  uint32_t cap_height, b200zkp_tree** out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!out) BAD(ctx, "null out");
+    *out = nullptr;
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) BAD(ctx, "number of leaves must be a power of two");
+    u32 lg = 0;
+    while (((u64)1 << lg) < n_leaves) lg++;
+    if (cap_height > lg) BAD(ctx, "cap_height exceeds log2(number of leaves)");
+    if (!leaves && leaf_len) BAD(ctx, "null leaves");
+    b200zkp_tree* t = new (std::nothrow) b200zkp_tree();
+    if (!t) return B200ZKP_ERR_OOM;
+    t->ctx = ctx; t->n_leaves = n_leaves; t->leaf_len = leaf_len; t->cap_height = cap_height;
+    t->digests_b = (size_t)2 * (n_leaves - ((u64)1 << cap_height)) * 32;
+    t->cap_b = ((size_t)32) << cap_height;
+    void* d_leaves = nullptr; size_t leaves_b = std::max<size_t>((size_t)n_leaves * leaf_len * 8, 8);
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, t->digests_b, (void**)&t->digests)) || (rc = dev_alloc(ctx, t->cap_b, (void**)&t->cap)) ||
+        (rc = dev_alloc(ctx, leaves_b, &d_leaves))) {
+        dev_release(ctx, d_leaves, leaves_b); dev_release(ctx, t->digests, t->digests_b); dev_release(ctx, t->cap, t->cap_b);
+        delete t; return rc;
+    }
+    auto fail = [&](int code) { dev_release(ctx, d_leaves, leaves_b); dev_release(ctx, t->digests, t->digests_b); dev_release(ctx, t->cap, t->cap_b); delete t; return code; };
+    if ((rc = h2d(ctx, d_leaves, leaves, (size_t)n_leaves * leaf_len * 8))) return fail(rc);
+    if ((rc = dev_merkle_locked(ctx, (const u64*)d_leaves, leaf_len, 1, leaf_len, n_leaves, cap_height, t->digests, t->cap))) return fail(rc);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("merkle_new: ") + cudaGetErrorString(e); return fail(B200ZKP_ERR_CUDA); }
+    dev_release(ctx, d_leaves, leaves_b);
+    *out = t;
+    return 0;
+}
+extern "C" void b200zkp_tree_free(b200zkp_tree* t) {
+    if (!t) return;
+    Guard g(t->ctx);
+    cudaStreamSynchronize(t->ctx->stream);
+    dev_release(t->ctx, t->digests, t->digests_b);
+    dev_release(t->ctx, t->cap, t->cap_b);
+    delete t;
+}
+extern "C" int b200zkp_tree_cap(b200zkp_tree* t, uint64_t* out) {
+    if (!t || !out) return B200ZKP_ERR_BAD_ARG;
+    Guard g(t->ctx);
+    return d2h(t->ctx, out, t->cap, t->cap_b);
+}
+extern "C" int b200zkp_tree_digests(b200zkp_tree* t, uint64_t* out) {
+    if (!t) return B200ZKP_ERR_BAD_ARG;
+    Guard g(t->ctx);
+    if (t->digests_b && !out) BAD(t->ctx, "null out");
+    return d2h(t->ctx, out, t->digests, t->digests_b);
+}
+extern "C" int b200zkp_tree_prove(b200zkp_tree* t, const uint64_t* idx, uint64_t n_idx, uint64_t* siblings) {
+    if (!t || (!idx && n_idx)) return B200ZKP_ERR_BAD_ARG;
+    Guard g(t->ctx);
+    u32 lg = 0;
+    while (((u64)1 << lg) < t->n_leaves) lg++;
+    if (lg == t->cap_height) {
+        for (u64 i = 0; i < n_idx; i++) if (idx[i] >= t->n_leaves) BAD(t->ctx, "leaf index out of range");
+        return 0;  // empty proofs
+    }
+    if (!siblings && n_idx) BAD(t->ctx, "null out");
+    return gather_locked(t->ctx, nullptr, t->n_leaves, 0, t->digests, lg - t->cap_height, (const u64*)idx, n_idx,
+                         nullptr, (u64*)siblings);
+}
+
+// ------------------------------------------------------------------------------------------------ Hasher / field helpers
+template <typename F>
+static int with_io(b200zkp_ctx* ctx, const void* in, size_t in_b, void* out, size_t out_b, F body) {
+    void *d_in = nullptr, *d_out = nullptr;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, std::max<size_t>(in_b, 8), &d_in)) || (rc = dev_alloc(ctx, std::max<size_t>(out_b, 8), &d_out))) {
+        dev_release(ctx, d_in, std::max<size_t>(in_b, 8));
+        return rc;
+    }
+    auto done = [&](int code) { dev_release(ctx, d_in, std::max<size_t>(in_b, 8)); dev_release(ctx, d_out, std::max<size_t>(out_b, 8)); return code; };
+    if ((rc = h2d(ctx, d_in, in, in_b))) return done(rc);
+    if ((rc = body((u64*)d_in, (u64*)d_out))) return done(rc);
+    if ((rc = d2h(ctx, out, d_out, out_b))) return done(rc);
+    return done(0);
+}
+
+extern "C" int b200zkp_poseidon_permute(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!count) return 0;
+    if (!in || !out) BAD(ctx, "null buffer");
+    return with_io(ctx, in, count * 96, out, count * 96, [&](u64* di, u64* dout) -> int {
+        merkle::permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(di, dout, count);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    });
+}
+
+static int hash_rows(b200zkp_ctx* ctx, const u64* in, u64 count, u32 len, u64* out, bool noop_short) {
+    if (!count) return 0;
+    if ((!in && len) || !out) BAD(ctx, "null buffer");
+    return with_io(ctx, in, count * len * 8, out, count * 32, [&](u64* di, u64* dout) -> int {
+        merkle::TreeShape shape; shape.sub_log = 0; shape.sub_digests = 0;
+        merkle::leaf_hash_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(di, len, 1, len, count, shape, nullptr, dout, noop_short ? 1u : 0u);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    });
+}
+extern "C" int b200zkp_hash_no_pad(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return hash_rows(ctx, (const u64*)in, count, len, (u64*)out, false);
+}
+extern "C" int b200zkp_hash_or_noop(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return hash_rows(ctx, (const u64*)in, count, len, (u64*)out, true);
+}
+
+extern "C" int b200zkp_two_to_one(b200zkp_ctx* ctx, const uint64_t* left, const uint64_t* right, uint64_t count,
+                                  uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!count) return 0;
+    if (!left || !right || !out) BAD(ctx, "null buffer");
+    void* d_r = nullptr;
+    TRY(dev_alloc(ctx, count * 32, &d_r));
+    int rc = h2d(ctx, d_r, right, count * 32);
+    if (!rc) rc = with_io(ctx, left, count * 32, out, count * 32, [&](u64* dl, u64* dout) -> int {
+        merkle::two_to_one_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(dl, (const u64*)d_r, dout, count);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    });
+    dev_release(ctx, d_r, count * 32);
+    return rc;
+}
+
+static int transform_host(b200zkp_ctx* ctx, u64* data, u32 n_log, u32 k, int dir) {
+    if (!k) return 0;
+    if (!data) BAD(ctx, "null buffer");
+    if (n_log > 32) BAD(ctx, "n_log exceeds two-adicity");
+    size_t bytes = ((size_t)k << n_log) * 8;
+    void *d = nullptr, *scratch = nullptr, *dout = nullptr;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, bytes, &d)) || (rc = dev_alloc(ctx, bytes, &scratch)) || (rc = dev_alloc(ctx, bytes, &dout))) {
+        dev_release(ctx, d, bytes); dev_release(ctx, scratch, bytes);
+        return rc;
+    }
+    auto done = [&](int code) { dev_release(ctx, d, bytes); dev_release(ctx, scratch, bytes); dev_release(ctx, dout, bytes); return code; };
+    if ((rc = h2d(ctx, d, data, bytes))) return done(rc);
+    u64 n = (u64)1 << n_log;
+    if (dir) rc = dev_intt_locked(ctx, (const u64*)d, n, (u64*)dout, n, (u64*)scratch, n_log, k);
+    else rc = run_transform(ctx, (const u64*)d, n, (u64*)dout, n, (u64*)scratch, n_log, k, 0, false, nullptr, 0, true);
+    if (rc) return done(rc);
+    return done(d2h(ctx, data, dout, bytes));
+}
+extern "C" int b200zkp_ntt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return transform_host(ctx, (u64*)data, n_log, k, 0);
+}
+extern "C" int b200zkp_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    return transform_host(ctx, (u64*)data, n_log, k, 1);
+}
+
+// natural-order coset LDE (an independent route from the leaf-order dev_lde: zero-pad, scale by 7^i,
+// one size-N natural transform) — plonky2's own formulation of A4.
+extern "C" int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,
+                                 uint32_t rate_bits, uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!k) return 0;
+    if (!coeffs || !out) BAD(ctx, "null buffer");
+    u32 N_log = n_log + rate_bits;
+    if (N_log > 32 || rate_bits > 8) BAD(ctx, "n_log + rate_bits exceeds two-adicity");
+    u64 n = (u64)1 << n_log, N = (u64)1 << N_log;
+    auto it = ctx->shift7.find(N_log);
+    if (it == ctx->shift7.end()) {
+        TwoLevel t;
+        TRY(make_two_level(ctx, 7, N_log, &t));
+        it = ctx->shift7.emplace(N_log, t).first;
+    }
+    size_t big = (size_t)k * N * 8;
+    void *d_pad = nullptr, *d_scr = nullptr, *d_out = nullptr;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, big, &d_pad)) || (rc = dev_alloc(ctx, big, &d_scr)) || (rc = dev_alloc(ctx, big, &d_out))) {
+        dev_release(ctx, d_pad, big); dev_release(ctx, d_scr, big);
+        return rc;
+    }
+    auto done = [&](int code) { dev_release(ctx, d_pad, big); dev_release(ctx, d_scr, big); dev_release(ctx, d_out, big); return code; };
+    cudaError_t e = cudaMemsetAsync(d_pad, 0, big, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_pad, N * 8, coeffs, n * 8, n * 8, k, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("coset_lde H2D: ") + cudaGetErrorString(e); return done(B200ZKP_ERR_CUDA); }
+    rc = run_transform(ctx, (const u64*)d_pad, N, (u64*)d_out, N, (u64*)d_scr, N_log, k, 0, false, &it->second, 0, true);
+    if (rc) return done(rc);
+    return done(d2h(ctx, out, d_out, big));
+}
+
+// ------------------------------------------------------------------------------------------------ integer-pipe roof
+template <int KIND>
+__global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
+    u32 a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 77u;
+    u64 w0 = a, w1 = b, w2 = a ^ b, w3 = a + b, w4 = a * 3u, w5 = b * 5u, w6 = a - b, w7 = ~a;
+    u32 x0 = a, x1 = b, x2 = a ^ b, x3 = a + b, x4 = a * 3u, x5 = b * 5u, x6 = a - b, x7 = ~a;
+    for (u32 it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            if (KIND == 0 || KIND == 3) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w0) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w1) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w2) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w3) : "r"(a), "r"(b));
+            }
+            if (KIND == 0) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w4) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w5) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w6) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w7) : "r"(a), "r"(b));
+            }
+            if (KIND == 1 || KIND == 3) {
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x0) : "r"(a));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x1) : "r"(b));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x2) : "r"(a));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x3) : "r"(b));
+            }
+            if (KIND == 1) {
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x4) : "r"(a));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x5) : "r"(b));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x6) : "r"(a));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(x7) : "r"(b));
+            }
+            if (KIND == 2) {
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x4) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x6) : "r"(a), "r"(b));
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x7) : "r"(a), "r"(b));
+            }
+            if (KIND == 4) {
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x0) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x1) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x2) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x3) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x4) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x5) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x6) : "r"(a), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
+            }
+        }
+    }
+    u64 w = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+    u32 x = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (u32)w ^ (u32)(w >> 32);
+    if (x == 0xdeadbeefu && iters == 0xffffffffu) *sink = x;   // keep the chains alive
+}
+
+extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!out_gips || kind < 0 || kind > 4) BAD(ctx, "bad argument");
+    int sms = 0;
+    CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    u32* sink = nullptr;
+    TRY(dev_alloc(ctx, 8, (void**)&sink));
+    unsigned blocks = (unsigned)sms * 8;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    auto launch = [&](u32 n) {
+        switch (kind) {
+            case 0: int_pipe_kernel<0><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 1: int_pipe_kernel<1><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 2: int_pipe_kernel<2><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 3: int_pipe_kernel<3><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            default: int_pipe_kernel<4><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+        }
+        ctx->launches++;
+    };
+    launch(iters / 8 + 1);  // warm-up
+    CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    launch(iters);
+    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    dev_release(ctx, sink, 8);
+    double instr = (double)blocks * 256.0 * (double)iters * 64.0;   // 8 rounds x 8 instructions per iteration
+    *out_gips = instr / (ms * 1e-3) / 1e9;
+    return 0;
+}

@@ -1,0 +1,238 @@
+// Goldilocks NTT passes for sm_100a: inverse NTT (values -> coefficients) and the coset
+// low-degree extension written directly in bit-reversed (leaf) order.
+//
+// Replaces plonky2_field `fft_classic` / `ifft_with_options` / `coset_fft_with_options` / `lde`
+// (plonky2 @ f99ed9c, field/src/fft.rs, field/src/polynomial/mod.rs) and, for the LDE, also
+// plonky2 `transpose` + `reverse_index_bits_in_place` (plonky2/src/util) — SURVEY.md rows A2, A4, A5,
+// A12.  Reached from the reference through PolynomialBatch::from_values / from_coeffs inside every
+// prove()/build(), e.g. /root/reference/src/transaction/circuits/mod.rs:158,453.
+//
+// A transform of 2^L points is split into P = ceil(L/8) passes (Cooley-Tukey / "4-step"):
+//   pass p views a column as [A][2^B][C]; a CTA stages a tile of 2^B x T elements (T batches of the
+//   contiguous inner dimension, so every global access is a run of >= 64 B) in shared memory, runs the
+//   2^B-point decimation-in-frequency sub-transform with radix-8 butterflies held in registers (one
+//   shared-memory round trip per three stages), multiplies by the inter-pass twiddle w_M^(c*k1) and
+//   writes the tile back.
+//   * bit-reversed output (LDE): every pass writes in place -> the result is the plain DIF order,
+//     which IS plonky2's leaf order inside one coset, so no transpose / bit-reversal pass exists.
+//   * natural output (iNTT): non-final passes write k1 in natural position, the final pass scatters
+//     with the digit-reversed batch index (runs of T contiguous elements).
+// All values are canonical (< p) inside the passes.
+#pragma once
+#include "goldilocks.cuh"
+
+namespace ntt {
+
+using gl::u32;
+using gl::u64;
+
+static constexpr int TILE_ELEMS = 2048;  // elements staged per CTA
+static constexpr int THREADS = 256;      // 8 elements per thread
+static constexpr int MAX_PASSES = 4;
+
+enum OutMode : u32 {
+    OUT_INPLACE_NATURAL = 0,  // non-final pass, element k1 stored at (a, k1, c)
+    OUT_INPLACE_BITREV = 1,   // any pass, element k1 stored at (a, bitrev(k1), c)
+    OUT_FINAL_NATURAL = 2,    // final pass, digit-reversed scatter to natural order
+};
+
+struct PassParams {
+    const u64* in;
+    u64* out;
+    u64 in_col_stride, out_col_stride;
+    u32 ncols;
+    u32 n_log;     // log2 of the column transform size
+    u32 C_log;     // log2 of the inner (contiguous) extent below this pass's dimension
+    u32 out_mode;
+    const u64* wtab;   // w_{2^B}^e for e < 2^(B-1), direction specific
+    const u64* sc_lo;  // optional input scaling s^i = sc_hi[i >> sc_lo_bits] * sc_lo[i & mask]
+    const u64* sc_hi;
+    u32 sc_lo_bits;
+    const u64* tw_lo;  // optional inter-pass twiddle w_n^e = tw_hi[e >> tw_lo_bits] * tw_lo[e & mask]
+    const u64* tw_hi;
+    u32 tw_lo_bits;
+    u64 out_scale;     // 0: none; else multiply every output (n^-1 of the inverse transform)
+    u32 canon_in;      // inputs may be non-canonical
+    u32 n_digits;      // OUT_FINAL_NATURAL: bit widths of the earlier passes, first pass first
+    u32 digits[MAX_PASSES];
+};
+
+GL_FN u32 bitrev(u32 x, u32 bits) { return bits ? (gl::brev32(x) >> (32 - bits)) : 0; }
+
+// The pass body is written once and compiled two ways: on the device one CUDA thread runs each
+// NTT_FOR_THREADS body and NTT_SYNC is __syncthreads(); under B200ZKP_HOST_EMU (tests only) the same
+// text steps all 256 "threads" of a CTA in a loop so the index logic can be checked without a GPU.
+#ifdef B200ZKP_HOST_EMU
+#define NTT_FOR_THREADS(tid) for (u32 tid = 0; tid < THREADS; tid++)
+#define NTT_SYNC() do {} while (0)
+#define NTT_SHARED static thread_local
+#else
+#define NTT_FOR_THREADS(tid) for (u32 tid = threadIdx.x, once__ = 1; once__; once__ = 0)
+#define NTT_SYNC() __syncthreads()
+#define NTT_SHARED __shared__
+#endif
+
+// in-register DIF over 2^A elements x[j] <-> g = gbase + j*st ; stages sigma0 .. sigma0+A-1 of a 2^B transform
+template <int A>
+GL_FN void dif_group(u64 (&x)[1 << A], const u64* __restrict__ wt, u32 ul, u32 st, u32 sigma0) {
+#pragma unroll
+    for (int u = 0; u < A; u++) {
+        const int half = (1 << A) >> (u + 1);
+#pragma unroll
+        for (int j = 0; j < (1 << A); j++) {
+            if (j & half) continue;
+            u32 jl = j & (half - 1);
+            u32 e = (jl * st + ul) << (sigma0 + u);
+            u64 a = x[j], b = x[j + half];
+            x[j] = gl::add(a, b);
+            x[j + half] = gl::mul(gl::sub(a, b), wt[e]);
+        }
+    }
+}
+
+template <int A>
+GL_FN void run_round(u64* __restrict__ tile, const u64* __restrict__ wt, u32 B, u32 T, u32 TP, u32 sigma0,
+                     u32 tid) {
+    const u32 st_log = B - sigma0 - A;
+    const u32 st = 1u << st_log;
+    constexpr int UNITS_PER_THREAD = 8 >> A;
+#pragma unroll
+    for (int r = 0; r < UNITS_PER_THREAD; r++) {
+        u32 U = tid + r * THREADS;
+        u32 t = U % T, w = U / T;
+        u32 ul = w & (st - 1), uh = w >> st_log;
+        u32 gbase = (uh << (st_log + A)) + ul;
+        u64 x[1 << A];
+#pragma unroll
+        for (int j = 0; j < (1 << A); j++) x[j] = tile[(gbase + j * st) * TP + t];
+        dif_group<A>(x, wt, ul, st, sigma0);
+#pragma unroll
+        for (int j = 0; j < (1 << A); j++) tile[(gbase + j * st) * TP + t] = x[j];
+    }
+}
+
+GL_FN u64 two_level(const u64* __restrict__ lo, const u64* __restrict__ hi, u32 lo_bits, u64 e) {
+    u64 a = gl::ldg(lo + (e & (((u64)1 << lo_bits) - 1)));
+    u64 b = gl::ldg(hi + (e >> lo_bits));
+    return gl::mul(a, b);
+}
+
+// digit reversal of a batch index: in-place position digits (d1 most significant) <-> natural
+// batch index beta' = d1 + 2^B1 * (d2 + 2^B2 * ...)
+GL_FN u64 digit_reverse(u64 beta_nat, const PassParams& p) {
+    u64 pos = 0;
+    for (u32 i = 0; i < p.n_digits; i++) {
+        u32 w = p.digits[i];
+        pos = (pos << w) | (beta_nat & (((u64)1 << w) - 1));
+        beta_nat >>= w;
+    }
+    return pos;
+}
+
+// B = bits of this pass (1..8, compile time so the rounds fully unroll); block = CTA index
+template <int B>
+GL_FN void pass_body(const PassParams& p, u32 block) {
+    constexpr u32 T = TILE_ELEMS >> B;
+    constexpr u32 TP = T + 1;
+    constexpr u32 NPTS = 1u << B;
+    NTT_SHARED u64 tile[NPTS * TP];
+    NTT_SHARED u64 wt[(NPTS / 2) ? (NPTS / 2) : 1];
+
+    const u32 batches_log = p.n_log - B;                 // batches per column
+    const u64 total_batches = (u64)p.ncols << batches_log;
+    const u64 tile_b0 = (u64)block * T;
+    const bool final_pass = (p.C_log == 0);
+    const u64 C_mask = ((u64)1 << p.C_log) - 1;
+
+    // ---- load
+    NTT_FOR_THREADS(tid) {
+        for (u32 i = tid; i < NPTS / 2; i += THREADS) wt[i] = p.wtab[i];
+        for (u32 idx = tid; idx < (u32)TILE_ELEMS; idx += THREADS) {
+            u32 b, g;
+            if (final_pass) { b = idx >> B; g = idx & (NPTS - 1); }
+            else { b = idx % T; g = idx / T; }
+            u64 bg = tile_b0 + b;
+            u64 v = 0;
+            if (bg < total_batches) {
+                u64 col = bg >> batches_log;
+                u64 beta = bg & (((u64)1 << batches_log) - 1);
+                if (p.out_mode == OUT_FINAL_NATURAL) beta = digit_reverse(beta, p);
+                u64 a = beta >> p.C_log, c = beta & C_mask;
+                u64 i_col = (a << (B + p.C_log)) + ((u64)g << p.C_log) + c;
+                v = p.in[col * p.in_col_stride + i_col];
+                if (p.canon_in) v = gl::canon(v);
+                if (p.sc_lo) v = gl::mul(v, two_level(p.sc_lo, p.sc_hi, p.sc_lo_bits, i_col));
+            }
+            tile[g * TP + b] = v;
+        }
+    }
+    NTT_SYNC();
+
+    // ---- 2^B-point DIF, radix-8 in registers
+    {
+        u32 sigma = 0;
+#pragma unroll
+        for (int r = 0; r < B / 3; r++) {
+            NTT_FOR_THREADS(tid) { run_round<3>(tile, wt, B, T, TP, sigma, tid); }
+            sigma += 3;
+            NTT_SYNC();
+        }
+        if (B % 3 == 2) { NTT_FOR_THREADS(tid) { run_round<2>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B % 3 == 1) { NTT_FOR_THREADS(tid) { run_round<1>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+    }
+
+    // ---- twiddle + store
+    NTT_FOR_THREADS(tid) {
+        for (u32 idx = tid; idx < (u32)TILE_ELEMS; idx += THREADS) {
+            u32 b, row;   // row = k1 (natural modes) or g~ (bit-reversed mode)
+            if (final_pass && p.out_mode == OUT_INPLACE_BITREV) { b = idx >> B; row = idx & (NPTS - 1); }
+            else { b = idx % T; row = idx / T; }
+            u64 bg = tile_b0 + b;
+            if (bg >= total_batches) continue;
+            u32 gt, k1;
+            if (p.out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
+            else { k1 = row; gt = bitrev(row, B); }
+            u64 v = tile[gt * TP + b];
+            u64 col = bg >> batches_log;
+            u64 beta = bg & (((u64)1 << batches_log) - 1);
+            u64 o_col;
+            if (p.out_mode == OUT_FINAL_NATURAL) {
+                o_col = beta + ((u64)k1 << batches_log);
+            } else {
+                u64 a = beta >> p.C_log, c = beta & C_mask;
+                u32 pos = (p.out_mode == OUT_INPLACE_BITREV) ? gt : k1;
+                o_col = (a << (B + p.C_log)) + ((u64)pos << p.C_log) + c;
+                if (p.tw_lo) {
+                    u64 e = (c * k1) << (p.n_log - B - p.C_log);
+                    v = gl::mul(v, two_level(p.tw_lo, p.tw_hi, p.tw_lo_bits, e));
+                }
+            }
+            if (p.out_scale) v = gl::mul(v, p.out_scale);
+            p.out[col * p.out_col_stride + o_col] = v;
+        }
+    }
+}
+
+#ifndef B200ZKP_HOST_EMU
+template <int B>
+__global__ void __launch_bounds__(THREADS) ntt_pass_kernel(PassParams p) { pass_body<B>(p, blockIdx.x); }
+
+// dst[c][bitrev(i)] = canon(src[c][i]) : salt columns enter the leaves in bit-reversed row order (A4/A5)
+__global__ void bitrev_copy_kernel(const u64* __restrict__ src, u64* __restrict__ dst, u32 n_log, u32 ncols,
+                                   u64 src_stride, u64 dst_stride) {
+    u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 n = (u64)1 << n_log;
+    if (g >= n * ncols) return;
+    u64 c = g >> n_log, i = g & (n - 1);
+    u64 j = n_log ? (gl::brev64(i) >> (64 - n_log)) : 0;
+    dst[c * dst_stride + j] = gl::canon(src[c * src_stride + i]);
+}
+
+__global__ void canon_copy_kernel(const u64* __restrict__ src, u64* __restrict__ dst, u64 count) {
+    u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < count) dst[g] = gl::canon(src[g]);
+}
+
+#endif  // !B200ZKP_HOST_EMU
+
+}  // namespace ntt
