@@ -62,6 +62,14 @@ const char* b200zkp_last_error(const b200zkp_ctx* ctx);
 int b200zkp_ctx_synchronize(b200zkp_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx);
+/* per-stage device timing (CUDA events on the ctx stream around each stage; off by default).
+ * b200zkp_ctx_stage_ms synchronises, returns the summed milliseconds and span counts per stage since the
+ * last call, and resets them.  Labels follow plonky2's TimingTree scopes ("IFFT", "FFT + blinding",
+ * "build Merkle tree" split into leaf hashing and the level reduction). */
+enum { B200ZKP_STAGE_INTT = 0, B200ZKP_STAGE_LDE = 1, B200ZKP_STAGE_LEAF_HASH = 2, B200ZKP_STAGE_TREE = 3,
+       B200ZKP_N_STAGES = 4 };
+int b200zkp_ctx_set_timing(b200zkp_ctx* ctx, int enabled);
+int b200zkp_ctx_stage_ms(b200zkp_ctx* ctx, double ms[B200ZKP_N_STAGES], uint32_t counts[B200ZKP_N_STAGES]);
 /* pinned host memory for callers that want full-speed H2D/D2H */
 int b200zkp_host_alloc(size_t bytes, void** out);
 void b200zkp_host_free(void* p);

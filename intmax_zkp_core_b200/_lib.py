@@ -1,0 +1,119 @@
+"""Loader for the C-ABI shared library (include/b200zkp.h).
+
+The library is built in-tree by `build()` (nvcc, sm_100a only) and loaded with ctypes.  There is no CPU
+fallback: if the library is missing and cannot be built, or no CUDA device is present, every compute call
+raises — the product path never routes through oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200zkp.so")
+SRC = os.path.join(_HERE, "csrc", "b200zkp.cu")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "b200zkp.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+
+class B200ZkpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200zkp status {code}: {msg}")
+        self.code = code
+
+
+def _sources():
+    d = os.path.join(_HERE, "csrc")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [HEADER]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/b200zkp.cu for sm_100a into libb200zkp.so (in-tree, so it travels with the repo)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libb200zkp.so (there is no CPU fallback)")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+_SIGS = {
+    "b200zkp_version": (C.c_char_p, []),
+    "b200zkp_device_count": (C.c_int, []),
+    "b200zkp_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200zkp_ctx_destroy": (None, [C.c_void_p]),
+    "b200zkp_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200zkp_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "b200zkp_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "b200zkp_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200zkp_ctx_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), u32p]),
+    "b200zkp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "b200zkp_host_free": (None, [C.c_void_p]),
+    "b200zkp_commit_from_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200zkp_commit_from_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200zkp_batch_free": (None, [C.c_void_p]),
+    "b200zkp_batch_shape": (C.c_int, [C.c_void_p, u32p]),
+    "b200zkp_batch_cap": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_batch_coeffs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_batch_leaves": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_batch_digests": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_batch_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "b200zkp_batch_lde_values": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b200zkp_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "b200zkp_merkle_new": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "b200zkp_tree_free": (None, [C.c_void_p]),
+    "b200zkp_tree_cap": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_tree_digests": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_tree_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zkp_poseidon_permute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zkp_hash_no_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "b200zkp_hash_or_noop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "b200zkp_two_to_one": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zkp_ntt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "b200zkp_intt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "b200zkp_coset_lde": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "b200zkp_dev_intt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32]),
+    "b200zkp_dev_lde": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "b200zkp_dev_salt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "b200zkp_dev_merkle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200zkp_dev_commit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zkp_dev_transpose_to_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b200zkp_int_pipe_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_double)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def lib() -> C.CDLL:
+    """Load (building first if the sources are newer) the shared library; raises if that is impossible."""
+    global _lib
+    if _lib is None:
+        if needs_build():
+            build()
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(l, name)      # AttributeError here = the library does not export the declared ABI
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib

@@ -39,6 +39,38 @@ struct b200zkp_ctx {
     std::map<u32, TwoLevel> shift7;                     // N_log -> 7^i (natural-order coset_lde helper)
     std::multimap<size_t, void*> pool;                  // cached device allocations
     std::vector<void*> table_allocs;
+    // optional per-stage timing (bench.py): CUDA event pairs recorded on the ctx stream
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_free;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+};
+
+struct StageTimer {
+    b200zkp_ctx* c;
+    int stage;
+    cudaEvent_t a = nullptr;
+    static cudaEvent_t get(b200zkp_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->ev_free.empty()) { e = c->ev_free.back(); c->ev_free.pop_back(); }
+        else if (cudaEventCreate(&e) != cudaSuccess) { (void)cudaGetLastError(); e = nullptr; }
+        return e;
+    }
+    StageTimer(b200zkp_ctx* ctx, int st) : c(ctx), stage(st) {
+        if (c->timing && (a = get(c))) cudaEventRecord(a, c->stream);
+    }
+    ~StageTimer() {
+        if (!a) return;
+        cudaEvent_t b = get(c);
+        if (b) { cudaEventRecord(b, c->stream); c->spans.push_back({stage, a, b}); }
+        else c->ev_free.push_back(a);
+    }
+};
+
+struct Guard {
+    b200zkp_ctx* c;
+    explicit Guard(b200zkp_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
+    ~Guard() { c->mu.unlock(); }
 };
 
 struct b200zkp_batch {
@@ -245,6 +277,8 @@ extern "C" void b200zkp_ctx_destroy(b200zkp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->pool) cudaFree(kv.second);
     for (void* p : ctx->table_allocs) cudaFree(p);
+    for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -258,6 +292,33 @@ extern "C" int b200zkp_ctx_synchronize(b200zkp_ctx* ctx) {
     return 0;
 }
 
+extern "C" int b200zkp_ctx_set_timing(b200zkp_ctx* ctx, int enabled) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    ctx->timing = enabled != 0;
+    return 0;
+}
+
+// Synchronises the stream, adds up the recorded spans per stage and clears them.
+extern "C" int b200zkp_ctx_stage_ms(b200zkp_ctx* ctx, double ms[B200ZKP_N_STAGES], uint32_t counts[B200ZKP_N_STAGES]) {
+    if (!ctx || !ms) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < B200ZKP_N_STAGES; i++) { ms[i] = 0; if (counts) counts[i] = 0; }
+    for (auto& sp : ctx->spans) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess && sp.stage >= 0 && sp.stage < B200ZKP_N_STAGES) {
+            ms[sp.stage] += t;
+            if (counts) counts[sp.stage]++;
+        }
+        ctx->ev_free.push_back(sp.a);
+        ctx->ev_free.push_back(sp.b);
+    }
+    (void)cudaGetLastError();
+    ctx->spans.clear();
+    return 0;
+}
+
 extern "C" int b200zkp_host_alloc(size_t bytes, void** out) {
     if (!out) return B200ZKP_ERR_BAD_ARG;
     cudaError_t e = cudaMallocHost(out, bytes);
@@ -267,15 +328,11 @@ extern "C" int b200zkp_host_alloc(size_t bytes, void** out) {
 extern "C" void b200zkp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 // ------------------------------------------------------------------------------------------------ device stages
-struct Guard {
-    b200zkp_ctx* c;
-    explicit Guard(b200zkp_ctx* ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
-    ~Guard() { c->mu.unlock(); }
-};
 
 static int dev_intt_locked(b200zkp_ctx* ctx, const u64* values, u64 in_stride, u64* coeffs, u64 out_stride,
                            u64* scratch, u32 n_log, u32 k) {
     u64 n_inv = hostgl::inv(((u64)1 << n_log) % hostgl::P);
+    StageTimer tm(ctx, B200ZKP_STAGE_INTT);
     return run_transform(ctx, values, in_stride, coeffs, out_stride, scratch, n_log, k, /*dir=*/1,
                          /*bitrev_out=*/false, nullptr, n_log ? n_inv : 0, /*canon_in=*/true);
 }
@@ -294,6 +351,7 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
     if (b0 > b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
     const std::vector<TwoLevel>* cs;
     TRY(get_coset(ctx, n_log, rate_bits, &cs));
+    StageTimer tm(ctx, B200ZKP_STAGE_LDE);
     for (u32 b = b0; b < b1; b++) {
         u64* dst = lde + ((u64)(b - b0) << n_log);
         TRY(run_transform(ctx, coeffs, coeff_stride, dst, lde_stride, nullptr, n_log, k, /*dir=*/0,
@@ -349,11 +407,13 @@ static int dev_merkle_locked(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride
     shape.sub_digests = 2 * (((u64)1 << shape.sub_log) - 1);
     if (shape.sub_log > 0 && !digests) BAD(ctx, "null digests buffer");
     {
+        StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
         u64 blocks = (n_leaves + 127) / 128;
         merkle::leaf_hash_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(leaves, row_stride, col_stride,
                                                                             leaf_len, n_leaves, shape, digests, cap, 1u);
         LAUNCH_CHECK(ctx);
     }
+    StageTimer tm(ctx, B200ZKP_STAGE_TREE);
     for (u32 layer = 0; layer < shape.sub_log; layer++) {
         u64 n_parents = n_leaves >> (layer + 1);
         u64 blocks = (n_parents + 127) / 128;

@@ -43,14 +43,18 @@ static inline uint64_t sbox(uint64_t x) {
     return mulnc(x3, x4);
 }
 static inline void mds(uint64_t s[WIDTH], const uint64_t* addc) {
-    uint64_t o[WIDTH];
+    /* split into 32-bit halves so the 12x12 small-constant products accumulate in plain u64 (plonky2's
+     * mds_row_shf works on the same idea); doubled array avoids the index wrap */
+    uint64_t lo[2 * WIDTH], hi[2 * WIDTH];
+    for (int i = 0; i < WIDTH; i++) { lo[i] = lo[i + WIDTH] = (uint32_t)s[i]; hi[i] = hi[i + WIDTH] = s[i] >> 32; }
     for (int r = 0; r < WIDTH; r++) {
-        u128 acc = addc ? addc[r] : 0;
-        for (int i = 0; i < WIDTH; i++) acc += (u128)s[(i + r) % WIDTH] * CIRC[i];
-        if (r == 0) acc += (u128)s[0] * 8;
-        o[r] = red128(acc);
+        uint64_t L = 0, H = 0;
+        for (int i = 0; i < WIDTH; i++) { L += lo[i + r] * CIRC[i]; H += hi[i + r] * CIRC[i]; }
+        if (r == 0) { L += lo[0] * 8; H += hi[0] * 8; }
+        u128 acc = (u128)L + ((u128)H << 32);
+        if (addc) acc += addc[r];
+        s[r] = red128(acc);
     }
-    memcpy(s, o, sizeof o);
 }
 void cpub_permute(uint64_t s[WIDTH]) {
     for (int i = 0; i < WIDTH; i++) s[i] = red128((u128)s[i] + RC_FULL[i]);

@@ -1,0 +1,97 @@
+"""N > 1 host logic on CPU: two gloo ranks walk the multi-GPU partition of intmax_zkp_core_b200.device
+(column-sharded iNTT -> all-gather coefficients -> leaf-range-sharded LDE + local cap subtrees -> all-gather cap)
+with the oracle standing in for the kernels, and must reproduce the unsharded oracle commitment."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_log, k, r, h, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from intmax_zkp_core_b200.device import shard_layout
+    from helpers import bitrev_perm
+    n, N = 1 << n_log, 1 << (n_log + r)
+    lay = shard_layout(n_log, k, r, h, rank, world)
+    values = O.synthetic_values(k, n, seed=2)
+    # 1. column shard of the inverse transform (zero-padded to kp columns)
+    mine = np.zeros((lay["kp"], n), np.uint64)
+    for i, c in enumerate(range(lay["col_begin"], lay["col_end"])):
+        mine[i] = O.ifft(values[c])
+    # 2. all-gather of coefficients
+    gathered = torch.zeros((world * lay["kp"], n), dtype=torch.int64)
+    dist.all_gather_into_tensor(gathered, torch.from_numpy(mine.view(np.int64)))
+    coeffs = gathered.numpy().view(np.uint64)[:k]
+    # 3. this rank's coset blocks: block b = leaves [b*n, (b+1)*n) = size-n coset NTT in bit-reversed order
+    perm_n = bitrev_perm(n_log)
+    g2 = 1753635133440165772
+    wN = pow(g2, 1 << (32 - n_log - r), O.P)
+    local = np.zeros((lay["N_local"], k), np.uint64)
+    for bi, b in enumerate(range(lay["block_begin"], lay["block_end"])):
+        t = int(format(b, f"0{r}b")[::-1], 2) if r else 0
+        s = 7 * pow(wN, t, O.P) % O.P
+        for c in range(k):
+            scaled = np.array([int(coeffs[c][j]) * pow(s, j, O.P) % O.P for j in range(n)], dtype=np.uint64)
+            local[bi * n:(bi + 1) * n, c] = O.fft(scaled)[perm_n]
+    dig, cap_local = O.merkle_new(local, lay["cap_height_local"])
+    # 4. all-gather of the cap
+    cap = torch.zeros((1 << h, 4), dtype=torch.int64)
+    dist.all_gather_into_tensor(cap, torch.from_numpy(cap_local.view(np.int64)))
+    full = O.commit(values, r, h)
+    ok = bool((cap.numpy().view(np.uint64) == full["cap"]).all())
+    ok &= bool((local == full["leaves"][lay["leaf_begin"]:lay["leaf_end"]]).all())
+    ok &= bool((coeffs == full["coeffs"]).all())
+    sub = 2 * ((N >> h) - 1)
+    ok &= bool((dig == full["digests"][lay["cap_begin"] * sub:lay["cap_end"] * sub]).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_log,k,r,h", [(4, 5, 3, 4), (3, 7, 1, 1)])
+def test_two_rank_partition_reproduces_commitment(n_log, k, r, h):
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(rk, world, port, n_log, k, r, h, q)) for rk in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_shard_layout_covers_everything():
+    from intmax_zkp_core_b200.device import shard_layout
+    for world in (1, 2, 4, 8):
+        lays = [shard_layout(20, 135, 3, 4, g, world) for g in range(world)]
+        assert lays[0]["col_begin"] == 0 and lays[-1]["col_end"] == 135
+        assert all(a["col_end"] == b["col_begin"] for a, b in zip(lays, lays[1:]))
+        assert sum(l["N_local"] for l in lays) == 1 << 23
+        assert [l["block_begin"] for l in lays] == [g * (8 // world) for g in range(world)]
+        assert all(l["cap_end"] - l["cap_begin"] == 16 // world for l in lays)
+    with pytest.raises(ValueError):
+        shard_layout(20, 135, 3, 2, 0, 8)      # more ranks than cap subtrees
+    with pytest.raises(ValueError):
+        shard_layout(20, 135, 3, 4, 0, 3)

@@ -1,0 +1,106 @@
+"""Kernel-body logic on the CPU: tests/emu/emu.cpp compiles the CUDA kernel bodies (csrc/*.cuh) with g++ under
+B200ZKP_HOST_EMU and steps the threads of each CTA in a loop.  This checks the index logic of the NTT passes,
+the Poseidon arithmetic and the digest slot formula against the oracle without a GPU.  It is NOT a product
+path (the library has no CPU mode); the GPU parity tests proper are in test_gpu_*.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import P, bitrev_perm, hostile_columns, rand_field
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+u64p = C.POINTER(C.c_uint64)
+
+
+def ptr(a):
+    return a.ctypes.data_as(u64p)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(HERE, "emu", "libemu.so")
+    src = os.path.join(HERE, "emu", "emu.cpp")
+    csrc = os.path.join(os.path.dirname(HERE), "intmax_zkp_core_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.emu_node_slot.restype = C.c_uint64
+    lib.emu_node_slot.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64]
+    lib.emu_sponge.argtypes = [u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p]
+    return lib
+
+
+def test_permutation_body(emu, oracle):
+    rng = np.random.default_rng(11)
+    states = [np.zeros(12, np.uint64), np.arange(12, dtype=np.uint64), np.full(12, P - 1, np.uint64),
+              np.full(12, 2**64 - 1, np.uint64), np.full(12, P, np.uint64)]
+    states += [rng.integers(0, 2**64, size=12, dtype=np.uint64) for _ in range(40)]
+    for st in states:
+        got = st.copy()
+        emu.emu_permute(ptr(got))
+        assert (got == oracle.permute(st)).all()
+
+
+def test_sponge_body(emu, oracle):
+    rng = np.random.default_rng(12)
+    for L in (0, 1, 3, 4, 5, 7, 8, 9, 12, 16, 17, 20, 135, 139):
+        x = rng.integers(0, 2**64, size=max(L, 1), dtype=np.uint64)
+        out = np.zeros(4, np.uint64)
+        emu.emu_sponge(ptr(x), 1, L, 1, ptr(out))
+        assert (out == oracle.hash_or_noop(x[:L])).all(), L
+        emu.emu_sponge(ptr(x), 1, L, 0, ptr(out))
+        assert (out == oracle.hash_no_pad(x[:L])).all(), L
+    # strided (column-major) leaf
+    m = rng.integers(0, 2**64, size=(20, 6), dtype=np.uint64)
+    out = np.zeros(4, np.uint64)
+    flat = np.ascontiguousarray(m)
+    emu.emu_sponge(C.cast(C.addressof(ptr(flat).contents) + 8 * 2, u64p), 6, 20, 1, ptr(out))
+    assert (out == oracle.hash_or_noop(m[:, 2])).all()
+
+
+def test_digest_slots_match_recursive_layout(emu, oracle):
+    """node_slot (index formula used by the kernels) == where plonky2's recursive fill puts each digest."""
+    rng = np.random.default_rng(13)
+    for (N, h) in ((16, 0), (16, 2), (32, 1), (8, 3)):
+        leaves = rand_field(rng, (N, 6))
+        dig, cap = oracle.merkle_new(leaves, h)
+        sub_log = (N.bit_length() - 1) - h
+        sub = 1 << sub_log
+        for s in range(1 << h):
+            layer = [oracle.hash_or_noop(leaves[s * sub + m]) for m in range(sub)]
+            for i in range(sub_log):
+                for m, d in enumerate(layer):
+                    assert (dig[emu.emu_node_slot(sub_log, s, i, m)] == d).all()
+                layer = [oracle.two_to_one(layer[2 * q], layer[2 * q + 1]) for q in range(len(layer) // 2)]
+            assert (cap[s] == layer[0]).all()
+
+
+@pytest.mark.parametrize("n_log", [0, 1, 2, 3, 4, 6, 8, 9, 11, 12, 16, 17])
+def test_ntt_pass_bodies(emu, oracle, n_log):
+    rng = np.random.default_rng(100 + n_log)
+    k = 3 if n_log < 14 else 1
+    n = 1 << n_log
+    v = rng.integers(0, 2**64, size=(k, n), dtype=np.uint64)       # includes non-canonical inputs
+    out = np.zeros_like(v)
+    emu.emu_ntt(ptr(v), ptr(out), n_log, k)
+    assert (out == np.stack([oracle.fft(c) for c in v])).all()
+    emu.emu_intt(ptr(v), ptr(out), n_log, k)
+    assert (out == np.stack([oracle.ifft(c) for c in v])).all()
+    for r in ((0, 1, 3) if n_log < 12 else (3,)):
+        N = n << r
+        lde = np.zeros((k, N), np.uint64)
+        emu.emu_lde(ptr(v), ptr(lde), n_log, k, r)
+        perm = bitrev_perm(n_log + r)
+        for c in range(k):
+            assert (lde[c] == oracle.coset_lde(v[c], r)[perm]).all()
+
+
+def test_ntt_hostile_columns(emu, oracle):
+    v = hostile_columns(64)
+    out = np.zeros_like(v)
+    emu.emu_intt(ptr(v), ptr(out), 6, v.shape[0])
+    assert (out == np.stack([oracle.ifft(c) for c in v])).all()
