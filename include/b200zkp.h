@@ -152,6 +152,10 @@ int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint
 /* column-major [cols][col_stride] rows [row0,row0+n_rows) -> row-major [n_rows][cols] (device) */
 int b200zkp_dev_transpose_to_rows(b200zkp_ctx* ctx, const uint64_t* cm, uint64_t col_stride, uint32_t cols,
                                   uint64_t row0, uint64_t n_rows, uint64_t* rm);
+/* device field primitives, element-wise over `count` pairs (test probe for the carry / borrow paths):
+ * op 0 mul, 1 add, 2 sub, 3 reduce128(lo = a, hi = b), 4 a + canon(b) lazily, 5 fold (a mod 2^44) + (b mod 2^44) * 2^32,
+ * 6 a^7, 7 (a ^ b) + a * b; every result canonical */
+int b200zkp_field_op(b200zkp_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t count, uint64_t* out);
 /* integer-pipe micro-benchmark: runs `iters` dependent-chain rounds of the chosen
  * instruction mix on every SM and returns giga thread-instructions per second in *out_gips.
  * kind: 0 IMAD.WIDE.U32, 1 IADD3, 2 IMAD (32-bit), 3 alternating IMAD.WIDE/IADD3, 4 LOP3 */

@@ -861,6 +861,43 @@ extern "C" int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint3
     return done(d2h(ctx, out, d_out, big));
 }
 
+// ------------------------------------------------------------------------------------------------ field primitive probe
+// Exposes the device field primitives one by one so tests can hit the rare carry / borrow paths directly.
+__global__ void field_op_kernel(int op, const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, u64 count) {
+    u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= count) return;
+    u64 x = a[g], y = b[g], r = 0;
+    switch (op) {
+        case 0: r = gl::mul(x, y); break;                          // any x any -> canonical
+        case 1: r = gl::add(gl::canon(x), gl::canon(y)); break;    // canonical + canonical
+        case 2: r = gl::sub(gl::canon(x), gl::canon(y)); break;
+        case 3: r = gl::canon(gl::reduce128(x, y)); break;         // (hi = y : lo = x) mod p
+        case 4: r = gl::canon(gl::add_nc(x, gl::canon(y))); break; // arbitrary + canonical
+        case 5: r = gl::canon(poseidon::fold_lh(x & 0xFFFFFFFFFFFull, y & 0xFFFFFFFFFFFull)); break;  // L + H * 2^32, L,H < 2^44
+        case 6: r = gl::canon(poseidon::sbox(x)); break;
+        case 7: r = gl::canon(poseidon::mul_add_nc(x, y, x ^ y)); break;   // (x ^ y) + x * y
+        default: break;
+    }
+    out[g] = r;
+}
+
+extern "C" int b200zkp_field_op(b200zkp_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t count, uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!count) return 0;
+    if (!a || !b || !out || op < 0 || op > 7) BAD(ctx, "bad argument");
+    void* d_b = nullptr;
+    TRY(dev_alloc(ctx, count * 8, &d_b));
+    int rc = h2d(ctx, d_b, b, count * 8);
+    if (!rc) rc = with_io(ctx, a, count * 8, out, count * 8, [&](u64* da, u64* dout) -> int {
+        field_op_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(op, da, (const u64*)d_b, dout, count);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    });
+    dev_release(ctx, d_b, count * 8);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------------ integer-pipe roof
 template <int KIND>
 __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {

@@ -28,8 +28,17 @@ typedef unsigned int u32;
 static constexpr u64 P = 0xFFFFFFFF00000001ull;
 static constexpr u64 EPS = 0xFFFFFFFFull;  // 2^64 mod p
 
-GL_FN u64 canon(u64 a) { return a >= P ? a - P : a; }
+// a >= p  <=>  hi == 0xFFFFFFFF and lo != 0, and then a - p = (0 : lo - 1)
+GL_FN u64 canon(u64 a) {
+    u32 lo = (u32)a, hi = (u32)(a >> 32);
+    bool q = (hi == 0xFFFFFFFFu) & (lo != 0u);
+    lo -= q ? 1u : 0u;
+    hi = q ? 0u : hi;
+    return ((u64)hi << 32) | lo;
+}
 
+#ifdef B200ZKP_HOST_EMU
+// ---- plain C versions (host emulation build of the kernel bodies; same results as the PTX below)
 // a, b canonical -> canonical
 GL_FN u64 add(u64 a, u64 b) {
     u64 s = a + b;
@@ -41,8 +50,6 @@ GL_FN u64 sub(u64 a, u64 b) {
     u64 d = a - b;
     return (a < b) ? d + P : d;
 }
-GL_FN u64 neg(u64 a) { return a ? P - a : 0; }
-
 // (hi:lo) 128-bit -> u64 congruent mod p, NOT necessarily canonical.
 GL_FN u64 reduce128(u64 lo, u64 hi) {
     u32 x2 = (u32)hi, x3 = (u32)(hi >> 32);
@@ -53,6 +60,87 @@ GL_FN u64 reduce128(u64 lo, u64 hi) {
     if (r < t1) r += EPS;                 // carry: +2^64 == +EPS (cannot carry twice)
     return r;
 }
+// a arbitrary u64, c canonical -> arbitrary u64 congruent to a + c
+GL_FN u64 add_nc(u64 a, u64 c) {
+    u64 s = a + c;
+    return (s < a) ? s + EPS : s;         // single wrap: cannot wrap twice because c < p
+}
+#else
+// ---- sm_100a versions: IADD3 carry chains written in PTX.  ptxas fuses `mul.wide.u32 + add.cc.u64` into
+// one IMAD.WIDE.U32 with a carry-out predicate, and `subc 0,0` turns a carry/borrow into a 0 / 0xFFFFFFFF
+// mask without compare+select (16 SASS instructions per modular product instead of 23).
+// (hi:lo) 128-bit -> u64 congruent mod p, NOT necessarily canonical.
+GL_FN u64 reduce128(u64 lo, u64 hi) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 l0, l1, x2, x3, b, m;\n\t"
+        ".reg .u64 t, u;\n\t"
+        "mov.b64 {l0, l1}, %1;\n\t"
+        "mov.b64 {x2, x3}, %2;\n\t"
+        "sub.cc.u32 l0, l0, x3;\n\t"          // lo - x3      (2^96 == -1)
+        "subc.cc.u32 l1, l1, 0;\n\t"
+        "subc.u32 b, 0, 0;\n\t"               // b = 0xFFFFFFFF on borrow
+        "sub.cc.u32 l0, l0, b;\n\t"           // borrow: -2^64 == -EPS
+        "subc.u32 l1, l1, 0;\n\t"
+        "mov.b64 t, {l0, l1};\n\t"
+        "mul.wide.u32 u, x2, 0xFFFFFFFF;\n\t" // x2 * EPS     (2^64 == EPS)
+        "add.cc.u64 t, t, u;\n\t"
+        "addc.u32 m, 0, 0;\n\t"               // m = carry (0/1); NB: subc after add.cc has the wrong polarity
+        "mov.b64 {l0, l1}, t;\n\t"
+        "sub.cc.u32 l0, l0, m;\n\t"           // + m * EPS == + m * 2^32 - m (cannot carry twice)
+        "subc.u32 l1, l1, 0;\n\t"
+        "add.u32 l1, l1, m;\n\t"
+        "mov.b64 %0, {l0, l1};\n\t"
+        "}" : "=l"(r) : "l"(lo), "l"(hi));
+    return r;
+}
+// a arbitrary u64, c canonical -> arbitrary u64 congruent to a + c
+GL_FN u64 add_nc(u64 a, u64 c) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 l0, l1, m;\n\t"
+        ".reg .u64 t;\n\t"
+        "add.cc.u64 t, %1, %2;\n\t"
+        "addc.u32 m, 0, 0;\n\t"               // m = carry (0/1); NB: subc after add.cc has the wrong polarity
+        "mov.b64 {l0, l1}, t;\n\t"
+        "sub.cc.u32 l0, l0, m;\n\t"           // + m * EPS == + m * 2^32 - m (cannot carry twice)
+        "subc.u32 l1, l1, 0;\n\t"
+        "add.u32 l1, l1, m;\n\t"
+        "mov.b64 %0, {l0, l1};\n\t"
+        "}" : "=l"(r) : "l"(a), "l"(c));
+    return r;
+}
+// a canonical, b canonical -> canonical
+GL_FN u64 sub(u64 a, u64 b) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 l0, l1, m;\n\t"
+        ".reg .u64 t;\n\t"
+        "sub.cc.u64 t, %1, %2;\n\t"
+        "subc.u32 m, 0, 0;\n\t"               // 0xFFFFFFFF on borrow: add p == subtract EPS
+        "mov.b64 {l0, l1}, t;\n\t"
+        "sub.cc.u32 l0, l0, m;\n\t"
+        "subc.u32 l1, l1, 0;\n\t"
+        "mov.b64 %0, {l0, l1};\n\t"
+        "}" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// a, b canonical -> canonical:  a + b = a - (p - b)
+GL_FN u64 add(u64 a, u64 b) { return sub(a, P - b); }
+#endif
+GL_FN u64 neg(u64 a) { return a ? P - a : 0; }
+
+// a * b + c with 32-bit a, b and a 64-bit accumulator: exactly one IMAD.WIDE.U32 (fma pipe)
+GL_FN u64 mad_wide(u32 a, u32 b, u64 c) {
+#ifdef B200ZKP_HOST_EMU
+    return (u64)a * b + c;
+#else
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+#endif
+}
+
 // any u64 operands -> congruent u64 (not necessarily canonical)
 GL_FN u64 mul_nc(u64 a, u64 b) {
     unsigned __int128 p = (unsigned __int128)a * b;

@@ -15,6 +15,39 @@ def z():
     return z
 
 
+# ------------------------------------------------------------------------------------------------ field primitives
+def test_field_primitives_edge_cases(z, ctx):
+    """The PTX carry-chain primitives against Python integers, with operands built to take the rare borrow
+    (lo < x3) and carry (t + x2*eps >= 2^64) corrections and the wrap of lazy additions."""
+    import ctypes as C
+    rng = np.random.default_rng(99)
+    M = 2**64
+    special = [0, 1, 2, 2**32 - 1, 2**32, 2**32 + 1, P - 1, P, P + 1, M - 1, M - 2**32, M - 2**32 + 1, 2**63, 2**33 - 1,
+               0xFFFFFFFF00000000, 0x00000000FFFFFFFF, 0xFFFFFFFEFFFFFFFF, 0x0000000100000000]
+    a = np.array([x for x in special for _ in special] + [int(v) for v in rng.integers(0, M, size=4000, dtype=np.uint64)], dtype=np.uint64)
+    b = np.array([y for _ in special for y in special] + [int(v) for v in rng.integers(0, M, size=4000, dtype=np.uint64)], dtype=np.uint64)
+    # half of the random pairs get a tiny low word / huge high word to force borrows in reduce128
+    a[400:2000] &= np.uint64(0xFFFF)
+    b[400:1200] |= np.uint64(0xFFFFFFFF00000000)
+
+    def run(op):
+        out = np.empty_like(a)
+        ctx.check(ctx._lib.b200zkp_field_op(ctx._h, op, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), a.size,
+                                            out.ctypes.data_as(C.c_void_p)))
+        return [int(v) for v in out]
+
+    A, B = [int(v) for v in a], [int(v) for v in b]
+    assert run(0) == [x * y % P for x, y in zip(A, B)]
+    assert run(1) == [(x + y) % P for x, y in zip(A, B)]
+    assert run(2) == [(x - y) % P for x, y in zip(A, B)]
+    assert run(3) == [(x + (y << 64)) % P for x, y in zip(A, B)]
+    assert run(4) == [(x + y) % P for x, y in zip(A, B)]
+    m44 = (1 << 44) - 1
+    assert run(5) == [((x & m44) + ((y & m44) << 32)) % P for x, y in zip(A, B)]
+    assert run(6) == [pow(x, 7, P) for x in A]
+    assert run(7) == [((x ^ y) + x * y) % P for x, y in zip(A, B)]
+
+
 # ------------------------------------------------------------------------------------------------ Poseidon
 def test_permute_matches_oracle(z, ctx, oracle):
     rng = np.random.default_rng(21)
