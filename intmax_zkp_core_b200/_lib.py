@@ -12,7 +12,8 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200zkp.so")
+# B200ZKP_LIB selects an alternative build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("B200ZKP_LIB") or os.path.join(_HERE, "libb200zkp.so")
 SRC = os.path.join(_HERE, "csrc", "b200zkp.cu")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "b200zkp.h")
 

@@ -35,8 +35,13 @@ struct b200zkp_ctx {
     u64 launches = 0;
     u64* wtab[2][9] = {};                               // [dir][B] w_{2^B}^(+-e)
     std::map<u32, TwoLevel> tw[2];                      // [dir][n_log] -> w_n^(+-e)
-    std::map<u64, std::vector<TwoLevel>> coset;         // (n_log<<8 | rate_bits) -> per leaf block
-    std::map<u32, TwoLevel> shift7;                     // N_log -> 7^i (natural-order coset_lde helper)
+    std::map<u64, std::vector<TwoLevel>> coset;         // (n_log<<8 | rate_bits) -> per leaf block (builder input)
+    std::map<u32, TwoLevel> shift7;                     // N_log -> 7^i (natural-order coset_lde helper, builder input)
+    // direct tables read by the pass kernels
+    struct Images { const u64* img[ntt::MAX_PASSES] = {}; };
+    std::map<u64, Images> twimg;                        // (n_log<<8 | dir<<1 | bitrev_out) -> twiddle image per pass
+    std::map<u64, u64*> coset_scale;                    // (n_log<<8 | rate_bits) -> [2^rate_bits][n] shift powers
+    std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
     std::multimap<size_t, void*> pool;                  // cached device allocations
     std::vector<void*> table_allocs;
     // optional per-stage timing (bench.py): CUDA event pairs recorded on the ctx stream
@@ -173,24 +178,25 @@ static int get_coset(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const std::vect
 }
 
 template <int B>
-static void launch_pass_b(const ntt::PassParams& p, u64 blocks, cudaStream_t s) {
-    ntt::ntt_pass_kernel<B><<<(unsigned)blocks, ntt::THREADS, 0, s>>>(p);
+static void launch_pass_b(const ntt::PassParams& p, dim3 grid, cudaStream_t s) {
+    ntt::ntt_pass_kernel<B><<<grid, ntt::THREADS, 0, s>>>(p);
 }
-static int launch_pass(b200zkp_ctx* ctx, const ntt::PassParams& p, u32 B) {
+static int launch_pass(b200zkp_ctx* ctx, const ntt::PassParams& p, u32 B, u32 n_blk) {
     u64 T = ntt::TILE_ELEMS >> B;
     u64 total_batches = (u64)p.ncols << (p.n_log - B);
     u64 blocks = (total_batches + T - 1) / T;
-    if (blocks == 0) return 0;
-    if (blocks > 0x7fffffffull) BAD(ctx, "transform too large for one launch");
+    if (blocks == 0 || n_blk == 0) return 0;
+    if (blocks > 0x7fffffffull || n_blk > 65535) BAD(ctx, "transform too large for one launch");
+    dim3 grid((unsigned)blocks, n_blk);
     switch (B) {
-        case 1: launch_pass_b<1>(p, blocks, ctx->stream); break;
-        case 2: launch_pass_b<2>(p, blocks, ctx->stream); break;
-        case 3: launch_pass_b<3>(p, blocks, ctx->stream); break;
-        case 4: launch_pass_b<4>(p, blocks, ctx->stream); break;
-        case 5: launch_pass_b<5>(p, blocks, ctx->stream); break;
-        case 6: launch_pass_b<6>(p, blocks, ctx->stream); break;
-        case 7: launch_pass_b<7>(p, blocks, ctx->stream); break;
-        case 8: launch_pass_b<8>(p, blocks, ctx->stream); break;
+        case 1: launch_pass_b<1>(p, grid, ctx->stream); break;
+        case 2: launch_pass_b<2>(p, grid, ctx->stream); break;
+        case 3: launch_pass_b<3>(p, grid, ctx->stream); break;
+        case 4: launch_pass_b<4>(p, grid, ctx->stream); break;
+        case 5: launch_pass_b<5>(p, grid, ctx->stream); break;
+        case 6: launch_pass_b<6>(p, grid, ctx->stream); break;
+        case 7: launch_pass_b<7>(p, grid, ctx->stream); break;
+        case 8: launch_pass_b<8>(p, grid, ctx->stream); break;
         default: BAD(ctx, "internal: bad pass width");
     }
     LAUNCH_CHECK(ctx);
@@ -204,31 +210,91 @@ static int launch_canon_copy(b200zkp_ctx* ctx, const u64* src, u64* dst, u64 cou
     return 0;
 }
 
-// One multi-pass transform over `ncols` columns.
+static int table_alloc(b200zkp_ctx* ctx, u64 count, u64** out) {
+    CUDA_TRY(ctx, cudaMalloc((void**)out, count * sizeof(u64)));
+    ctx->table_allocs.push_back(*out);
+    return 0;
+}
+
+// twiddle images of every non-final pass of a 2^n_log transform (built on the device, cached per ctx);
+// the inverse direction carries n^-1 in the first image
+static int get_twiddle_images(b200zkp_ctx* ctx, u32 n_log, int dir, bool bitrev_out, b200zkp_ctx::Images* out) {
+    u64 key = ((u64)n_log << 8) | ((u64)dir << 1) | (bitrev_out ? 1 : 0);
+    auto it = ctx->twimg.find(key);
+    if (it == ctx->twimg.end()) {
+        b200zkp_ctx::Images im;
+        ntt::TwiddleImageShape shapes[ntt::MAX_PASSES];
+        u32 n_img = ntt::twiddle_images(n_log, shapes);
+        if (n_img) {
+            TwoLevel tw{};
+            TRY(get_tw(ctx, dir, n_log, &tw));
+            u64 n_inv = hostgl::inv(((u64)1 << n_log) % hostgl::P);
+            for (u32 pi = 0; pi < n_img; pi++) {
+                u64 count = (u64)1 << (shapes[pi].B + shapes[pi].C_log);
+                u64* d = nullptr;
+                TRY(table_alloc(ctx, count, &d));
+                u64 f = (dir == 1 && pi == 0) ? n_inv : 0;
+                ntt::build_twiddle_image_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+                    d, shapes[pi].B, shapes[pi].C_log, shapes[pi].shift, bitrev_out ? 1u : 0u, f, tw.lo, tw.hi, tw.lo_bits);
+                LAUNCH_CHECK(ctx);
+                im.img[pi] = d;
+            }
+        }
+        it = ctx->twimg.emplace(key, im).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// [2^rate_bits][n] powers of the coset shift of every leaf block
+static int get_coset_scale(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const u64** out) {
+    u64 key = ((u64)n_log << 8) | rate_bits;
+    auto it = ctx->coset_scale.find(key);
+    if (it == ctx->coset_scale.end()) {
+        const std::vector<TwoLevel>* cs;
+        TRY(get_coset(ctx, n_log, rate_bits, &cs));
+        u64 n = (u64)1 << n_log;
+        u64* d = nullptr;
+        TRY(table_alloc(ctx, n << rate_bits, &d));
+        for (u32 b = 0; b < (1u << rate_bits); b++) {
+            ntt::build_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d + (u64)b * n, n, (*cs)[b].lo, (*cs)[b].hi, (*cs)[b].lo_bits);
+            LAUNCH_CHECK(ctx);
+        }
+        it = ctx->coset_scale.emplace(key, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// One multi-pass transform over `ncols` columns, for `n_blk` blocks at once (blockIdx.y: the coset blocks of an
+// LDE share the input and differ in scale table and output offset).
 //   bitrev_out: in-place DIF order (LDE leaf order); else natural order (needs scratch when P > 1)
 static int run_transform(b200zkp_ctx* ctx, const u64* in, u64 in_stride, u64* out, u64 out_stride,
                          u64* scratch, u32 n_log, u32 ncols, int dir, bool bitrev_out,
-                         const TwoLevel* scale, u64 out_scale, bool canon_in) {
+                         const u64* scale, u64 scale_blk_stride, bool inverse_scale, bool canon_in,
+                         u32 n_blk = 1, u64 out_blk_stride = 0) {
     if (ncols == 0) return 0;
     if (n_log == 0) {
         // single point: the transform is the identity (scale^0 = 1)
-        for (u32 c = 0; c < ncols; c++) {
-            // rare path (n = 1): one tiny launch per column keeps strides general
-            TRY(launch_canon_copy(ctx, in + c * in_stride, out + c * out_stride, 1));
-        }
+        for (u32 blk = 0; blk < n_blk; blk++)
+            for (u32 c = 0; c < ncols; c++)   // rare path (n = 1): tiny launches keep strides general
+                TRY(launch_canon_copy(ctx, in + c * in_stride, out + blk * out_blk_stride + c * out_stride, 1));
         return 0;
     }
     if (n_log > 32) BAD(ctx, "n_log exceeds the field's two-adicity (32)");
-    TwoLevel tw{};
-    if (n_log > 8) TRY(get_tw(ctx, dir, n_log, &tw));
     if (!bitrev_out && n_log > 8 && !scratch) BAD(ctx, "scratch buffer required for n_log > 8");
-    ntt::TwoLevelPtr twp{tw.lo, tw.hi, tw.lo_bits};
-    ntt::TwoLevelPtr scp{};
-    if (scale) scp = ntt::TwoLevelPtr{scale->lo, scale->hi, scale->lo_bits};
+    b200zkp_ctx::Images im;
+    TRY(get_twiddle_images(ctx, n_log, dir, bitrev_out, &im));
+    ntt::TransformTables tb{};
+    tb.wtab = ctx->wtab[dir];
+    for (u32 i = 0; i < ntt::MAX_PASSES; i++) tb.twimg[i] = im.img[i];
+    tb.scale = scale;
+    tb.scale_blk_stride = scale_blk_stride;
+    u64 n_inv = hostgl::inv(((u64)1 << n_log) % hostgl::P);
     ntt::Plan plan;
-    ntt::make_plan(&plan, in, in_stride, out, out_stride, scratch, n_log, ncols, ctx->wtab[dir], twp, bitrev_out,
-                   scale ? &scp : nullptr, out_scale, canon_in);
-    for (u32 pi = 0; pi < plan.n_passes; pi++) TRY(launch_pass(ctx, plan.pass[pi], plan.bits[pi]));
+    ntt::make_plan(&plan, in, in_stride, out, out_stride, scratch, n_log, ncols, tb, bitrev_out,
+                   inverse_scale ? n_inv : 0, canon_in, /*in_blk_stride=*/0, out_blk_stride);
+    for (u32 pi = 0; pi < plan.n_passes; pi++) TRY(launch_pass(ctx, plan.pass[pi], plan.bits[pi], n_blk));
     return 0;
 }
 
@@ -331,10 +397,9 @@ extern "C" void b200zkp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 static int dev_intt_locked(b200zkp_ctx* ctx, const u64* values, u64 in_stride, u64* coeffs, u64 out_stride,
                            u64* scratch, u32 n_log, u32 k) {
-    u64 n_inv = hostgl::inv(((u64)1 << n_log) % hostgl::P);
     StageTimer tm(ctx, B200ZKP_STAGE_INTT);
     return run_transform(ctx, values, in_stride, coeffs, out_stride, scratch, n_log, k, /*dir=*/1,
-                         /*bitrev_out=*/false, nullptr, n_log ? n_inv : 0, /*canon_in=*/true);
+                         /*bitrev_out=*/false, nullptr, 0, /*inverse_scale=*/true, /*canon_in=*/true);
 }
 
 extern "C" int b200zkp_dev_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
@@ -349,15 +414,14 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
                           u32 n_log, u32 k, u32 rate_bits, u32 b0, u32 b1) {
     if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "rate_bits / n_log out of range");
     if (b0 > b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
-    const std::vector<TwoLevel>* cs;
-    TRY(get_coset(ctx, n_log, rate_bits, &cs));
+    const u64* cs = nullptr;
+    TRY(get_coset_scale(ctx, n_log, rate_bits, &cs));
     StageTimer tm(ctx, B200ZKP_STAGE_LDE);
-    for (u32 b = b0; b < b1; b++) {
-        u64* dst = lde + ((u64)(b - b0) << n_log);
-        TRY(run_transform(ctx, coeffs, coeff_stride, dst, lde_stride, nullptr, n_log, k, /*dir=*/0,
-                          /*bitrev_out=*/true, &(*cs)[b], 0, /*canon_in=*/true));
-    }
-    return 0;
+    // all coset blocks in one launch per pass (blockIdx.y): block b reads the same coefficients, scales them
+    // by the powers of its shift and writes leaves [(b - b0) * n, (b - b0 + 1) * n) of every column
+    u64 n = (u64)1 << n_log;
+    return run_transform(ctx, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, k, /*dir=*/0, /*bitrev_out=*/true,
+                         cs + (u64)b0 * n, n, /*inverse_scale=*/false, /*canon_in=*/true, b1 - b0, n);
 }
 
 extern "C" int b200zkp_dev_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,
@@ -813,7 +877,7 @@ static int transform_host(b200zkp_ctx* ctx, u64* data, u32 n_log, u32 k, int dir
     if ((rc = h2d(ctx, d, data, bytes))) return done(rc);
     u64 n = (u64)1 << n_log;
     if (dir) rc = dev_intt_locked(ctx, (const u64*)d, n, (u64*)dout, n, (u64*)scratch, n_log, k);
-    else rc = run_transform(ctx, (const u64*)d, n, (u64*)dout, n, (u64*)scratch, n_log, k, 0, false, nullptr, 0, true);
+    else rc = run_transform(ctx, (const u64*)d, n, (u64*)dout, n, (u64*)scratch, n_log, k, 0, false, nullptr, 0, false, true);
     if (rc) return done(rc);
     return done(d2h(ctx, data, dout, bytes));
 }
@@ -839,11 +903,15 @@ extern "C" int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint3
     u32 N_log = n_log + rate_bits;
     if (N_log > 32 || rate_bits > 8) BAD(ctx, "n_log + rate_bits exceeds two-adicity");
     u64 n = (u64)1 << n_log, N = (u64)1 << N_log;
-    auto it = ctx->shift7.find(N_log);
-    if (it == ctx->shift7.end()) {
+    auto it = ctx->shift7_scale.find(N_log);
+    if (it == ctx->shift7_scale.end()) {
         TwoLevel t;
         TRY(make_two_level(ctx, 7, N_log, &t));
-        it = ctx->shift7.emplace(N_log, t).first;
+        u64* d = nullptr;
+        TRY(table_alloc(ctx, N, &d));
+        ntt::build_powers_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d, N, t.lo, t.hi, t.lo_bits);
+        LAUNCH_CHECK(ctx);
+        it = ctx->shift7_scale.emplace(N_log, d).first;
     }
     size_t big = (size_t)k * N * 8;
     void *d_pad = nullptr, *d_scr = nullptr, *d_out = nullptr;
@@ -856,7 +924,7 @@ extern "C" int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint3
     cudaError_t e = cudaMemsetAsync(d_pad, 0, big, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(d_pad, N * 8, coeffs, n * 8, n * 8, k, cudaMemcpyHostToDevice, ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("coset_lde H2D: ") + cudaGetErrorString(e); return done(B200ZKP_ERR_CUDA); }
-    rc = run_transform(ctx, (const u64*)d_pad, N, (u64*)d_out, N, (u64*)d_scr, N_log, k, 0, false, &it->second, 0, true);
+    rc = run_transform(ctx, (const u64*)d_pad, N, (u64*)d_out, N, (u64*)d_scr, N_log, k, 0, false, it->second, 0, false, true);
     if (rc) return done(rc);
     return done(d2h(ctx, out, d_out, big));
 }
@@ -899,69 +967,56 @@ extern "C" int b200zkp_field_op(b200zkp_ctx* ctx, int op, const uint64_t* a, con
 }
 
 // ------------------------------------------------------------------------------------------------ integer-pipe roof
+// Every instruction consumes a value produced inside the loop, so ptxas cannot hoist or strength-reduce it
+// (a multiply by loop-invariant operands is hoisted and the "IMAD.WIDE" chain degenerates into 64-bit adds).
 template <int KIND>
 __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
     u32 a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 77u;
-    u64 w0 = a, w1 = b, w2 = a ^ b, w3 = a + b, w4 = a * 3u, w5 = b * 5u, w6 = a - b, w7 = ~a;
-    u32 x0 = a, x1 = b, x2 = a ^ b, x3 = a + b, x4 = a * 3u, x5 = b * 5u, x6 = a - b, x7 = ~a;
+    u64 w[8];
+    u32 x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[i] = ((u64)(a + i) << 32) | (b * (i + 3)); x[i] = a * (2 * i + 1) + b; }
     for (u32 it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            if (KIND == 0 || KIND == 3) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w0) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w1) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w2) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w3) : "r"(a), "r"(b));
-            }
-            if (KIND == 0) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w4) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w5) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w6) : "r"(a), "r"(b));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w7) : "r"(a), "r"(b));
-            }
-            if (KIND == 1 || KIND == 3) {
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x0) : "r"(a));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x1) : "r"(b));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x2) : "r"(a));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x3) : "r"(b));
-            }
-            if (KIND == 1) {
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x4) : "r"(a));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x5) : "r"(b));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x6) : "r"(a));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x7) : "r"(b));
-            }
-            if (KIND == 2) {
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x0) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x1) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x2) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x3) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x4) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x5) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x6) : "r"(a), "r"(b));
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x7) : "r"(a), "r"(b));
-            }
-            if (KIND == 4) {
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x0) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x1) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x2) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x3) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x4) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x5) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x6) : "r"(a), "r"(b));
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x7) : "r"(a), "r"(b));
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int j = (i + 1) & 7;
+                if (KIND == 0) {          // IMAD.WIDE.U32 with a 64-bit accumulator, multiplicand from another chain
+                    asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[i]) : "l"(w[j]), "r"(b));
+                } else if (KIND == 1) {   // IADD3
+                    asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(x[j]));
+                } else if (KIND == 2) {   // IMAD (32-bit)
+                    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                } else if (KIND == 3) {   // alternating IMAD.WIDE / LOP3 (fma pipe + alu pipe)
+                    if (i & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                    else asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[i]) : "l"(w[(i + 2) & 7]), "r"(b));
+                } else if (KIND == 4) {   // LOP3
+                    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                } else if (KIND == 5) {   // IMAD.HI.U32
+                    asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(x[j]));
+                } else if (KIND == 6) {   // alternating IMAD (32-bit) / LOP3
+                    if (i & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                    else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
+                } else if (KIND == 7) {   // add with carry chain (IADD3 + IADD3.X)
+                    asm volatile("{ add.cc.u32 %0, %0, %1; addc.u32 %0, %0, %2; }" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                } else {                  // KIND 8: IMAD.WIDE.U32 without an accumulator (32x32 -> 64, addend RZ)
+                    asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mul.wide.u32 %0, lo, hi; }" : "=l"(w[i]) : "l"(w[j]));
+                }
             }
         }
     }
-    u64 w = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
-    u32 x = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7 ^ (u32)w ^ (u32)(w >> 32);
-    if (x == 0xdeadbeefu && iters == 0xffffffffu) *sink = x;   // keep the chains alive
+    u64 ww = 0; u32 xx = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { ww ^= w[i]; xx ^= x[i]; }
+    xx ^= (u32)ww ^ (u32)(ww >> 32);
+    if (xx == 0xdeadbeefu && iters == 0xffffffffu) *sink = xx;   // keep the chains alive
 }
 
 extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips) {
     if (!ctx) return B200ZKP_ERR_BAD_ARG;
     Guard g(ctx);
-    if (!out_gips || kind < 0 || kind > 4) BAD(ctx, "bad argument");
+    if (!out_gips || kind < 0 || kind > 8) BAD(ctx, "bad argument");
     int sms = 0;
     CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     u32* sink = nullptr;
@@ -976,7 +1031,11 @@ extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters
             case 1: int_pipe_kernel<1><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
             case 2: int_pipe_kernel<2><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
             case 3: int_pipe_kernel<3><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
-            default: int_pipe_kernel<4><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 4: int_pipe_kernel<4><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 5: int_pipe_kernel<5><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 6: int_pipe_kernel<6><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 7: int_pipe_kernel<7><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            default: int_pipe_kernel<8><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
         }
         ctx->launches++;
     };
@@ -989,7 +1048,7 @@ extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     dev_release(ctx, sink, 8);
-    double instr = (double)blocks * 256.0 * (double)iters * 64.0;   // 8 rounds x 8 instructions per iteration
+    double instr = (double)blocks * 256.0 * (double)iters * 64.0 * (kind == 7 ? 2.0 : 1.0);   // 8 rounds x 8 instructions (x2 for the carry pair)
     *out_gips = instr / (ms * 1e-3) / 1e9;
     return 0;
 }

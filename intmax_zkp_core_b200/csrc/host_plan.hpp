@@ -54,12 +54,6 @@ static inline u64 coset_shift_of_block(u32 n_log, u32 rate_bits, u32 b) {
 
 namespace ntt {
 
-struct TwoLevelPtr {
-    const u64* lo;
-    const u64* hi;
-    u32 lo_bits;
-};
-
 struct Plan {
     u32 n_passes;
     u32 bits[MAX_PASSES];
@@ -73,11 +67,32 @@ static inline void split_passes(u32 n_log, u32* bits, u32* n_passes) {
     for (u32 i = 0; i < P; i++) bits[i] = n_log / P + (i < n_log % P ? 1 : 0);
 }
 
-// wtab[B] = small_root_table(B, dir) on the device; tw = two-level powers of w_n^(+-1) (needed when P > 1)
+// What a transform needs from the caller's table cache.
+struct TransformTables {
+    u64* const* wtab;          // [B] -> small_root_table(B, dir) on the device
+    const u64* twimg[MAX_PASSES];   // per non-final pass: twiddle image (nullptr for the final pass)
+    const u64* scale;          // optional [n_blk][n] input scaling tables (coset shift powers)
+    u64 scale_blk_stride;
+};
+
+// geometry of the twiddle image of pass `pi`: entries = 2^(B + C_log), exponent shift = n_log - B - C_log
+struct TwiddleImageShape { u32 B, C_log, shift; };
+static inline u32 twiddle_images(u32 n_log, TwiddleImageShape* shapes) {
+    u32 bits[MAX_PASSES], P;
+    split_passes(n_log, bits, &P);
+    u32 consumed = 0;
+    for (u32 pi = 0; pi + 1 < P; pi++) {
+        consumed += bits[pi];
+        shapes[pi] = TwiddleImageShape{bits[pi], n_log - consumed, consumed - bits[pi]};
+    }
+    return P ? P - 1 : 0;
+}
+
 //   bitrev_out: every pass in place in `out` (DIF order); else natural order through `scratch`
+//   out_scale (n^-1 of an inverse transform) must already be folded into twimg[0] when P > 1
 static inline void make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch,
-                             u32 n_log, u32 ncols, u64* const* wtab, TwoLevelPtr tw, bool bitrev_out,
-                             const TwoLevelPtr* scale, u64 out_scale, bool canon_in) {
+                             u32 n_log, u32 ncols, const TransformTables& tb, bool bitrev_out, u64 out_scale,
+                             bool canon_in, u64 in_blk_stride, u64 out_blk_stride) {
     u32 P;
     split_passes(n_log, plan->bits, &P);
     plan->n_passes = P;
@@ -89,16 +104,16 @@ static inline void make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
         p.ncols = ncols;
         p.n_log = n_log;
         p.C_log = n_log - consumed;
-        p.wtab = wtab[B];
+        p.wtab = tb.wtab[B];
         bool last = (pi + 1 == P);
         if (pi == 0) {
-            p.in = in; p.in_col_stride = in_stride;
+            p.in = in; p.in_col_stride = in_stride; p.in_blk_stride = in_blk_stride;
             p.canon_in = canon_in;
-            if (scale) { p.sc_lo = scale->lo; p.sc_hi = scale->hi; p.sc_lo_bits = scale->lo_bits; }
+            p.scale = tb.scale; p.scale_blk_stride = tb.scale_blk_stride;
         }
         if (bitrev_out) {
-            if (pi > 0) { p.in = out; p.in_col_stride = out_stride; }
-            p.out = out; p.out_col_stride = out_stride;
+            if (pi > 0) { p.in = out; p.in_col_stride = out_stride; p.in_blk_stride = out_blk_stride; }
+            p.out = out; p.out_col_stride = out_stride; p.out_blk_stride = out_blk_stride;
             p.out_mode = OUT_INPLACE_BITREV;
         } else {
             if (pi > 0) { p.in = scratch; p.in_col_stride = (u64)1 << n_log; }
@@ -112,8 +127,8 @@ static inline void make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
                 p.out_mode = OUT_INPLACE_NATURAL;
             }
         }
-        if (!last) { p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_lo_bits = tw.lo_bits; }
-        if (last) p.out_scale = out_scale;
+        if (!last) p.twimg = tb.twimg[pi];
+        if (last && P == 1) p.out_scale = out_scale;
         plan->pass[pi] = p;
     }
 }

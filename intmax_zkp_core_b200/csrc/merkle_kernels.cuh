@@ -16,6 +16,10 @@
 #pragma once
 #include "poseidon.cuh"
 
+#ifndef B200ZKP_HASH_MINBLOCKS
+#define B200ZKP_HASH_MINBLOCKS 4
+#endif
+
 namespace merkle {
 
 using gl::u32;
@@ -68,7 +72,7 @@ __device__ __forceinline__ void store_digest(u64* dst, const u64 (&s)[poseidon::
 }
 
 // hash_or_noop over one leaf per thread.  leaf element (row, c) = leaves[row*row_stride + c*col_stride].
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, B200ZKP_HASH_MINBLOCKS)
 leaf_hash_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len,
                  u64 n_leaves, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap,
                  u32 noop_short /* 1: hash_or_noop, 0: hash_no_pad */) {
@@ -86,7 +90,7 @@ leaf_hash_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride,
 }
 
 // parents of layer `layer` (children) -> layer+1, or the cap when layer+1 == sub_log.
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, B200ZKP_HASH_MINBLOCKS)
 merkle_level_kernel(u64* __restrict__ digests, u64* __restrict__ cap, TreeShape shape, u32 layer,
                     u64 n_parents) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;

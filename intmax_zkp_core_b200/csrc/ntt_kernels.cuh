@@ -40,20 +40,19 @@ struct PassParams {
     const u64* in;
     u64* out;
     u64 in_col_stride, out_col_stride;
+    u64 in_blk_stride, out_blk_stride;   // element offsets per blockIdx.y (coset block of an LDE)
     u32 ncols;
     u32 n_log;     // log2 of the column transform size
     u32 C_log;     // log2 of the inner (contiguous) extent below this pass's dimension
     u32 out_mode;
-    const u64* wtab;   // w_{2^B}^e for e < 2^(B-1), direction specific
-    const u64* sc_lo;  // optional input scaling s^i = sc_hi[i >> sc_lo_bits] * sc_lo[i & mask]
-    const u64* sc_hi;
-    u32 sc_lo_bits;
-    const u64* tw_lo;  // optional inter-pass twiddle w_n^e = tw_hi[e >> tw_lo_bits] * tw_lo[e & mask]
-    const u64* tw_hi;
-    u32 tw_lo_bits;
-    u64 out_scale;     // 0: none; else multiply every output (n^-1 of the inverse transform)
-    u32 canon_in;      // inputs may be non-canonical
-    u32 n_digits;      // OUT_FINAL_NATURAL: bit widths of the earlier passes, first pass first
+    const u64* wtab;    // w_{2^B}^e for e < 2^(B-1), direction specific
+    const u64* scale;   // optional input scaling, direct table [blk][n]: scale[blk*scale_blk_stride + i] (coset shift^i)
+    u64 scale_blk_stride;
+    const u64* twimg;   // optional inter-pass twiddle image, 2^(B+C_log) entries laid out like the output block:
+                        // twimg[pos*C + c] = w_M^(c*k1) (k1 = pos, or bitrev(pos) for OUT_INPLACE_BITREV)
+    u64 out_scale;      // 0: none; else multiply every output (n^-1 of a single-pass inverse transform)
+    u32 canon_in;       // inputs may be non-canonical
+    u32 n_digits;       // OUT_FINAL_NATURAL: bit widths of the earlier passes, first pass first
     u32 digits[MAX_PASSES];
 };
 
@@ -121,50 +120,99 @@ GL_FN u64 two_level(const u64* __restrict__ lo, const u64* __restrict__ hi, u32 
 // batch index beta' = d1 + 2^B1 * (d2 + 2^B2 * ...)
 GL_FN u64 digit_reverse(u64 beta_nat, const PassParams& p) {
     u64 pos = 0;
-    for (u32 i = 0; i < p.n_digits; i++) {
-        u32 w = p.digits[i];
-        pos = (pos << w) | (beta_nat & (((u64)1 << w) - 1));
-        beta_nat >>= w;
+#pragma unroll
+    for (u32 i = 0; i < (u32)MAX_PASSES; i++) {   // static indices keep the parameter block out of local memory
+        if (i < p.n_digits) {
+            u32 w = p.digits[i];
+            pos = (pos << w) | (beta_nat & (((u64)1 << w) - 1));
+            beta_nat >>= w;
+        }
     }
     return pos;
 }
 
-// B = bits of this pass (1..8, compile time so the rounds fully unroll); block = CTA index
+// B = bits of this pass (1..8, compile time so the rounds fully unroll); block = CTA index, blk = coset block
 template <int B>
-GL_FN void pass_body(const PassParams& p, u32 block) {
+GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
     constexpr u32 T = TILE_ELEMS >> B;
     constexpr u32 TP = T + 1;
     constexpr u32 NPTS = 1u << B;
+    constexpr u32 IT = TILE_ELEMS / THREADS;             // elements per thread
+    constexpr bool kOwnBatch = (T <= (u32)THREADS);      // strided tiles: a thread keeps one batch for all its elements
+    constexpr u32 GSTEP = kOwnBatch ? (THREADS / T) : 1; // row step between a thread's consecutive elements
     NTT_SHARED u64 tile[NPTS * TP];
     NTT_SHARED u64 wt[(NPTS / 2) ? (NPTS / 2) : 1];
 
     const u32 batches_log = p.n_log - B;                 // batches per column
     const u64 total_batches = (u64)p.ncols << batches_log;
+    const u64 batch_mask = ((u64)1 << batches_log) - 1;
     const u64 tile_b0 = (u64)block * T;
     const bool final_pass = (p.C_log == 0);
-    const u64 C_mask = ((u64)1 << p.C_log) - 1;
+    const u32 C_mask = (u32)(((u64)1 << p.C_log) - 1);
+    const u64* __restrict__ in = p.in + (u64)blk * p.in_blk_stride;
+    u64* __restrict__ out = p.out + (u64)blk * p.out_blk_stride;
+    const u64* __restrict__ scale = p.scale ? p.scale + (u64)blk * p.scale_blk_stride : nullptr;
 
-    // ---- load
+    // ---- load (all of a thread's loads are issued before the first use)
     NTT_FOR_THREADS(tid) {
         for (u32 i = tid; i < NPTS / 2; i += THREADS) wt[i] = p.wtab[i];
-        for (u32 idx = tid; idx < (u32)TILE_ELEMS; idx += THREADS) {
-            u32 b, g;
-            if (final_pass) { b = idx >> B; g = idx & (NPTS - 1); }
-            else { b = idx % T; g = idx / T; }
-            u64 bg = tile_b0 + b;
-            u64 v = 0;
-            if (bg < total_batches) {
+        u64 v[IT];
+        u32 sm[IT];
+        if (!final_pass && kOwnBatch) {
+            const u32 b = tid % T, g0 = tid / T;
+            const u64 bg = tile_b0 + b;
+            const bool valid = bg < total_batches;
+            u64 base = 0;
+            u32 icol0 = 0;
+            if (valid) {
                 u64 col = bg >> batches_log;
-                u64 beta = bg & (((u64)1 << batches_log) - 1);
-                if (p.out_mode == OUT_FINAL_NATURAL) beta = digit_reverse(beta, p);
-                u64 a = beta >> p.C_log, c = beta & C_mask;
-                u64 i_col = (a << (B + p.C_log)) + ((u64)g << p.C_log) + c;
-                v = p.in[col * p.in_col_stride + i_col];
-                if (p.canon_in) v = gl::canon(v);
-                if (p.sc_lo) v = gl::mul(v, two_level(p.sc_lo, p.sc_hi, p.sc_lo_bits, i_col));
+                u32 beta = (u32)(bg & batch_mask);
+                u32 a = beta >> p.C_log, c = beta & C_mask;
+                icol0 = (a << (B + p.C_log)) + c;
+                base = col * p.in_col_stride + icol0;
             }
-            tile[g * TP + b] = v;
+#pragma unroll
+            for (u32 it = 0; it < IT; it++) {
+                u32 g = g0 + it * GSTEP;
+                sm[it] = g * TP + b;
+                v[it] = valid ? in[base + ((u64)g << p.C_log)] : 0;
+            }
+            if (scale && valid) {
+                u64 f[IT];
+#pragma unroll
+                for (u32 it = 0; it < IT; it++) f[it] = scale[icol0 + ((g0 + it * GSTEP) << p.C_log)];
+#pragma unroll
+                for (u32 it = 0; it < IT; it++) v[it] = gl::mul(p.canon_in ? gl::canon(v[it]) : v[it], f[it]);
+            } else if (p.canon_in) {
+#pragma unroll
+                for (u32 it = 0; it < IT; it++) v[it] = gl::canon(v[it]);
+            }
+        } else {
+            // contiguous tiles of the final pass (and the generic path of very small transforms)
+#pragma unroll
+            for (u32 it = 0; it < IT; it++) {
+                u32 idx = tid + it * THREADS;
+                u32 b, g;
+                if (final_pass) { b = idx >> B; g = idx & (NPTS - 1); }
+                else { b = idx % T; g = idx / T; }
+                sm[it] = g * TP + b;
+                u64 bg = tile_b0 + b;
+                u64 x = 0;
+                if (bg < total_batches) {
+                    u64 col = bg >> batches_log;
+                    u64 beta = bg & batch_mask;
+                    if (p.out_mode == OUT_FINAL_NATURAL) beta = digit_reverse(beta, p);
+                    u64 a = beta >> p.C_log, c = beta & C_mask;
+                    u64 i_col = (a << (B + p.C_log)) + ((u64)g << p.C_log) + c;
+                    x = in[col * p.in_col_stride + i_col];
+                    if (p.canon_in) x = gl::canon(x);
+                    if (scale) x = gl::mul(x, scale[i_col]);
+                }
+                v[it] = x;
+            }
         }
+#pragma unroll
+        for (u32 it = 0; it < IT; it++) tile[sm[it]] = v[it];
     }
     NTT_SYNC();
 
@@ -183,39 +231,103 @@ GL_FN void pass_body(const PassParams& p, u32 block) {
 
     // ---- twiddle + store
     NTT_FOR_THREADS(tid) {
-        for (u32 idx = tid; idx < (u32)TILE_ELEMS; idx += THREADS) {
-            u32 b, row;   // row = k1 (natural modes) or g~ (bit-reversed mode)
-            if (final_pass && p.out_mode == OUT_INPLACE_BITREV) { b = idx >> B; row = idx & (NPTS - 1); }
-            else { b = idx % T; row = idx / T; }
-            u64 bg = tile_b0 + b;
-            if (bg >= total_batches) continue;
-            u32 gt, k1;
-            if (p.out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
-            else { k1 = row; gt = bitrev(row, B); }
-            u64 v = tile[gt * TP + b];
-            u64 col = bg >> batches_log;
-            u64 beta = bg & (((u64)1 << batches_log) - 1);
-            u64 o_col;
-            if (p.out_mode == OUT_FINAL_NATURAL) {
-                o_col = beta + ((u64)k1 << batches_log);
-            } else {
-                u64 a = beta >> p.C_log, c = beta & C_mask;
-                u32 pos = (p.out_mode == OUT_INPLACE_BITREV) ? gt : k1;
-                o_col = (a << (B + p.C_log)) + ((u64)pos << p.C_log) + c;
-                if (p.tw_lo) {
-                    u64 e = (c * k1) << (p.n_log - B - p.C_log);
-                    v = gl::mul(v, two_level(p.tw_lo, p.tw_hi, p.tw_lo_bits, e));
+        const bool contiguous = final_pass && p.out_mode == OUT_INPLACE_BITREV;
+        if (!contiguous && kOwnBatch) {
+            // row = k1 (natural modes) or g~ (bit-reversed mode); the thread keeps batch b
+            const u32 b = tid % T, r0 = tid / T;
+            const u64 bg = tile_b0 + b;
+            if (bg < total_batches) {
+                u64 col = bg >> batches_log;
+                u32 beta = (u32)(bg & batch_mask);
+                u64 v[IT];
+                u32 pos[IT], kk[IT];
+#pragma unroll
+                for (u32 it = 0; it < IT; it++) {
+                    u32 row = r0 + it * GSTEP;
+                    u32 gt, k1;
+                    if (p.out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
+                    else { k1 = row; gt = bitrev(row, B); }
+                    v[it] = tile[gt * TP + b];
+                    pos[it] = (p.out_mode == OUT_INPLACE_BITREV) ? gt : k1;
+                    kk[it] = k1;
+                }
+                if (p.out_mode == OUT_FINAL_NATURAL) {
+                    u64 obase = col * p.out_col_stride + beta;
+#pragma unroll
+                    for (u32 it = 0; it < IT; it++) {
+                        u64 x = p.out_scale ? gl::mul(v[it], p.out_scale) : v[it];
+                        out[obase + ((u64)kk[it] << batches_log)] = x;
+                    }
+                } else {
+                    u32 a = beta >> p.C_log, c = beta & C_mask;
+                    u64 obase = col * p.out_col_stride + ((u64)a << (B + p.C_log)) + c;
+                    if (p.twimg) {
+                        u64 f[IT];
+#pragma unroll
+                        for (u32 it = 0; it < IT; it++) f[it] = gl::ldg(p.twimg + ((u64)pos[it] << p.C_log) + c);
+#pragma unroll
+                        for (u32 it = 0; it < IT; it++) v[it] = gl::mul(v[it], f[it]);
+                    }
+#pragma unroll
+                    for (u32 it = 0; it < IT; it++) {
+                        u64 x = p.out_scale ? gl::mul(v[it], p.out_scale) : v[it];
+                        out[obase + ((u64)pos[it] << p.C_log)] = x;
+                    }
                 }
             }
-            if (p.out_scale) v = gl::mul(v, p.out_scale);
-            p.out[col * p.out_col_stride + o_col] = v;
+        } else {
+#pragma unroll
+            for (u32 it = 0; it < IT; it++) {
+                u32 idx = tid + it * THREADS;
+                u32 b, row;
+                if (contiguous) { b = idx >> B; row = idx & (NPTS - 1); }
+                else { b = idx % T; row = idx / T; }
+                u64 bg = tile_b0 + b;
+                if (bg >= total_batches) continue;
+                u32 gt, k1;
+                if (p.out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
+                else { k1 = row; gt = bitrev(row, B); }
+                u64 x = tile[gt * TP + b];
+                u64 col = bg >> batches_log;
+                u64 beta = bg & batch_mask;
+                u64 o_col;
+                if (p.out_mode == OUT_FINAL_NATURAL) {
+                    o_col = beta + ((u64)k1 << batches_log);
+                } else {
+                    u64 a = beta >> p.C_log, c = beta & C_mask;
+                    u32 pos = (p.out_mode == OUT_INPLACE_BITREV) ? gt : k1;
+                    o_col = (a << (B + p.C_log)) + ((u64)pos << p.C_log) + c;
+                    if (p.twimg) x = gl::mul(x, gl::ldg(p.twimg + ((u64)pos << p.C_log) + c));
+                }
+                if (p.out_scale) x = gl::mul(x, p.out_scale);
+                out[col * p.out_col_stride + o_col] = x;
+            }
         }
     }
 }
 
 #ifndef B200ZKP_HOST_EMU
 template <int B>
-__global__ void __launch_bounds__(THREADS) ntt_pass_kernel(PassParams p) { pass_body<B>(p, blockIdx.x); }
+__global__ void __launch_bounds__(THREADS) ntt_pass_kernel(PassParams p) { pass_body<B>(p, blockIdx.x, blockIdx.y); }
+
+// table builders (run once per (n_log, direction, rate_bits) and cached by the context)
+// out[i] = base^i for i < count, from the two-level power tables of `base`
+__global__ void build_powers_kernel(u64* __restrict__ out, u64 count, const u64* __restrict__ lo, const u64* __restrict__ hi,
+                                    u32 lo_bits) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = two_level(lo, hi, lo_bits, i);
+}
+// out[pos*C + c] = f * w_n^((c * k1) << shift), k1 = pos or bitrev(pos, B); (lo, hi) are the two-level powers of w_n
+__global__ void build_twiddle_image_kernel(u64* __restrict__ out, u32 B, u32 C_log, u32 shift, u32 bitrev_pos, u64 f,
+                                           const u64* __restrict__ lo, const u64* __restrict__ hi, u32 lo_bits) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((u64)1 << (B + C_log))) return;
+    u32 pos = (u32)(i >> C_log);
+    u64 c = i & (((u64)1 << C_log) - 1);
+    u32 k1 = bitrev_pos ? bitrev(pos, B) : pos;
+    u64 w = two_level(lo, hi, lo_bits, (c * k1) << shift);
+    out[i] = f ? gl::mul(w, f) : w;
+}
 
 // dst[c][bitrev(i)] = canon(src[c][i]) : salt columns enter the leaves in bit-reversed row order (A4/A5)
 __global__ void bitrev_copy_kernel(const u64* __restrict__ src, u64* __restrict__ dst, u32 n_log, u32 ncols,

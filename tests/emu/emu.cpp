@@ -13,22 +13,23 @@
 using gl::u32;
 using gl::u64;
 
-static void run_pass(const ntt::PassParams& p, u32 B) {
+static void run_pass(const ntt::PassParams& p, u32 B, u32 n_blk) {
     u64 T = ntt::TILE_ELEMS >> B;
     u64 total_batches = (u64)p.ncols << (p.n_log - B);
     u64 blocks = (total_batches + T - 1) / T;
-    for (u64 blk = 0; blk < blocks; blk++) {
-        switch (B) {
-            case 1: ntt::pass_body<1>(p, (u32)blk); break;
-            case 2: ntt::pass_body<2>(p, (u32)blk); break;
-            case 3: ntt::pass_body<3>(p, (u32)blk); break;
-            case 4: ntt::pass_body<4>(p, (u32)blk); break;
-            case 5: ntt::pass_body<5>(p, (u32)blk); break;
-            case 6: ntt::pass_body<6>(p, (u32)blk); break;
-            case 7: ntt::pass_body<7>(p, (u32)blk); break;
-            case 8: ntt::pass_body<8>(p, (u32)blk); break;
+    for (u32 y = 0; y < n_blk; y++)
+        for (u64 blk = 0; blk < blocks; blk++) {
+            switch (B) {
+                case 1: ntt::pass_body<1>(p, (u32)blk, y); break;
+                case 2: ntt::pass_body<2>(p, (u32)blk, y); break;
+                case 3: ntt::pass_body<3>(p, (u32)blk, y); break;
+                case 4: ntt::pass_body<4>(p, (u32)blk, y); break;
+                case 5: ntt::pass_body<5>(p, (u32)blk, y); break;
+                case 6: ntt::pass_body<6>(p, (u32)blk, y); break;
+                case 7: ntt::pass_body<7>(p, (u32)blk, y); break;
+                case 8: ntt::pass_body<8>(p, (u32)blk, y); break;
+            }
         }
-    }
 }
 
 struct Tables {
@@ -37,21 +38,58 @@ struct Tables {
 };
 static Tables g_tab;
 
-static void transform(const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch, u32 n_log, u32 ncols,
-                      int dir, bool bitrev_out, bool has_scale, u64 scale_base, u64 out_scale) {
-    if (n_log == 0) { for (u32 c = 0; c < ncols; c++) out[c * out_stride] = gl::canon(in[c * in_stride]); return; }
-    u64* wt[9];
-    for (u32 B = 0; B <= 8; B++) wt[B] = B ? g_tab.w[dir][B].data() : nullptr;
-    std::vector<u64> tlo, thi, slo, shi;
+// host replicas of the device table builders (build_twiddle_image_kernel / build_powers_kernel)
+static std::vector<u64> twiddle_image(u32 n_log, int dir, bool bitrev_pos, const ntt::TwiddleImageShape& sh, u64 f) {
     u64 w = hostgl::root(n_log);
     if (dir) w = hostgl::inv(w);
-    ntt::TwoLevelPtr tw{nullptr, nullptr, 0}, sc{nullptr, nullptr, 0};
-    tw.lo_bits = hostgl::two_level_powers(w, n_log, &tlo, &thi); tw.lo = tlo.data(); tw.hi = thi.data();
-    if (has_scale) { sc.lo_bits = hostgl::two_level_powers(scale_base, n_log, &slo, &shi); sc.lo = slo.data(); sc.hi = shi.data(); }
+    u64 count = (u64)1 << (sh.B + sh.C_log);
+    std::vector<u64> img(count);
+    for (u64 i = 0; i < count; i++) {
+        u32 pos = (u32)(i >> sh.C_log);
+        u64 c = i & (((u64)1 << sh.C_log) - 1);
+        u32 k1 = bitrev_pos ? hostgl::bitrev(pos, sh.B) : pos;
+        u64 t = hostgl::pw(w, (c * k1) << sh.shift);
+        img[i] = f ? hostgl::mul(t, f) : t;
+    }
+    return img;
+}
+
+// scale_bases: one shift per block (nullptr: no scaling)
+static void transform(const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch, u32 n_log, u32 ncols,
+                      int dir, bool bitrev_out, const std::vector<u64>* scale_bases, bool inverse_scale,
+                      u32 n_blk = 1, u64 out_blk_stride = 0) {
+    if (n_log == 0) {
+        for (u32 y = 0; y < n_blk; y++)
+            for (u32 c = 0; c < ncols; c++) out[y * out_blk_stride + c * out_stride] = gl::canon(in[c * in_stride]);
+        return;
+    }
+    u64 n = (u64)1 << n_log;
+    u64* wt[9];
+    for (u32 B = 0; B <= 8; B++) wt[B] = B ? g_tab.w[dir][B].data() : nullptr;
+    ntt::TwiddleImageShape shapes[ntt::MAX_PASSES];
+    u32 n_img = ntt::twiddle_images(n_log, shapes);
+    u64 n_inv = hostgl::inv(n % hostgl::P);
+    std::vector<std::vector<u64>> imgs(n_img);
+    ntt::TransformTables tb{};
+    tb.wtab = wt;
+    for (u32 i = 0; i < n_img; i++) {
+        imgs[i] = twiddle_image(n_log, dir, bitrev_out, shapes[i], (dir == 1 && i == 0) ? n_inv : 0);
+        tb.twimg[i] = imgs[i].data();
+    }
+    std::vector<u64> sc;
+    if (scale_bases) {
+        sc.resize((size_t)n * scale_bases->size());
+        for (size_t y = 0; y < scale_bases->size(); y++) {
+            u64 x = 1;
+            for (u64 i = 0; i < n; i++) { sc[y * n + i] = x; x = hostgl::mul(x, (*scale_bases)[y]); }
+        }
+        tb.scale = sc.data();
+        tb.scale_blk_stride = n;
+    }
     ntt::Plan plan;
-    ntt::make_plan(&plan, in, in_stride, out, out_stride, scratch, n_log, ncols, wt, tw, bitrev_out,
-                   has_scale ? &sc : nullptr, out_scale, true);
-    for (u32 pi = 0; pi < plan.n_passes; pi++) run_pass(plan.pass[pi], plan.bits[pi]);
+    ntt::make_plan(&plan, in, in_stride, out, out_stride, scratch, n_log, ncols, tb, bitrev_out,
+                   inverse_scale ? n_inv : 0, true, 0, out_blk_stride);
+    for (u32 pi = 0; pi < plan.n_passes; pi++) run_pass(plan.pass[pi], plan.bits[pi], n_blk);
 }
 
 extern "C" {
@@ -69,19 +107,19 @@ u64 emu_node_slot(u32 sub_log, u64 subtree, u32 layer, u64 m) {
 void emu_intt(const u64* in, u64* out, u32 n_log, u32 k) {
     u64 n = (u64)1 << n_log;
     std::vector<u64> scratch((size_t)k * n);
-    u64 n_inv = hostgl::inv(n % hostgl::P);
-    transform(in, n, out, n, scratch.data(), n_log, k, 1, false, false, 0, n_log ? n_inv : 0);
+    transform(in, n, out, n, scratch.data(), n_log, k, 1, false, nullptr, true);
 }
 void emu_ntt(const u64* in, u64* out, u32 n_log, u32 k) {
     u64 n = (u64)1 << n_log;
     std::vector<u64> scratch((size_t)k * n);
-    transform(in, n, out, n, scratch.data(), n_log, k, 0, false, false, 0, 0);
+    transform(in, n, out, n, scratch.data(), n_log, k, 0, false, nullptr, false);
 }
 // coeffs [k][n] -> lde [k][N] in leaf order
 void emu_lde(const u64* coeffs, u64* lde, u32 n_log, u32 k, u32 rate_bits) {
     u64 n = (u64)1 << n_log, N = n << rate_bits;
-    for (u32 b = 0; b < (1u << rate_bits); b++)
-        transform(coeffs, n, lde + b * n, N, nullptr, n_log, k, 0, true, true,
-                  hostgl::coset_shift_of_block(n_log, rate_bits, b), 0);
+    std::vector<u64> bases;
+    for (u32 b = 0; b < (1u << rate_bits); b++) bases.push_back(hostgl::coset_shift_of_block(n_log, rate_bits, b));
+    // all coset blocks in one "launch" per pass, exactly as the library does (blockIdx.y = block)
+    transform(coeffs, n, lde, N, nullptr, n_log, k, 0, true, &bases, false, 1u << rate_bits, n);
 }
 }
