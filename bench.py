@@ -272,9 +272,10 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = cells / float(dt.item())
-    if world == 1:
-        cap_dev = out.cap.cpu()
-        assert bool((cap_dev == cap_host).all()), "device-resident and host-buffer paths disagree on the cap"
+    cap_dev = (out.cap if world == 1 else sh.cap).cpu()
+    assert bool((cap_dev == cap_host).all()), "device-resident and end-to-end paths disagree on the cap"
+    # the same synthetic input must give the same cap for every N (compare across runs)
+    cap_checksum = "%016x" % (int(np.bitwise_xor.reduce(cap_dev.numpy().view(np.uint64).reshape(-1))))
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -307,6 +308,7 @@ def run_b200(args):
                            "frac_of_peak": algorithmic_bytes(n_log, k) / (ms_step * 1e-3) / 1e9 / (peak * world)},
             "stages_ms_per_step": {s: v[0] / args.steps for s, v in stages.items()},
             "poseidon_perms_per_s": perms / (ms_step * 1e-3),
+            "cap_checksum": cap_checksum,
         }
         if world == 1:
             gips = {}
