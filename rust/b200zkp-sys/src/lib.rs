@@ -1,0 +1,36 @@
+//! NOT BUILT IN THIS ENVIRONMENT (no Rust toolchain) — see INTEGRATION.md.
+//! Raw bindings to include/b200zkp.h, one `extern "C"` item per declared entry point used by the plonky2 patch.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] pub struct b200zkp_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct b200zkp_batch { _p: [u8; 0] }
+#[repr(C)] pub struct b200zkp_tree { _p: [u8; 0] }
+
+extern "C" {
+    pub fn b200zkp_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut b200zkp_ctx) -> c_int;
+    pub fn b200zkp_ctx_destroy(ctx: *mut b200zkp_ctx);
+    pub fn b200zkp_last_error(ctx: *const b200zkp_ctx) -> *const c_char;
+
+    pub fn b200zkp_commit_from_values(ctx: *mut b200zkp_ctx, values: *const u64, n_log: u32, k: u32, rate_bits: u32,
+        cap_height: u32, salt: *const u64, out: *mut *mut b200zkp_batch) -> c_int;
+    pub fn b200zkp_commit_from_coeffs(ctx: *mut b200zkp_ctx, coeffs: *const u64, n_log: u32, k: u32, rate_bits: u32,
+        cap_height: u32, salt: *const u64, out: *mut *mut b200zkp_batch) -> c_int;
+    pub fn b200zkp_batch_free(b: *mut b200zkp_batch);
+    pub fn b200zkp_batch_cap(b: *mut b200zkp_batch, out: *mut u64) -> c_int;
+    pub fn b200zkp_batch_coeffs(b: *mut b200zkp_batch, out: *mut u64) -> c_int;
+    pub fn b200zkp_batch_leaves(b: *mut b200zkp_batch, out: *mut u64) -> c_int;
+    pub fn b200zkp_batch_digests(b: *mut b200zkp_batch, out: *mut u64) -> c_int;
+    pub fn b200zkp_batch_rows(b: *mut b200zkp_batch, idx: *const u64, n_idx: u64, rows: *mut u64, siblings: *mut u64) -> c_int;
+    pub fn b200zkp_batch_lde_values(b: *mut b200zkp_batch, index: u64, step: u64, out: *mut u64) -> c_int;
+
+    pub fn b200zkp_merkle_new(ctx: *mut b200zkp_ctx, leaves: *const u64, n_leaves: u64, leaf_len: u32, cap_height: u32,
+        out: *mut *mut b200zkp_tree) -> c_int;
+    pub fn b200zkp_tree_free(t: *mut b200zkp_tree);
+    pub fn b200zkp_tree_cap(t: *mut b200zkp_tree, out: *mut u64) -> c_int;
+    pub fn b200zkp_tree_digests(t: *mut b200zkp_tree, out: *mut u64) -> c_int;
+    pub fn b200zkp_tree_prove(t: *mut b200zkp_tree, idx: *const u64, n_idx: u64, siblings: *mut u64) -> c_int;
+
+    pub fn b200zkp_hash_no_pad(ctx: *mut b200zkp_ctx, input: *const u64, count: u64, len: u32, out: *mut u64) -> c_int;
+    pub fn b200zkp_two_to_one(ctx: *mut b200zkp_ctx, left: *const u64, right: *const u64, count: u64, out: *mut u64) -> c_int;
+}
