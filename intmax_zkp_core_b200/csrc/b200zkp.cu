@@ -472,16 +472,16 @@ static int dev_merkle_locked(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride
     if (shape.sub_log > 0 && !digests) BAD(ctx, "null digests buffer");
     {
         StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
-        u64 blocks = (n_leaves + 127) / 128;
-        merkle::leaf_hash_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(leaves, row_stride, col_stride,
+        u64 blocks = (n_leaves + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS;
+        merkle::leaf_hash_kernel<<<(unsigned)blocks, B200ZKP_HASH_THREADS, 0, ctx->stream>>>(leaves, row_stride, col_stride,
                                                                             leaf_len, n_leaves, shape, digests, cap, 1u);
         LAUNCH_CHECK(ctx);
     }
     StageTimer tm(ctx, B200ZKP_STAGE_TREE);
     for (u32 layer = 0; layer < shape.sub_log; layer++) {
         u64 n_parents = n_leaves >> (layer + 1);
-        u64 blocks = (n_parents + 127) / 128;
-        merkle::merkle_level_kernel<<<(unsigned)blocks, 128, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
+        u64 blocks = (n_parents + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS;
+        merkle::merkle_level_kernel<<<(unsigned)blocks, B200ZKP_HASH_THREADS, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
         LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -828,7 +828,7 @@ static int hash_rows(b200zkp_ctx* ctx, const u64* in, u64 count, u32 len, u64* o
     if ((!in && len) || !out) BAD(ctx, "null buffer");
     return with_io(ctx, in, count * len * 8, out, count * 32, [&](u64* di, u64* dout) -> int {
         merkle::TreeShape shape; shape.sub_log = 0; shape.sub_digests = 0;
-        merkle::leaf_hash_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(di, len, 1, len, count, shape, nullptr, dout, noop_short ? 1u : 0u);
+        merkle::leaf_hash_kernel<<<(unsigned)((count + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS), B200ZKP_HASH_THREADS, 0, ctx->stream>>>(di, len, 1, len, count, shape, nullptr, dout, noop_short ? 1u : 0u);
         LAUNCH_CHECK(ctx);
         return 0;
     });

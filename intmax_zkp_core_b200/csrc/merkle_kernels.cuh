@@ -17,7 +17,13 @@
 #include "poseidon.cuh"
 
 #ifndef B200ZKP_HASH_MINBLOCKS
-#define B200ZKP_HASH_MINBLOCKS 4
+#define B200ZKP_HASH_MINBLOCKS 2
+#endif
+#ifndef B200ZKP_HASH_THREADS
+#define B200ZKP_HASH_THREADS 512
+#endif
+#ifndef B200ZKP_HASH_PREFETCH
+#define B200ZKP_HASH_PREFETCH 0
 #endif
 
 namespace merkle {
@@ -47,6 +53,15 @@ GL_FN void sponge_leaf(const u64* __restrict__ p, u64 col_stride, u32 leaf_len, 
         }
         return;
     }
+#if !B200ZKP_HASH_PREFETCH
+    for (u32 c = 0; c < leaf_len; c += poseidon::RATE) {
+#pragma unroll
+        for (int i = 0; i < poseidon::RATE; i++)
+            if (c + i < leaf_len) s[i] = p[(u64)(c + i) * col_stride];
+        poseidon::permute(s);
+    }
+    return;
+#endif
     u64 nx[poseidon::RATE];
 #pragma unroll
     for (int i = 0; i < poseidon::RATE; i++) nx[i] = (u32)i < leaf_len ? p[(u64)i * col_stride] : 0;
@@ -72,7 +87,7 @@ __device__ __forceinline__ void store_digest(u64* dst, const u64 (&s)[poseidon::
 }
 
 // hash_or_noop over one leaf per thread.  leaf element (row, c) = leaves[row*row_stride + c*col_stride].
-__global__ void __launch_bounds__(128, B200ZKP_HASH_MINBLOCKS)
+__global__ void __launch_bounds__(B200ZKP_HASH_THREADS, B200ZKP_HASH_MINBLOCKS)
 leaf_hash_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len,
                  u64 n_leaves, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap,
                  u32 noop_short /* 1: hash_or_noop, 0: hash_no_pad */) {
@@ -90,7 +105,7 @@ leaf_hash_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride,
 }
 
 // parents of layer `layer` (children) -> layer+1, or the cap when layer+1 == sub_log.
-__global__ void __launch_bounds__(128, B200ZKP_HASH_MINBLOCKS)
+__global__ void __launch_bounds__(B200ZKP_HASH_THREADS, B200ZKP_HASH_MINBLOCKS)
 merkle_level_kernel(u64* __restrict__ digests, u64* __restrict__ cap, TreeShape shape, u32 layer,
                     u64 n_parents) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;

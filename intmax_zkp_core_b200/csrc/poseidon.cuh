@@ -27,7 +27,7 @@ static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 
 #ifndef B200ZKP_FAST_PARTIAL
-#define B200ZKP_FAST_PARTIAL 1
+#define B200ZKP_FAST_PARTIAL 0
 #endif
 
 GL_FN u64 sbox(u64 x) {
@@ -75,7 +75,7 @@ GL_FN u64 fold_lh(u64 L, u64 H) {
 
 // s <- MDS * s (+ addc, the constants of the next round, if addc != nullptr)
 template <bool kAddConst>
-GL_FN void mds_layer(u64 (&s)[WIDTH], const unsigned long long* addc) {
+GL_FN void mds_layer_halves(u64 (&s)[WIDTH], const unsigned long long* addc) {
     constexpr u32 C[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
     u32 lo[WIDTH], hi[WIDTH];
 #pragma unroll
@@ -93,6 +93,82 @@ GL_FN void mds_layer(u64 (&s)[WIDTH], const unsigned long long* addc) {
         }
         s[r] = fold_lh(L, H);
     }
+}
+
+// value = O0 + O1 * 2^22 + O2 * 2^43 + rc  with O_i < 2^31, rc canonical  ->  arbitrary u64 congruent mod p
+GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc) {
+#ifdef B200ZKP_HOST_EMU
+    unsigned __int128 v = (unsigned __int128)O0 + ((unsigned __int128)O1 << 22) + ((unsigned __int128)O2 << 43) + rc;
+    u64 lo = (u64)v;
+    u64 top = (u64)(v >> 64);                     // < 2^12
+    u64 e = (top << 32) - top;                    // top * EPS
+    u64 r = lo + e;
+    return (r < e) ? r + gl::EPS : r;
+#else
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 a, b, c, d, w0, w1, top, rc0, rc1, m;\n\t"
+        ".reg .u64 t, u;\n\t"
+        "mov.b64 {rc0, rc1}, %4;\n\t"
+        "shl.b32 a, %2, 22;\n\t"
+        "shr.u32 b, %2, 10;\n\t"
+        "shl.b32 c, %3, 11;\n\t"
+        "shr.u32 d, %3, 21;\n\t"
+        "add.cc.u32 w0, %1, a;\n\t"
+        "addc.cc.u32 w1, b, c;\n\t"
+        "addc.u32 top, d, 0;\n\t"
+        "add.cc.u32 w0, w0, rc0;\n\t"
+        "addc.cc.u32 w1, w1, rc1;\n\t"
+        "addc.u32 top, top, 0;\n\t"             // multiples of 2^64 == EPS
+        "mov.b64 t, {w0, w1};\n\t"
+        "mul.wide.u32 u, top, 0xFFFFFFFF;\n\t"
+        "add.cc.u64 t, t, u;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "mov.b64 {w0, w1}, t;\n\t"
+        "sub.cc.u32 w0, w0, m;\n\t"             // + m * EPS
+        "subc.u32 w1, w1, 0;\n\t"
+        "add.u32 w1, w1, m;\n\t"
+        "mov.b64 %0, {w0, w1};\n\t"
+        "}" : "=l"(r) : "r"(O0), "r"(O1), "r"(O2), "l"(rc));
+    return r;
+#endif
+}
+
+// MDS on three limbs (22 + 21 + 21 bits) so every product and 12-term sum fits 32 bits: the multiplies are
+// 32-bit IMADs (2 pipe cycles) instead of IMAD.WIDE (4), and the 12x12 circulant is split by
+// x^12 - 1 = (x^6 - 1)(x^6 + 1) into a cyclic and a negacyclic 6x6 product whose halved constants are
+//   P = (15, 24, 18, 17, 40, 14)   and   Q = (2, -4, 16, 1, -1, -1)      (all +-powers of two in Q)
+// out[k] = A[k] + B[k], out[k+6] = A[k] - B[k]; arithmetic is mod 2^32 (exact: true sums < 2^31).
+template <bool kAddConst>
+GL_FN void mds_layer(u64 (&s)[WIDTH], const unsigned long long* addc) {
+    constexpr u32 Pc[6] = {15, 24, 18, 17, 40, 14};
+    constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
+    u32 o[3][WIDTH];
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+        u32 l[WIDTH];
+#pragma unroll
+        for (int i = 0; i < WIDTH; i++)
+            l[i] = (L == 0) ? ((u32)s[i] & 0x3FFFFFu) : (L == 1) ? ((u32)(s[i] >> 22) & 0x1FFFFFu) : (u32)(s[i] >> 43);
+        u32 sp[6], sm[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { sp[i] = l[i] + l[i + 6]; sm[i] = l[i] - l[i + 6]; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            u32 A = 0, B = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                A += sp[i] * Pc[(k - i + 6) % 6];
+                const int q = (k >= i) ? Qc[k - i] : -Qc[k - i + 6];
+                B += sm[i] * (u32)q;
+            }
+            o[L][k] = A + B;
+            o[L][k + 6] = A - B;
+        }
+        o[L][0] += 8u * l[0];     // diag(8, 0, ..., 0)
+    }
+#pragma unroll
+    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], kAddConst ? (u64)addc[r] : 0ull);
 }
 
 // Column accumulator for dot products of 64-bit words: sum of 32x32 partial products of one weight,
@@ -189,6 +265,7 @@ GL_FN void partial_rounds_pushed(u64 (&s)[WIDTH]) {
 }
 
 // In-place permutation; input words arbitrary u64, output canonical.
+#if B200ZKP_FAST_PARTIAL
 GL_FN void permute(u64 (&s)[WIDTH]) {
     using namespace poseidon_tables;
 #pragma unroll
@@ -197,23 +274,12 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
     for (int r = 0; r < 4; r++) {
 #pragma unroll
         for (int i = 0; i < WIDTH; i++) s[i] = sbox(s[i]);
-#if B200ZKP_FAST_PARTIAL
         const unsigned long long* nxt = (r < 3) ? &RC_FULL[(r + 1) * WIDTH] : FAST_FIRST;
         mds_layer<true>(s, nxt);
-#else
-        if (r < 3) mds_layer<true>(s, &RC_FULL[(r + 1) * WIDTH]);
-        else mds_layer<false>(s, nullptr);
-#endif
     }
-#if B200ZKP_FAST_PARTIAL
     partial_rounds_fast(s);
 #pragma unroll
     for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], RC_FULL_PAD[4 * WIDTH + i]);
-#else
-    partial_rounds_pushed(s);
-#pragma unroll
-    for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], PUSH_TAIL[i]);
-#endif
 #pragma unroll 1
     for (int r = 4; r < 8; r++) {
 #pragma unroll
@@ -224,5 +290,38 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
 #pragma unroll
     for (int i = 0; i < WIDTH; i++) s[i] = gl::canon(s[i]);
 }
+#else
+// One loop over all 30 rounds with a single copy of the S-box row and of the MDS body: the whole permutation is
+// ~22 KB of SASS and stays resident in the instruction cache (the two-loop form was 59 KB and ncu showed
+// "no instruction" as the top stall with a 67 % instruction-cache hit rate).  The round kind is warp-uniform.
+GL_FN void permute(u64 (&s)[WIDTH]) {
+    using namespace poseidon_tables;
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], ROUND_ADD[i]);
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < WIDTH; i++) s[i] = sbox(s[i]);
+        } else {
+            s[0] = sbox(s[0]);
+        }
+        mds_layer<false>(s, nullptr);
+        if (r + 1 < 30) {
+            const unsigned long long* nxt = &ROUND_ADD[(r + 1) * WIDTH];
+            const bool next_full = (r + 1 < 4) || (r + 1 >= 26);
+            if (next_full) {
+#pragma unroll
+                for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], nxt[i]);
+            } else {
+                s[0] = add_const(s[0], nxt[0]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) s[i] = gl::canon(s[i]);
+}
+#endif
 
 }  // namespace poseidon
