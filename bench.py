@@ -173,6 +173,8 @@ def run_b200(args):
     cells = n * k
 
     ctx = D.torch_context(local_rank)          # enqueues on torch's current stream: torch.cuda.Event sees our kernels
+    if os.environ.get("B200ZKP_NO_OVERLAP"):
+        ctx.set_overlap(False)
     lay = D.shard_layout(n_log, k, RATE_BITS, CAP_HEIGHT, rank, world)
 
     # synthetic input: v[c][i] = splitmix64(c*n + i) mod p; each rank generates only its column shard

@@ -69,6 +69,8 @@ uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx);
 enum { B200ZKP_STAGE_INTT = 0, B200ZKP_STAGE_LDE = 1, B200ZKP_STAGE_LEAF_HASH = 2, B200ZKP_STAGE_TREE = 3,
        B200ZKP_N_STAGES = 4 };
 int b200zkp_ctx_set_timing(b200zkp_ctx* ctx, int enabled);
+/* LDE / leaf-hash overlap on two streams (off by default: no gain measured on B200); 0 = strictly sequential stages */
+int b200zkp_ctx_set_overlap(b200zkp_ctx* ctx, int enabled);
 int b200zkp_ctx_stage_ms(b200zkp_ctx* ctx, double ms[B200ZKP_N_STAGES], uint32_t counts[B200ZKP_N_STAGES]);
 /* pinned host memory for callers that want full-speed H2D/D2H */
 int b200zkp_host_alloc(size_t bytes, void** out);
@@ -144,6 +146,11 @@ int b200zkp_dev_salt(b200zkp_ctx* ctx, const uint64_t* salt, uint64_t* lde_salt_
 int b200zkp_dev_merkle(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t row_stride, uint64_t col_stride,
                        uint32_t leaf_len, uint64_t n_leaves, uint32_t cap_height, uint64_t* digests,
                        uint64_t* cap);
+/* b200zkp_dev_lde + b200zkp_dev_merkle over the same leaf blocks (leaves (block_end - block_begin) * n, cap_height counted
+ * within that range), software-pipelined: the transforms of block b+1 run on a second stream while block b is hashed. */
+int b200zkp_dev_lde_merkle(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,
+                           uint64_t lde_stride, uint32_t n_log, uint32_t k, uint32_t rate_bits, uint32_t block_begin,
+                           uint32_t block_end, uint32_t cap_height, uint64_t* digests, uint64_t* cap);
 /* whole commitment on caller-owned device buffers (what bench.py times with inputs resident in HBM):
  * in [k][n] -> coeffs [k][n], lde [(k+salt)][N], digests, cap.  is_coeffs selects from_coeffs. */
 int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,

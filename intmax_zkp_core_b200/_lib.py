@@ -66,6 +66,7 @@ _SIGS = {
     "b200zkp_last_error": (C.c_char_p, [C.c_void_p]),
     "b200zkp_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "b200zkp_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "b200zkp_ctx_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "b200zkp_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "b200zkp_ctx_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), u32p]),
     "b200zkp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -97,6 +98,7 @@ _SIGS = {
     "b200zkp_dev_lde": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "b200zkp_dev_salt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "b200zkp_dev_merkle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200zkp_dev_lde_merkle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "b200zkp_dev_commit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200zkp_dev_transpose_to_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200zkp_field_op": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

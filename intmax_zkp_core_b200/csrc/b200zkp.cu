@@ -44,6 +44,10 @@ struct b200zkp_ctx {
     std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
     std::multimap<size_t, void*> pool;                  // cached device allocations
     std::vector<void*> table_allocs;
+    // second, higher-priority stream: coset transforms run here while finished blocks are hashed on `stream`
+    cudaStream_t stream2 = nullptr;
+    bool overlap = false;   // measured on B200: no gain (both kernels are issue/I-cache limited when co-resident)
+    std::vector<cudaEvent_t> sync_events;
     // optional per-stage timing (bench.py): CUDA event pairs recorded on the ctx stream
     bool timing = false;
     std::vector<cudaEvent_t> ev_free;
@@ -345,6 +349,8 @@ extern "C" void b200zkp_ctx_destroy(b200zkp_ctx* ctx) {
     for (void* p : ctx->table_allocs) cudaFree(p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
+    for (auto e : ctx->sync_events) cudaEventDestroy(e);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -355,6 +361,13 @@ extern "C" uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx) { return ct
 extern "C" int b200zkp_ctx_synchronize(b200zkp_ctx* ctx) {
     if (!ctx) return B200ZKP_ERR_BAD_ARG;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b200zkp_ctx_set_overlap(b200zkp_ctx* ctx, int enabled) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    ctx->overlap = enabled != 0;
     return 0;
 }
 
@@ -459,24 +472,31 @@ extern "C" int b200zkp_dev_salt(b200zkp_ctx* ctx, const uint64_t* salt, uint64_t
     return dev_salt_locked(ctx, (const u64*)salt, (u64*)lde_salt_cols, lde_stride, n_log, rate_bits, block_begin, block_end);
 }
 
-static int dev_merkle_locked(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride, u64 col_stride, u32 leaf_len,
-                             u64 n_leaves, u32 cap_height, u64* digests, u64* cap) {
+static int merkle_shape(b200zkp_ctx* ctx, u64 n_leaves, u32 cap_height, const void* leaves, const void* digests, const void* cap,
+                        merkle::TreeShape* shape) {
     if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) BAD(ctx, "number of leaves must be a power of two");
     u32 lg = 0;
     while (((u64)1 << lg) < n_leaves) lg++;
     if (cap_height > lg) BAD(ctx, "cap_height exceeds log2(number of leaves)");
     if (!leaves || !cap) BAD(ctx, "null buffer");
-    merkle::TreeShape shape;
-    shape.sub_log = lg - cap_height;
-    shape.sub_digests = 2 * (((u64)1 << shape.sub_log) - 1);
-    if (shape.sub_log > 0 && !digests) BAD(ctx, "null digests buffer");
-    {
-        StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
-        u64 blocks = (n_leaves + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS;
-        merkle::leaf_hash_kernel<<<(unsigned)blocks, B200ZKP_HASH_THREADS, 0, ctx->stream>>>(leaves, row_stride, col_stride,
-                                                                            leaf_len, n_leaves, shape, digests, cap, 1u);
-        LAUNCH_CHECK(ctx);
-    }
+    shape->sub_log = lg - cap_height;
+    shape->sub_digests = 2 * (((u64)1 << shape->sub_log) - 1);
+    if (shape->sub_log > 0 && !digests) BAD(ctx, "null digests buffer");
+    return 0;
+}
+
+static int launch_leaf_hash(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 row0,
+                            u64 n_rows, const merkle::TreeShape& shape, u64* digests, u64* cap) {
+    if (!n_rows) return 0;
+    StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
+    u64 blocks = (n_rows + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS;
+    merkle::leaf_hash_kernel<<<(unsigned)blocks, B200ZKP_HASH_THREADS, 0, ctx->stream>>>(leaves, row_stride, col_stride, leaf_len,
+                                                                                         row0, n_rows, shape, digests, cap, 1u);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+static int launch_tree_levels(b200zkp_ctx* ctx, u64 n_leaves, const merkle::TreeShape& shape, u64* digests, u64* cap) {
     StageTimer tm(ctx, B200ZKP_STAGE_TREE);
     for (u32 layer = 0; layer < shape.sub_log; layer++) {
         u64 n_parents = n_leaves >> (layer + 1);
@@ -487,6 +507,74 @@ static int dev_merkle_locked(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride
     return 0;
 }
 
+static int dev_merkle_locked(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride, u64 col_stride, u32 leaf_len,
+                             u64 n_leaves, u32 cap_height, u64* digests, u64* cap) {
+    merkle::TreeShape shape;
+    TRY(merkle_shape(ctx, n_leaves, cap_height, leaves, digests, cap, &shape));
+    TRY(launch_leaf_hash(ctx, leaves, row_stride, col_stride, leaf_len, 0, n_leaves, shape, digests, cap));
+    return launch_tree_levels(ctx, n_leaves, shape, digests, cap);
+}
+
+static int get_sync_event(b200zkp_ctx* ctx, size_t i, cudaEvent_t* out) {
+    while (ctx->sync_events.size() <= i) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->sync_events.push_back(e);
+    }
+    *out = ctx->sync_events[i];
+    return 0;
+}
+
+// Coset LDE of leaf blocks [b0, b1) + Merkle forest over those leaves, software-pipelined: the transforms of block b+1
+// (ALU-pipe bound) run on a second stream while block b is hashed (multiplier bound) on the main stream.
+static int dev_lde_merkle_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride, u64* lde, u64 lde_stride, u32 n_log,
+                                 u32 k, u32 rate_bits, u32 b0, u32 b1, u32 leaf_len, u32 cap_height, u64* digests, u64* cap) {
+    if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "rate_bits / n_log out of range");
+    if (b0 >= b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
+    u64 n = (u64)1 << n_log;
+    u64 n_leaves = (u64)(b1 - b0) << n_log;
+    merkle::TreeShape shape;
+    TRY(merkle_shape(ctx, n_leaves, cap_height, lde, digests, cap, &shape));
+    if (!ctx->overlap || b1 - b0 < 2) {
+        TRY(dev_lde_locked(ctx, coeffs, coeff_stride, lde, lde_stride, n_log, k, rate_bits, b0, b1));
+        TRY(launch_leaf_hash(ctx, lde, 1, lde_stride, leaf_len, 0, n_leaves, shape, digests, cap));
+        return launch_tree_levels(ctx, n_leaves, shape, digests, cap);
+    }
+    if (!ctx->stream2) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+    }
+    const u64* cs = nullptr;
+    TRY(get_coset_scale(ctx, n_log, rate_bits, &cs));          // (table build, if any, happens on the main stream)
+    b200zkp_ctx::Images im;
+    TRY(get_twiddle_images(ctx, n_log, 0, true, &im));
+    cudaStream_t main_stream = ctx->stream;
+    cudaEvent_t e0;
+    TRY(get_sync_event(ctx, 0, &e0));
+    CUDA_TRY(ctx, cudaEventRecord(e0, main_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, e0, 0));   // coefficients (and tables) are ready
+    int rc = 0;
+    for (u32 b = b0; b < b1 && !rc; b++) {
+        u64 off = (u64)(b - b0) << n_log;
+        ctx->stream = ctx->stream2;
+        {
+            StageTimer tm(ctx, B200ZKP_STAGE_LDE);
+            rc = run_transform(ctx, coeffs, coeff_stride, lde + off, lde_stride, nullptr, n_log, k, /*dir=*/0, /*bitrev_out=*/true,
+                               cs + (u64)b * n, n, /*inverse_scale=*/false, /*canon_in=*/true, 1, n);
+        }
+        cudaEvent_t eb = nullptr;
+        if (!rc) rc = get_sync_event(ctx, 1 + (b - b0), &eb);
+        if (!rc && cudaEventRecord(eb, ctx->stream2) != cudaSuccess) rc = B200ZKP_ERR_CUDA;
+        ctx->stream = main_stream;
+        if (!rc && cudaStreamWaitEvent(main_stream, eb, 0) != cudaSuccess) rc = B200ZKP_ERR_CUDA;
+        if (!rc) rc = launch_leaf_hash(ctx, lde, 1, lde_stride, leaf_len, off, n, shape, digests, cap);
+    }
+    ctx->stream = main_stream;
+    if (rc) { if (rc == B200ZKP_ERR_CUDA) ctx->err = "stream/event error in the LDE/hash pipeline"; (void)cudaGetLastError(); return rc; }
+    return launch_tree_levels(ctx, n_leaves, shape, digests, cap);
+}
+
 extern "C" int b200zkp_dev_merkle(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t row_stride,
                                   uint64_t col_stride, uint32_t leaf_len, uint64_t n_leaves, uint32_t cap_height,
                                   uint64_t* digests, uint64_t* cap) {
@@ -494,6 +582,16 @@ extern "C" int b200zkp_dev_merkle(b200zkp_ctx* ctx, const uint64_t* leaves, uint
     Guard g(ctx);
     return dev_merkle_locked(ctx, (const u64*)leaves, row_stride, col_stride, leaf_len, n_leaves, cap_height,
                              (u64*)digests, (u64*)cap);
+}
+
+extern "C" int b200zkp_dev_lde_merkle(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,
+                                      uint64_t lde_stride, uint32_t n_log, uint32_t k, uint32_t rate_bits, uint32_t block_begin,
+                                      uint32_t block_end, uint32_t cap_height, uint64_t* digests, uint64_t* cap) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!coeffs || !lde) BAD(ctx, "null buffer");
+    return dev_lde_merkle_locked(ctx, (const u64*)coeffs, coeff_stride, (u64*)lde, lde_stride, n_log, k, rate_bits, block_begin,
+                                 block_end, k, cap_height, (u64*)digests, (u64*)cap);
 }
 
 static int dev_commit_locked(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log, u32 k, u32 rate_bits,
@@ -506,9 +604,8 @@ static int dev_commit_locked(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32
     u32 row = k + (salt ? B200ZKP_SALT_SIZE : 0);
     if (is_coeffs) TRY(launch_canon_copy(ctx, in, coeffs, (u64)k * n));
     else TRY(dev_intt_locked(ctx, in, n, coeffs, n, /*scratch=*/lde, n_log, k));   // the LDE buffer is free until step 2
-    TRY(dev_lde_locked(ctx, coeffs, n, lde, N, n_log, k, rate_bits, 0, 1u << rate_bits));
     if (salt) TRY(dev_salt_locked(ctx, salt, lde + (u64)k * N, N, n_log, rate_bits, 0, 1u << rate_bits));
-    return dev_merkle_locked(ctx, lde, /*row_stride=*/1, /*col_stride=*/N, row, N, cap_height, digests, cap);
+    return dev_lde_merkle_locked(ctx, coeffs, n, lde, N, n_log, k, rate_bits, 0, 1u << rate_bits, row, cap_height, digests, cap);
 }
 
 extern "C" int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,
@@ -574,12 +671,56 @@ static int commit_host(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log
         batch_release(b);
         return rc;
     }
-    auto fail = [&](int code) { dev_release(ctx, d_in, in_b); dev_release(ctx, d_salt, salt_b); batch_release(b); return code; };
-    cudaError_t e = cudaMemcpyAsync(d_in, in, in_b, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && salt) e = cudaMemcpyAsync(d_salt, salt, salt_b, cudaMemcpyHostToDevice, ctx->stream);
-    if (e != cudaSuccess) { ctx->err = std::string("H2D: ") + cudaGetErrorString(e); return fail(B200ZKP_ERR_CUDA); }
-    rc = dev_commit_locked(ctx, (const u64*)d_in, is_coeffs, n_log, k, rate_bits, cap_height, (const u64*)d_salt,
-                           b->coeffs, b->lde, b->digests, b->cap);
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);   // nothing may still be writing the buffers we recycle
+        (void)cudaGetLastError();
+        dev_release(ctx, d_in, in_b); dev_release(ctx, d_salt, salt_b); batch_release(b); return code;
+    };
+    // Column-chunked upload pipeline: chunk c+1 crosses PCIe on the copy stream while chunk c is inverse-transformed
+    // and extended on the main stream (columns are independent until the leaf hash), so the 8nk-byte H2D hides behind
+    // the transforms when the caller's buffer is pinned.
+    if (!ctx->stream2) {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ctx->err = "cannot create the copy stream";
+            return fail(B200ZKP_ERR_CUDA);
+        }
+    }
+    cudaError_t e = cudaSuccess;
+    const u32 n_chunks = (k >= 16 && in_b >= ((size_t)64 << 20)) ? 8 : 1;
+    const u32 per = (k + n_chunks - 1) / n_chunks;
+    cudaEvent_t e_free;
+    if ((rc = get_sync_event(ctx, 0, &e_free))) return fail(rc);
+    // d_in / lde may be recycled buffers still in use by earlier work on the main stream
+    if (cudaEventRecord(e_free, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream2, e_free, 0) != cudaSuccess) {
+        (void)cudaGetLastError(); ctx->err = "event error"; return fail(B200ZKP_ERR_CUDA);
+    }
+    if (salt) e = cudaMemcpyAsync(d_salt, salt, salt_b, cudaMemcpyHostToDevice, ctx->stream2);
+    std::vector<cudaEvent_t> up(n_chunks);
+    for (u32 c = 0; c < n_chunks && e == cudaSuccess; c++) {
+        u32 c0 = std::min(k, c * per), c1 = std::min(k, (c + 1) * per);
+        if ((rc = get_sync_event(ctx, 1 + c, &up[c]))) return fail(rc);
+        if (c1 > c0) e = cudaMemcpyAsync((u64*)d_in + (u64)c0 * n, in + (u64)c0 * n, (size_t)(c1 - c0) * n * 8, cudaMemcpyHostToDevice, ctx->stream2);
+        if (e == cudaSuccess) e = cudaEventRecord(up[c], ctx->stream2);
+    }
+    if (e != cudaSuccess) { ctx->err = std::string("H2D: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return fail(B200ZKP_ERR_CUDA); }
+    for (u32 c = 0; c < n_chunks; c++) {
+        u32 c0 = std::min(k, c * per), c1 = std::min(k, (c + 1) * per);
+        if (cudaStreamWaitEvent(ctx->stream, up[c], 0) != cudaSuccess) { (void)cudaGetLastError(); ctx->err = "event error"; return fail(B200ZKP_ERR_CUDA); }
+        if (c1 == c0) continue;
+        const u64* src = (const u64*)d_in + (u64)c0 * n;
+        u64* cf = b->coeffs + (u64)c0 * n;
+        u64* ld = b->lde + (u64)c0 * N;
+        if (is_coeffs) rc = launch_canon_copy(ctx, src, cf, (u64)(c1 - c0) * n);
+        else rc = dev_intt_locked(ctx, src, n, cf, n, /*scratch=*/ld, n_log, c1 - c0);     // this chunk's LDE columns are still free
+        if (!rc) rc = dev_lde_locked(ctx, cf, n, ld, N, n_log, c1 - c0, rate_bits, 0, 1u << rate_bits);
+        if (rc) return fail(rc);
+    }
+    if (salt) rc = dev_salt_locked(ctx, (const u64*)d_salt, b->lde + (u64)k * N, N, n_log, rate_bits, 0, 1u << rate_bits);
+    if (!rc) rc = dev_merkle_locked(ctx, b->lde, /*row_stride=*/1, /*col_stride=*/N, row, N, cap_height, b->digests, b->cap);
     if (rc) return fail(rc);
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = std::string("commit: ") + cudaGetErrorString(e); return fail(B200ZKP_ERR_CUDA); }
@@ -828,7 +969,7 @@ static int hash_rows(b200zkp_ctx* ctx, const u64* in, u64 count, u32 len, u64* o
     if ((!in && len) || !out) BAD(ctx, "null buffer");
     return with_io(ctx, in, count * len * 8, out, count * 32, [&](u64* di, u64* dout) -> int {
         merkle::TreeShape shape; shape.sub_log = 0; shape.sub_digests = 0;
-        merkle::leaf_hash_kernel<<<(unsigned)((count + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS), B200ZKP_HASH_THREADS, 0, ctx->stream>>>(di, len, 1, len, count, shape, nullptr, dout, noop_short ? 1u : 0u);
+        merkle::leaf_hash_kernel<<<(unsigned)((count + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS), B200ZKP_HASH_THREADS, 0, ctx->stream>>>(di, len, 1, len, 0, count, shape, nullptr, dout, noop_short ? 1u : 0u);
         LAUNCH_CHECK(ctx);
         return 0;
     });

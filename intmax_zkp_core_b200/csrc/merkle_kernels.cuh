@@ -60,8 +60,7 @@ GL_FN void sponge_leaf(const u64* __restrict__ p, u64 col_stride, u32 leaf_len, 
             if (c + i < leaf_len) s[i] = p[(u64)(c + i) * col_stride];
         poseidon::permute(s);
     }
-    return;
-#endif
+#else
     u64 nx[poseidon::RATE];
 #pragma unroll
     for (int i = 0; i < poseidon::RATE; i++) nx[i] = (u32)i < leaf_len ? p[(u64)i * col_stride] : 0;
@@ -77,6 +76,7 @@ GL_FN void sponge_leaf(const u64* __restrict__ p, u64 col_stride, u32 leaf_len, 
             if (c2 + i < leaf_len) nx[i] = p[(u64)(c2 + i) * col_stride];
         poseidon::permute(s);
     }
+#endif
 }
 
 #ifndef B200ZKP_HOST_EMU
@@ -89,10 +89,12 @@ __device__ __forceinline__ void store_digest(u64* dst, const u64 (&s)[poseidon::
 // hash_or_noop over one leaf per thread.  leaf element (row, c) = leaves[row*row_stride + c*col_stride].
 __global__ void __launch_bounds__(B200ZKP_HASH_THREADS, B200ZKP_HASH_MINBLOCKS)
 leaf_hash_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len,
-                 u64 n_leaves, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap,
+                 u64 row0, u64 n_rows, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap,
                  u32 noop_short /* 1: hash_or_noop, 0: hash_no_pad */) {
-    u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n_leaves) return;
+    // rows [row0, row0 + n_rows) of the leaf range: one launch per finished coset block when pipelined with the LDE
+    u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_rows) return;
+    u64 row = row0 + gid;
     u64 s[poseidon::WIDTH];
     sponge_leaf(leaves + row * row_stride, col_stride, leaf_len, noop_short, s);
     if (shape.sub_log == 0) {

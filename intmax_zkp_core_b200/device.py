@@ -132,10 +132,9 @@ class ShardedCommitment:
         if self.world > 1:
             dist.all_gather_into_tensor(self.coeffs_all, mine, group=self.group)
         b0 = self.rank * self.blocks_per_rank
-        ctx.check(lib.b200zkp_dev_lde(ctx._h, _ptr(self.coeffs_all), n, _ptr(self.lde), self.N_local, self.n_log,
-                                      self.k, self.rate_bits, b0, b0 + self.blocks_per_rank))
-        ctx.check(lib.b200zkp_dev_merkle(ctx._h, _ptr(self.lde), 1, self.N_local, self.k, self.N_local,
-                                         self.cap_height_local, _ptr(self.digests), _ptr(self.cap_local)))
+        ctx.check(lib.b200zkp_dev_lde_merkle(ctx._h, _ptr(self.coeffs_all), n, _ptr(self.lde), self.N_local, self.n_log,
+                                             self.k, self.rate_bits, b0, b0 + self.blocks_per_rank, self.cap_height_local,
+                                             _ptr(self.digests), _ptr(self.cap_local)))
         if self.world > 1:
             dist.all_gather_into_tensor(self.cap, self.cap_local, group=self.group)
         else:

@@ -79,6 +79,10 @@ class Context:
 
     STAGES = ("intt", "lde", "leaf_hash", "tree")
 
+    def set_overlap(self, enabled: bool):
+        """LDE / leaf-hash overlap on two streams (default on)."""
+        self.check(self._lib.b200zkp_ctx_set_overlap(self._h, int(enabled)))
+
     def set_timing(self, enabled: bool):
         self.check(self._lib.b200zkp_ctx_set_timing(self._h, int(enabled)))
 
