@@ -485,12 +485,21 @@ static int merkle_shape(b200zkp_ctx* ctx, u64 n_leaves, u32 cap_height, const vo
     return 0;
 }
 
+// Block size of the hash kernels: 512 threads when the launch fills the GPU anyway, smaller CTAs for small trees so
+// that every SM gets work (the kernels are compiled for up to 512 threads at 64 registers).
+static unsigned hash_block_threads(u64 n_items) {
+    unsigned t = B200ZKP_HASH_THREADS;
+    while (t > 32 && n_items / t < 2 * 148) t >>= 1;
+    return t;
+}
+
 static int launch_leaf_hash(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 row0,
                             u64 n_rows, const merkle::TreeShape& shape, u64* digests, u64* cap) {
     if (!n_rows) return 0;
     StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
-    u64 blocks = (n_rows + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS;
-    merkle::leaf_hash_kernel<<<(unsigned)blocks, B200ZKP_HASH_THREADS, 0, ctx->stream>>>(leaves, row_stride, col_stride, leaf_len,
+    unsigned threads = hash_block_threads(n_rows);
+    u64 blocks = (n_rows + threads - 1) / threads;
+    merkle::leaf_hash_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(leaves, row_stride, col_stride, leaf_len,
                                                                                          row0, n_rows, shape, digests, cap, 1u);
     LAUNCH_CHECK(ctx);
     return 0;
@@ -500,8 +509,9 @@ static int launch_tree_levels(b200zkp_ctx* ctx, u64 n_leaves, const merkle::Tree
     StageTimer tm(ctx, B200ZKP_STAGE_TREE);
     for (u32 layer = 0; layer < shape.sub_log; layer++) {
         u64 n_parents = n_leaves >> (layer + 1);
-        u64 blocks = (n_parents + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS;
-        merkle::merkle_level_kernel<<<(unsigned)blocks, B200ZKP_HASH_THREADS, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
+        unsigned threads = hash_block_threads(n_parents);
+        u64 blocks = (n_parents + threads - 1) / threads;
+        merkle::merkle_level_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
         LAUNCH_CHECK(ctx);
     }
     return 0;

@@ -26,21 +26,34 @@
 #define WIDTH 12
 static const uint64_t CIRC[WIDTH] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 
-/* non-canonical-tolerant helpers: values are arbitrary u64 congruent mod p, canonicalised on output */
+/* non-canonical-tolerant helpers: values are arbitrary u64 congruent mod p, canonicalised on output.
+ * Written the way plonky2's scalar x86-64 path is (branch-free reduce128, u128 dot products with a carry word,
+ * MDS on 32-bit halves); plonky2 additionally ships hand-written asm / AVX2 variants of the same arithmetic. */
 static inline uint64_t red128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t hh = hi >> 32, hl = hi & GL_EPS;
     uint64_t t0 = lo - hh;
-    if (lo < hh) t0 -= GL_EPS;
+    t0 -= (uint64_t)(-(int64_t)(lo < hh)) & GL_EPS;       /* borrow: -2^64 = -EPS */
     uint64_t t1 = hl * GL_EPS;
     uint64_t r = t0 + t1;
-    if (r < t1) r += GL_EPS;
+    r += (uint64_t)(-(int64_t)(r < t1)) & GL_EPS;         /* carry: +2^64 = +EPS */
     return r;
 }
 static inline uint64_t mulnc(uint64_t a, uint64_t b) { return red128((u128)a * b); }
 static inline uint64_t sbox(uint64_t x) {
     uint64_t x2 = mulnc(x, x), x4 = mulnc(x2, x2), x3 = mulnc(x2, x);
     return mulnc(x3, x4);
+}
+/* sum of up to 16 u64*u64 products: 128-bit accumulator + carry word; 2^128 = -2^32 (mod p) */
+typedef struct { u128 acc; uint64_t over; } acc160_t;
+static inline void acc_mac(acc160_t* a, uint64_t x, uint64_t y) {
+    u128 p = (u128)x * y;
+    a->acc += p;
+    a->over += a->acc < p;
+}
+static inline uint64_t acc_reduce(const acc160_t* a) {
+    uint64_t r = gl_canon(red128(a->acc));
+    return gl_sub(r, a->over << 32);
 }
 static inline void mds(uint64_t s[WIDTH], const uint64_t* addc) {
     /* split into 32-bit halves so the 12x12 small-constant products accumulate in plain u64 (plonky2's
@@ -65,19 +78,18 @@ void cpub_permute(uint64_t s[WIDTH]) {
     {
         uint64_t t[WIDTH - 1];
         for (int r = 0; r < WIDTH - 1; r++) {
-            uint64_t acc = 0;
-            for (int c = 0; c < WIDTH - 1; c++) acc = red128((u128)FAST_INIT[r * (WIDTH - 1) + c] * s[1 + c] + acc);
-            t[r] = acc;
+            acc160_t a = {0, 0};
+            for (int c = 0; c < WIDTH - 1; c++) acc_mac(&a, FAST_INIT[r * (WIDTH - 1) + c], s[1 + c]);
+            t[r] = acc_reduce(&a);
         }
         memcpy(s + 1, t, sizeof t);
     }
     for (int i = 0; i < 22; i++) {
         uint64_t s0 = red128((u128)sbox(s[0]) + FAST_POST[i]);
-        /* d = 25*s0 + sum vhat*s[j]: accumulate with a running reduction every term (u128 + u64) */
-        uint64_t d = red128((u128)s0 * 25);
-        for (int j = 0; j < WIDTH - 1; j++) d = red128((u128)FAST_VHAT[i * (WIDTH - 1) + j] * s[1 + j] + d);
+        acc160_t a = {(u128)s0 * 25, 0};
+        for (int j = 0; j < WIDTH - 1; j++) acc_mac(&a, FAST_VHAT[i * (WIDTH - 1) + j], s[1 + j]);
         for (int j = 0; j < WIDTH - 1; j++) s[1 + j] = red128((u128)FAST_WHAT[i * (WIDTH - 1) + j] * s0 + s[1 + j]);
-        s[0] = d;
+        s[0] = acc_reduce(&a);
     }
     for (int i = 0; i < WIDTH; i++) s[i] = red128((u128)s[i] + RC_FULL[4 * WIDTH + i]);
     for (int r = 4; r < 8; r++) {
