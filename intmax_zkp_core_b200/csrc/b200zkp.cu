@@ -183,7 +183,12 @@ static int get_coset(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const std::vect
 
 template <int B>
 static void launch_pass_b(const ntt::PassParams& p, dim3 grid, cudaStream_t s) {
-    ntt::ntt_pass_kernel<B><<<grid, ntt::THREADS, 0, s>>>(p);
+    switch (ntt::pass_mode(p)) {
+        case ntt::MODE_MID_NATURAL: ntt::ntt_pass_kernel<B, ntt::MODE_MID_NATURAL><<<grid, ntt::THREADS, 0, s>>>(p); break;
+        case ntt::MODE_MID_BITREV: ntt::ntt_pass_kernel<B, ntt::MODE_MID_BITREV><<<grid, ntt::THREADS, 0, s>>>(p); break;
+        case ntt::MODE_FINAL_BITREV: ntt::ntt_pass_kernel<B, ntt::MODE_FINAL_BITREV><<<grid, ntt::THREADS, 0, s>>>(p); break;
+        default: ntt::ntt_pass_kernel<B, ntt::MODE_FINAL_NATURAL><<<grid, ntt::THREADS, 0, s>>>(p); break;
+    }
 }
 static int launch_pass(b200zkp_ctx* ctx, const ntt::PassParams& p, u32 B, u32 n_blk) {
     u64 T = ntt::TILE_ELEMS >> B;

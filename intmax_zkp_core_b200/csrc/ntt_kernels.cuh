@@ -131,8 +131,18 @@ GL_FN u64 digit_reverse(u64 beta_nat, const PassParams& p) {
     return pos;
 }
 
+// Kernel flavours (compile time, so each instantiation carries only its own load/store path and stays small in
+// the instruction cache): non-final passes in natural / bit-reversed position, final pass in place (LDE) or
+// scattered to natural order (inverse transform).
+enum PassMode : int { MODE_MID_NATURAL = 0, MODE_MID_BITREV = 1, MODE_FINAL_BITREV = 2, MODE_FINAL_NATURAL = 3 };
+static inline int pass_mode(const PassParams& p) {   // host side (launcher / emulation harness)
+    if (p.out_mode == OUT_FINAL_NATURAL) return MODE_FINAL_NATURAL;
+    if (p.out_mode == OUT_INPLACE_NATURAL) return MODE_MID_NATURAL;
+    return p.C_log == 0 ? MODE_FINAL_BITREV : MODE_MID_BITREV;
+}
+
 // B = bits of this pass (1..8, compile time so the rounds fully unroll); block = CTA index, blk = coset block
-template <int B>
+template <int B, int MODE>
 GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
     constexpr u32 T = TILE_ELEMS >> B;
     constexpr u32 TP = T + 1;
@@ -147,7 +157,10 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
     const u64 total_batches = (u64)p.ncols << batches_log;
     const u64 batch_mask = ((u64)1 << batches_log) - 1;
     const u64 tile_b0 = (u64)block * T;
-    const bool final_pass = (p.C_log == 0);
+    constexpr bool final_pass = (MODE == MODE_FINAL_BITREV || MODE == MODE_FINAL_NATURAL);
+    constexpr u32 out_mode = MODE == MODE_MID_NATURAL ? OUT_INPLACE_NATURAL : (MODE == MODE_FINAL_NATURAL ? OUT_FINAL_NATURAL : OUT_INPLACE_BITREV);
+    // final in-place tiles are one contiguous run of TILE_ELEMS elements unless a tile straddles two columns
+    const bool whole_tile_in_column = (((u64)1 << batches_log) >= T) && (tile_b0 + T <= total_batches);
     const u32 C_mask = (u32)(((u64)1 << p.C_log) - 1);
     const u64* __restrict__ in = p.in + (u64)blk * p.in_blk_stride;
     u64* __restrict__ out = p.out + (u64)blk * p.out_blk_stride;
@@ -187,8 +200,26 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
 #pragma unroll
                 for (u32 it = 0; it < IT; it++) v[it] = gl::canon(v[it]);
             }
+        } else if (MODE == MODE_FINAL_BITREV && whole_tile_in_column) {
+            // the tile is the contiguous run [base, base + TILE_ELEMS) of one column
+            const u64 base = (tile_b0 >> batches_log) * p.in_col_stride + ((tile_b0 & batch_mask) << B);
+#pragma unroll
+            for (u32 it = 0; it < IT; it++) {
+                u32 idx = tid + it * THREADS;
+                sm[it] = (idx & (NPTS - 1)) * TP + (idx >> B);
+                v[it] = in[base + idx];
+            }
+            if (scale) {
+                const u64 sbase = (tile_b0 & batch_mask) << B;
+#pragma unroll
+                for (u32 it = 0; it < IT; it++)
+                    v[it] = gl::mul(p.canon_in ? gl::canon(v[it]) : v[it], scale[sbase + tid + it * THREADS]);
+            } else if (p.canon_in) {
+#pragma unroll
+                for (u32 it = 0; it < IT; it++) v[it] = gl::canon(v[it]);
+            }
         } else {
-            // contiguous tiles of the final pass (and the generic path of very small transforms)
+            // generic path: final natural-order pass, tiles straddling columns, very small transforms
 #pragma unroll
             for (u32 it = 0; it < IT; it++) {
                 u32 idx = tid + it * THREADS;
@@ -201,7 +232,7 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
                 if (bg < total_batches) {
                     u64 col = bg >> batches_log;
                     u64 beta = bg & batch_mask;
-                    if (p.out_mode == OUT_FINAL_NATURAL) beta = digit_reverse(beta, p);
+                    if (out_mode == OUT_FINAL_NATURAL) beta = digit_reverse(beta, p);
                     u64 a = beta >> p.C_log, c = beta & C_mask;
                     u64 i_col = (a << (B + p.C_log)) + ((u64)g << p.C_log) + c;
                     x = in[col * p.in_col_stride + i_col];
@@ -219,7 +250,7 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
     // ---- 2^B-point DIF, radix-8 in registers
     {
         u32 sigma = 0;
-#pragma unroll
+#pragma unroll 1   // one copy of the radix-8 round in the instruction cache; stride and twiddle step are run-time
         for (int r = 0; r < B / 3; r++) {
             NTT_FOR_THREADS(tid) { run_round<3>(tile, wt, B, T, TP, sigma, tid); }
             sigma += 3;
@@ -231,8 +262,16 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
 
     // ---- twiddle + store
     NTT_FOR_THREADS(tid) {
-        const bool contiguous = final_pass && p.out_mode == OUT_INPLACE_BITREV;
-        if (!contiguous && kOwnBatch) {
+        constexpr bool contiguous = (MODE == MODE_FINAL_BITREV);
+        if (contiguous && whole_tile_in_column) {
+            const u64 base = (tile_b0 >> batches_log) * p.out_col_stride + ((tile_b0 & batch_mask) << B);
+#pragma unroll
+            for (u32 it = 0; it < IT; it++) {
+                u32 idx = tid + it * THREADS;
+                u64 x = tile[(idx & (NPTS - 1)) * TP + (idx >> B)];
+                out[base + idx] = p.out_scale ? gl::mul(x, p.out_scale) : x;
+            }
+        } else if (!contiguous && kOwnBatch) {
             // row = k1 (natural modes) or g~ (bit-reversed mode); the thread keeps batch b
             const u32 b = tid % T, r0 = tid / T;
             const u64 bg = tile_b0 + b;
@@ -245,13 +284,13 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
                 for (u32 it = 0; it < IT; it++) {
                     u32 row = r0 + it * GSTEP;
                     u32 gt, k1;
-                    if (p.out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
+                    if (out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
                     else { k1 = row; gt = bitrev(row, B); }
                     v[it] = tile[gt * TP + b];
-                    pos[it] = (p.out_mode == OUT_INPLACE_BITREV) ? gt : k1;
+                    pos[it] = (out_mode == OUT_INPLACE_BITREV) ? gt : k1;
                     kk[it] = k1;
                 }
-                if (p.out_mode == OUT_FINAL_NATURAL) {
+                if (out_mode == OUT_FINAL_NATURAL) {
                     u64 obase = col * p.out_col_stride + beta;
 #pragma unroll
                     for (u32 it = 0; it < IT; it++) {
@@ -285,17 +324,17 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
                 u64 bg = tile_b0 + b;
                 if (bg >= total_batches) continue;
                 u32 gt, k1;
-                if (p.out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
+                if (out_mode == OUT_INPLACE_BITREV) { gt = row; k1 = bitrev(row, B); }
                 else { k1 = row; gt = bitrev(row, B); }
                 u64 x = tile[gt * TP + b];
                 u64 col = bg >> batches_log;
                 u64 beta = bg & batch_mask;
                 u64 o_col;
-                if (p.out_mode == OUT_FINAL_NATURAL) {
+                if (out_mode == OUT_FINAL_NATURAL) {
                     o_col = beta + ((u64)k1 << batches_log);
                 } else {
                     u64 a = beta >> p.C_log, c = beta & C_mask;
-                    u32 pos = (p.out_mode == OUT_INPLACE_BITREV) ? gt : k1;
+                    u32 pos = (out_mode == OUT_INPLACE_BITREV) ? gt : k1;
                     o_col = (a << (B + p.C_log)) + ((u64)pos << p.C_log) + c;
                     if (p.twimg) x = gl::mul(x, gl::ldg(p.twimg + ((u64)pos << p.C_log) + c));
                 }
@@ -307,8 +346,8 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
 }
 
 #ifndef B200ZKP_HOST_EMU
-template <int B>
-__global__ void __launch_bounds__(THREADS) ntt_pass_kernel(PassParams p) { pass_body<B>(p, blockIdx.x, blockIdx.y); }
+template <int B, int MODE>
+__global__ void __launch_bounds__(THREADS, 4) ntt_pass_kernel(PassParams p) { pass_body<B, MODE>(p, blockIdx.x, blockIdx.y); }
 
 // table builders (run once per (n_log, direction, rate_bits) and cached by the context)
 // out[i] = base^i for i < count, from the two-level power tables of `base`

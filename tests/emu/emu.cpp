@@ -19,16 +19,17 @@ static void run_pass(const ntt::PassParams& p, u32 B, u32 n_blk) {
     u64 blocks = (total_batches + T - 1) / T;
     for (u32 y = 0; y < n_blk; y++)
         for (u64 blk = 0; blk < blocks; blk++) {
-            switch (B) {
-                case 1: ntt::pass_body<1>(p, (u32)blk, y); break;
-                case 2: ntt::pass_body<2>(p, (u32)blk, y); break;
-                case 3: ntt::pass_body<3>(p, (u32)blk, y); break;
-                case 4: ntt::pass_body<4>(p, (u32)blk, y); break;
-                case 5: ntt::pass_body<5>(p, (u32)blk, y); break;
-                case 6: ntt::pass_body<6>(p, (u32)blk, y); break;
-                case 7: ntt::pass_body<7>(p, (u32)blk, y); break;
-                case 8: ntt::pass_body<8>(p, (u32)blk, y); break;
-            }
+#define EMU_PASS(BB)                                                                                           \
+    case BB:                                                                                                   \
+        switch (ntt::pass_mode(p)) {                                                                           \
+            case ntt::MODE_MID_NATURAL: ntt::pass_body<BB, ntt::MODE_MID_NATURAL>(p, (u32)blk, y); break;      \
+            case ntt::MODE_MID_BITREV: ntt::pass_body<BB, ntt::MODE_MID_BITREV>(p, (u32)blk, y); break;        \
+            case ntt::MODE_FINAL_BITREV: ntt::pass_body<BB, ntt::MODE_FINAL_BITREV>(p, (u32)blk, y); break;    \
+            default: ntt::pass_body<BB, ntt::MODE_FINAL_NATURAL>(p, (u32)blk, y); break;                       \
+        }                                                                                                      \
+        break;
+            switch (B) { EMU_PASS(1) EMU_PASS(2) EMU_PASS(3) EMU_PASS(4) EMU_PASS(5) EMU_PASS(6) EMU_PASS(7) EMU_PASS(8) }
+#undef EMU_PASS
         }
 }
 
