@@ -279,6 +279,28 @@ def run_b200(args):
     # the same synthetic input must give the same cap for every N (compare across runs)
     cap_checksum = "%016x" % (int(np.bitwise_xor.reduce(cap_dev.numpy().view(np.uint64).reshape(-1))))
 
+    # ---- strict drop-in: + D2H of coefficients, row-major leaves and digests, overlapped with the hashing (N = 1 only)
+    e2e_strict = None
+    if world == 1 and not os.environ.get("B200ZKP_SKIP_STRICT"):
+        row = k
+        outs = [torch.empty(sz, dtype=torch.int64).pin_memory() for sz in (k * n, N * row, 8 * (N - (1 << CAP_HEIGHT)))]
+
+        def strict_step():
+            hctx.check(lib.b200zkp_commit_copy_back(hctx._h, C.c_void_p(host_vals.data_ptr()), 0, n_log, k, RATE_BITS, CAP_HEIGHT, None,
+                                                    C.c_void_p(outs[0].data_ptr()), C.c_void_p(outs[1].data_ptr()),
+                                                    C.c_void_p(outs[2].data_ptr()), C.c_void_p(cap_host.data_ptr()), None))
+        strict_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(args.steps, 3))):
+            strict_step()
+        torch.cuda.synchronize()
+        dt_s = (time.perf_counter() - t0) / max(1, min(args.steps, 3))
+        e2e_strict = {"value": cells / dt_s, "unit": UNIT, "ms_per_step": dt_s * 1e3, "h2d_bytes_per_step": 8 * n * k,
+                      "d2h_bytes_per_step": sum(o.numel() for o in outs) * 8 + (32 << CAP_HEIGHT),
+                      "api": "b200zkp_commit_copy_back: coefficients + row-major leaves + digests + cap to pinned host memory"}
+        del outs
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         N_local = lay["N_local"]
@@ -312,6 +334,12 @@ def run_b200(args):
             "poseidon_perms_per_s": perms / (ms_step * 1e-3),
             "cap_checksum": cap_checksum,
         }
+        if e2e_strict:
+            line["e2e_strict"] = e2e_strict
+        if world == 1 and n_log == N_LOG and k == K:
+            # dram__bytes_read.sum + dram__bytes_write.sum of the leaf hash at this size, ncu --set full capture
+            # profiles/r1_leaf_kernel_ncu_details.txt (9.09 GB + 0.27 GB)
+            line["roofline"]["traffic"] = 9.36e9
         if world == 1:
             gips = {}
             for kind, name in ((0, "imad_wide"), (1, "iadd3"), (2, "imad"), (3, "imad_wide+lop3"), (4, "lop3"), (5, "imad_hi"), (6, "imad+lop3"), (7, "iadd3_carry_pair"), (8, "imad_wide_noacc")):

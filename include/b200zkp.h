@@ -87,6 +87,14 @@ int b200zkp_commit_from_values(b200zkp_ctx* ctx, const uint64_t* values, uint32_
 int b200zkp_commit_from_coeffs(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,
                                uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
                                b200zkp_batch** out);
+/* Strict drop-in ("copy-back") commit in one call: what plonky2's struct fields need, written to host buffers while the
+ * device is still hashing (coefficients and row-major leaves stream out on a copy stream during the leaf hash).
+ * Any of coeffs_out (k*n), leaves_out (N*(k+salt)), digests_out (4*2*(N-2^h)), cap_out (4*2^h) may be NULL;
+ * out may be NULL (nothing is kept on the device) or receives the batch handle as in b200zkp_commit_from_values.
+ * Use pinned host buffers (b200zkp_host_alloc) for full PCIe speed. */
+int b200zkp_commit_copy_back(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,
+                             uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, uint64_t* coeffs_out,
+                             uint64_t* leaves_out, uint64_t* digests_out, uint64_t* cap_out, b200zkp_batch** out);
 void b200zkp_batch_free(b200zkp_batch* b);
 /* shape: n_log, k, rate_bits, cap_height, salt_size */
 int b200zkp_batch_shape(const b200zkp_batch* b, uint32_t shape[5]);
@@ -160,7 +168,8 @@ int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint
 int b200zkp_dev_transpose_to_rows(b200zkp_ctx* ctx, const uint64_t* cm, uint64_t col_stride, uint32_t cols,
                                   uint64_t row0, uint64_t n_rows, uint64_t* rm);
 /* device field primitives, element-wise over `count` pairs (test probe for the carry / borrow paths):
- * op 0 mul, 1 add, 2 sub, 3 reduce128(lo = a, hi = b), 4 a + canon(b) lazily, 5 fold (a mod 2^44) + (b mod 2^44) * 2^32,
+ * op 0 mul, 1 add, 2 sub, 3 reduce128(lo = a, hi = b), 4 a + canon(b) lazily,
+ * 5 limb recombination O0 + O1*2^22 + O2*2^43 + rc with O0 = a[0:31], O1 = a[32:63], O2 = b[0:31], rc = canon(b >> 1),
  * 6 a^7, 7 (a ^ b) + a * b; every result canonical */
 int b200zkp_field_op(b200zkp_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t count, uint64_t* out);
 /* integer-pipe micro-benchmark: runs `iters` dependent-chain rounds of the chosen

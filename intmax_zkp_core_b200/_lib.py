@@ -73,6 +73,7 @@ _SIGS = {
     "b200zkp_host_free": (None, [C.c_void_p]),
     "b200zkp_commit_from_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200zkp_commit_from_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b200zkp_commit_copy_back": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200zkp_batch_free": (None, [C.c_void_p]),
     "b200zkp_batch_shape": (C.c_int, [C.c_void_p, u32p]),
     "b200zkp_batch_cap": (C.c_int, [C.c_void_p, C.c_void_p]),

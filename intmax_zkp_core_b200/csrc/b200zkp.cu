@@ -658,10 +658,18 @@ static void batch_release(b200zkp_batch* b) {
     delete b;
 }
 
+// host destinations of a copy-back commit (any may be null)
+struct CopyBack {
+    u64* coeffs = nullptr;   // k * n
+    u64* leaves = nullptr;   // N * (k + salt), row-major
+    u64* digests = nullptr;  // 4 * 2(N - 2^h)
+    u64* cap = nullptr;      // 4 * 2^h
+};
+
 static int commit_host(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log, u32 k, u32 rate_bits,
-                       u32 cap_height, const u64* salt, b200zkp_batch** out) {
-    if (!out) BAD(ctx, "null out");
-    *out = nullptr;
+                       u32 cap_height, const u64* salt, b200zkp_batch** out, const CopyBack* cb = nullptr) {
+    if (!out && !cb) BAD(ctx, "null out");
+    if (out) *out = nullptr;
     if (k == 0) BAD(ctx, "empty polynomial batch");
     if (n_log + rate_bits > 32 || rate_bits > 8) BAD(ctx, "n_log + rate_bits exceeds two-adicity");
     if (cap_height > n_log + rate_bits) BAD(ctx, "cap_height exceeds log2(LDE size)");
@@ -735,14 +743,55 @@ static int commit_host(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log
         if (rc) return fail(rc);
     }
     if (salt) rc = dev_salt_locked(ctx, (const u64*)d_salt, b->lde + (u64)k * N, N, n_log, rate_bits, 0, 1u << rate_bits);
-    if (!rc) rc = dev_merkle_locked(ctx, b->lde, /*row_stride=*/1, /*col_stride=*/N, row, N, cap_height, b->digests, b->cap);
     if (rc) return fail(rc);
-    e = cudaStreamSynchronize(ctx->stream);
+    // Copy-back (strict drop-in) mode: coefficients and row-major leaves leave the device on the copy stream while the
+    // main stream hashes — the 8N(k+salt)-byte D2H (PCIe bound) overlaps the leaf hash instead of following it.
+    void* stage = nullptr; size_t stage_b = 0;
+    if (cb && (cb->coeffs || cb->leaves)) {
+        cudaEvent_t e_lde;
+        if ((rc = get_sync_event(ctx, 1 + n_chunks, &e_lde))) return fail(rc);
+        e = cudaEventRecord(e_lde, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, e_lde, 0);
+        if (e == cudaSuccess && cb->coeffs) e = cudaMemcpyAsync(cb->coeffs, b->coeffs, b->coeffs_b, cudaMemcpyDeviceToHost, ctx->stream2);
+        if (e == cudaSuccess && cb->leaves) {
+            u64 chunk_rows = std::min<u64>(N, std::max<u64>(1, ((u64)256 << 20) / ((u64)row * 8)));
+            stage_b = (size_t)chunk_rows * row * 8;
+            if ((rc = dev_alloc(ctx, stage_b, &stage))) return fail(rc);
+            cudaStream_t main_stream = ctx->stream;
+            ctx->stream = ctx->stream2;     // transposes are issued on the copy stream (same order as their D2H)
+            for (u64 r0 = 0; r0 < N && !rc && e == cudaSuccess; r0 += chunk_rows) {
+                u64 nr = std::min(chunk_rows, N - r0);
+                rc = dev_transpose_rows_locked(ctx, b->lde, N, row, r0, nr, (u64*)stage);
+                if (!rc) e = cudaMemcpyAsync(cb->leaves + r0 * row, stage, (size_t)nr * row * 8, cudaMemcpyDeviceToHost, ctx->stream2);
+            }
+            ctx->stream = main_stream;
+            if (rc) { dev_release(ctx, stage, stage_b); return fail(rc); }
+        }
+        if (e != cudaSuccess) { ctx->err = std::string("copy-back: ") + cudaGetErrorString(e); (void)cudaGetLastError(); dev_release(ctx, stage, stage_b); return fail(B200ZKP_ERR_CUDA); }
+    }
+    rc = dev_merkle_locked(ctx, b->lde, /*row_stride=*/1, /*col_stride=*/N, row, N, cap_height, b->digests, b->cap);
+    if (rc) { dev_release(ctx, stage, stage_b); return fail(rc); }
+    if (cb && cb->digests && b->digests_b) e = cudaMemcpyAsync(cb->digests, b->digests, b->digests_b, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && cb && cb->cap) e = cudaMemcpyAsync(cb->cap, b->cap, b->cap_b, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream2);
+    dev_release(ctx, stage, stage_b);
     if (e != cudaSuccess) { ctx->err = std::string("commit: ") + cudaGetErrorString(e); return fail(B200ZKP_ERR_CUDA); }
     dev_release(ctx, d_in, in_b);
     dev_release(ctx, d_salt, salt_b);
-    *out = b;
+    if (out) *out = b;
+    else batch_release(b);
     return 0;
+}
+
+extern "C" int b200zkp_commit_copy_back(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,
+                                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, uint64_t* coeffs_out,
+                                        uint64_t* leaves_out, uint64_t* digests_out, uint64_t* cap_out, b200zkp_batch** out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    CopyBack cb;
+    cb.coeffs = (u64*)coeffs_out; cb.leaves = (u64*)leaves_out; cb.digests = (u64*)digests_out; cb.cap = (u64*)cap_out;
+    return commit_host(ctx, (const u64*)in, is_coeffs, n_log, k, rate_bits, cap_height, (const u64*)salt, out, &cb);
 }
 
 extern "C" int b200zkp_commit_from_values(b200zkp_ctx* ctx, const uint64_t* values, uint32_t n_log, uint32_t k,
@@ -1097,7 +1146,7 @@ __global__ void field_op_kernel(int op, const u64* __restrict__ a, const u64* __
         case 2: r = gl::sub(gl::canon(x), gl::canon(y)); break;
         case 3: r = gl::canon(gl::reduce128(x, y)); break;         // (hi = y : lo = x) mod p
         case 4: r = gl::canon(gl::add_nc(x, gl::canon(y))); break; // arbitrary + canonical
-        case 5: r = gl::canon(poseidon::fold_lh(x & 0xFFFFFFFFFFFull, y & 0xFFFFFFFFFFFull)); break;  // L + H * 2^32, L,H < 2^44
+        case 5: r = gl::canon(poseidon::combine3((u32)x & 0x7FFFFFFFu, (u32)(x >> 32) & 0x7FFFFFFFu, (u32)y & 0x7FFFFFFFu, gl::canon(y >> 1))); break;
         case 6: r = gl::canon(poseidon::sbox(x)); break;
         case 7: r = gl::canon(poseidon::mul_add_nc(x, y, x ^ y)); break;   // (x ^ y) + x * y
         default: break;

@@ -431,7 +431,7 @@ class PolynomialBatch:
 
     @classmethod
     def _commit(cls, data, is_coeffs: bool, rate_bits: int, blinding: bool, cap_height: int,
-                salt, ctx: Optional[Context]):
+                salt, ctx: Optional[Context], copy_back: bool = False):
         ctx = ctx or default_context()
         x = _u64(data)
         if x.ndim != 2 or x.shape[0] == 0:
@@ -460,27 +460,42 @@ class PolynomialBatch:
         self.num_polys = k
         self.salt_size = SALT_SIZE if blinding else 0
         h = C.c_void_p()
-        fn = ctx._lib.b200zkp_commit_from_coeffs if is_coeffs else ctx._lib.b200zkp_commit_from_values
-        ctx.check(fn(ctx._h, _p(x), n_log, k, rate_bits, cap_height, _p(s), C.byref(h)))
-        self._h = h
         cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
-        ctx.check(ctx._lib.b200zkp_batch_cap(h, _p(cap)))
+        if copy_back:
+            # strict drop-in: every plonky2 struct field is materialised on the host in the same call, the D2H of
+            # coefficients and leaves overlapping the leaf hash (b200zkp_commit_copy_back)
+            polys = np.empty((k, n), dtype=np.uint64)
+            leaves = np.empty((N, k + self.salt_size), dtype=np.uint64)
+            digests = np.empty((2 * (N - (1 << cap_height)), 4), dtype=np.uint64)
+            ctx.check(ctx._lib.b200zkp_commit_copy_back(ctx._h, _p(x), int(is_coeffs), n_log, k, rate_bits, cap_height, _p(s),
+                                                        _p(polys), _p(leaves), _p(digests) if digests.size else None, _p(cap),
+                                                        C.byref(h)))
+        else:
+            fn = ctx._lib.b200zkp_commit_from_coeffs if is_coeffs else ctx._lib.b200zkp_commit_from_values
+            ctx.check(fn(ctx._h, _p(x), n_log, k, rate_bits, cap_height, _p(s), C.byref(h)))
+            ctx.check(ctx._lib.b200zkp_batch_cap(h, _p(cap)))
+        self._h = h
         self._cap = MerkleCap(cap)
         self.merkle_tree = _BatchMerkleTree(self)
         self._polys = None
+        if copy_back:
+            self._polys = polys
+            self.merkle_tree._leaves = leaves
+            self.merkle_tree._digests = digests
         return self
 
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
-                    fft_root_table=None, salt=None, ctx: Optional[Context] = None) -> "PolynomialBatch":
+                    fft_root_table=None, salt=None, ctx: Optional[Context] = None, copy_back: bool = False) -> "PolynomialBatch":
         """values: (k, n) — k PolynomialValues of n points each.  `timing` / `fft_root_table` are accepted
-        for signature parity (the ctx owns the root tables)."""
-        return cls._commit(values, False, rate_bits, blinding, cap_height, salt, ctx)
+        for signature parity (the ctx owns the root tables).  copy_back=True fills polynomials / leaves / digests on
+        the host in the same call (strict drop-in); otherwise they stay in HBM until an accessor asks."""
+        return cls._commit(values, False, rate_bits, blinding, cap_height, salt, ctx, copy_back)
 
     @classmethod
     def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
-                    fft_root_table=None, salt=None, ctx: Optional[Context] = None) -> "PolynomialBatch":
-        return cls._commit(polynomials, True, rate_bits, blinding, cap_height, salt, ctx)
+                    fft_root_table=None, salt=None, ctx: Optional[Context] = None, copy_back: bool = False) -> "PolynomialBatch":
+        return cls._commit(polynomials, True, rate_bits, blinding, cap_height, salt, ctx, copy_back)
 
     @property
     def polynomials(self) -> np.ndarray:

@@ -42,8 +42,8 @@ def test_field_primitives_edge_cases(z, ctx):
     assert run(2) == [(x - y) % P for x, y in zip(A, B)]
     assert run(3) == [(x + (y << 64)) % P for x, y in zip(A, B)]
     assert run(4) == [(x + y) % P for x, y in zip(A, B)]
-    m44 = (1 << 44) - 1
-    assert run(5) == [((x & m44) + ((y & m44) << 32)) % P for x, y in zip(A, B)]
+    m31 = (1 << 31) - 1
+    assert run(5) == [((x & m31) + (((x >> 32) & m31) << 22) + ((y & m31) << 43) + ((y >> 1) % P)) % P for x, y in zip(A, B)]
     assert run(6) == [pow(x, 7, P) for x in A]
     assert run(7) == [((x ^ y) + x * y) % P for x, y in zip(A, B)]
 
@@ -161,6 +161,21 @@ def test_blinding_with_given_salt(z, ctx, oracle, n_log, k, r, h):
     ref = oracle.commit(v, r, h, salt=salt)
     _compare(b, ref, k)
     assert (b.get_lde_values(3) == ref["leaves"][bitrev(3, n_log + r)][:k]).all()   # salt stripped
+
+
+@pytest.mark.parametrize("n_log,k,r,h,coeffs,salted", [(10, 135, 3, 4, False, False), (13, 20, 3, 4, False, False),
+                                                        (9, 16, 3, 4, True, False), (6, 5, 2, 3, False, True), (0, 3, 3, 3, False, False)])
+def test_copy_back_commit(z, ctx, oracle, n_log, k, r, h, coeffs, salted):
+    """b200zkp_commit_copy_back: every plonky2 field on the host in one call (D2H overlapped with hashing)."""
+    v = oracle.synthetic_values(k, 1 << n_log, seed=11)
+    salt = oracle.synthetic_values(4, 1 << (n_log + r), seed=13) if salted else None
+    ctor = z.PolynomialBatch.from_coeffs if coeffs else z.PolynomialBatch.from_values
+    b = ctor(v, r, salted, h, salt=salt, ctx=ctx, copy_back=True)
+    assert b._polys is not None and b.merkle_tree._leaves is not None      # filled by the call itself
+    _compare(b, oracle.commit(v, r, h, is_coeffs=coeffs, salt=salt), k)
+    # the device copy stays usable
+    rows, _ = b.rows([0, (1 << (n_log + r)) - 1])
+    assert (rows[0] == b.merkle_tree.leaves[0]).all() and (rows[1] == b.merkle_tree.leaves[-1]).all()
 
 
 def test_golden_vectors_on_gpu(z, ctx, oracle, golden):
