@@ -129,12 +129,28 @@ class ShardedCommitment:
                 # the LDE buffer is free until step 3: use it as the transform scratch
                 ctx.check(lib.b200zkp_dev_intt(ctx._h, _ptr(values_local), n, _ptr(mine), n, _ptr(self.lde),
                                                self.n_log, kl))
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.coeffs_all, mine, group=self.group)
         b0 = self.rank * self.blocks_per_rank
-        ctx.check(lib.b200zkp_dev_lde_merkle(ctx._h, _ptr(self.coeffs_all), n, _ptr(self.lde), self.N_local, self.n_log,
-                                             self.k, self.rate_bits, b0, b0 + self.blocks_per_rank, self.cap_height_local,
-                                             _ptr(self.digests), _ptr(self.cap_local)))
+        b1 = b0 + self.blocks_per_rank
+        N_loc = self.N_local
+
+        def lde_cols(c0, c1):
+            if c1 > c0:
+                ctx.check(lib.b200zkp_dev_lde(ctx._h, C.c_void_p(self.coeffs_all.data_ptr() + 8 * n * c0), n,
+                                              C.c_void_p(self.lde.data_ptr() + 8 * N_loc * c0), N_loc, self.n_log,
+                                              c1 - c0, self.rate_bits, b0, b1))
+
+        if self.world > 1:
+            # the all-gather of the other ranks' coefficients (NCCL, its own stream) overlaps the coset transforms of
+            # the columns this rank already holds
+            work = dist.all_gather_into_tensor(self.coeffs_all, mine, group=self.group, async_op=True)
+            lde_cols(self.col_begin, self.col_end)
+            work.wait()
+            lde_cols(0, self.col_begin)
+            lde_cols(self.col_end, self.k)
+        else:
+            lde_cols(0, self.k)
+        ctx.check(lib.b200zkp_dev_merkle(ctx._h, _ptr(self.lde), 1, N_loc, self.k, N_loc, self.cap_height_local,
+                                         _ptr(self.digests), _ptr(self.cap_local)))
         if self.world > 1:
             dist.all_gather_into_tensor(self.cap, self.cap_local, group=self.group)
         else:

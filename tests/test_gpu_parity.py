@@ -119,6 +119,18 @@ def test_transforms_match_oracle(z, ctx, oracle, n_log):
         assert (z.coset_lde_batch(v, r, ctx) == np.stack([oracle.coset_lde(c, r) for c in v])).all()
 
 
+@pytest.mark.parametrize("n_log", [21, 24, 25])
+def test_transforms_three_and_four_passes(z, ctx, oracle, n_log):
+    """3 passes of 7/8 bits (2^21, 2^24: config #5's column size) and 4 passes (2^25) against the oracle's radix-2 transform."""
+    rng = np.random.default_rng(n_log)
+    v = rng.integers(0, 2**64, size=(1, 1 << n_log), dtype=np.uint64)
+    assert (z.fft_batch(v, ctx)[0] == oracle.fft(v[0])).all()
+    assert (z.ifft_batch(v, ctx)[0] == oracle.ifft(v[0])).all()
+    if n_log == 21:
+        lde = z.coset_lde_batch(v, 1, ctx)[0]
+        assert (lde == oracle.coset_lde(v[0], 1)).all()
+
+
 def test_transform_roundtrip_large(z, ctx):
     rng = np.random.default_rng(31)
     v = rand_field(rng, (3, 1 << 20))
@@ -324,3 +336,28 @@ def test_full_size_properties(z, ctx, oracle):
     tctx.synchronize()
     assert (out.cap.cpu().numpy().view(np.uint64) == cap).all()
     tctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ property-based
+def test_hypothesis_commit_shapes(z, ctx, oracle):
+    """Random (n, k, rate_bits, cap_height, from_values / from_coeffs, salted) with full-range u64 inputs
+    (non-canonical values included) against the oracle — SURVEY.md section 4(d)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 7), st.integers(1, 12), st.integers(0, 3), st.integers(0, 10), st.booleans(), st.booleans(),
+           st.integers(0, 2**32 - 1))
+    def run(n_log, k, r, h, coeffs, salted, seed):
+        h = min(h, n_log + r)
+        rng = np.random.default_rng(seed)
+        v = rng.integers(0, 2**64, size=(k, 1 << n_log), dtype=np.uint64)
+        salt = rng.integers(0, 2**64, size=(4, 1 << (n_log + r)), dtype=np.uint64) if salted else None
+        ctor = z.PolynomialBatch.from_coeffs if coeffs else z.PolynomialBatch.from_values
+        b = ctor(v, r, salted, h, salt=salt, ctx=ctx)
+        ref = oracle.commit(v, r, h, is_coeffs=coeffs, salt=salt)
+        assert (b.merkle_tree.cap.elements == ref["cap"]).all()
+        assert (b.merkle_tree.leaves == ref["leaves"]).all()
+        assert (b.polynomials == ref["coeffs"]).all()
+        assert (b.merkle_tree.digests == ref["digests"]).all()
+
+    run()
