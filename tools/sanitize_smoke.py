@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Small commitments + accessors for compute-sanitizer (memcheck / racecheck) runs on the GPU box:
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import intmax_zkp_core_b200 as z
+from oracle import oracle as O
+
+ctx = z.Context(0)
+for (n_log, k, r, h, coeffs, salted) in [(0, 3, 3, 2, False, False), (3, 9, 3, 2, False, False), (7, 5, 1, 0, True, False),
+                                         (9, 20, 3, 4, False, True), (10, 135, 3, 4, False, False), (13, 4, 2, 6, False, False)]:
+    v = O.synthetic_values(k, 1 << n_log, seed=1)
+    salt = O.synthetic_values(4, 1 << (n_log + r), seed=2) if salted else None
+    ctor = z.PolynomialBatch.from_coeffs if coeffs else z.PolynomialBatch.from_values
+    b = ctor(v, r, salted, h, salt=salt, ctx=ctx, copy_back=(n_log == 9))
+    ref = O.commit(v, r, h, is_coeffs=coeffs, salt=salt)
+    assert (b.merkle_tree.cap.elements == ref["cap"]).all()
+    assert (b.merkle_tree.leaves == ref["leaves"]).all()
+    assert (b.merkle_tree.digests == ref["digests"]).all()
+    N = 1 << (n_log + r)
+    rows, sib = b.rows([0, N - 1, N // 2])
+    assert (rows[1] == ref["leaves"][N - 1]).all()
+    b.get_lde_values(0)
+x = np.arange(5 * 64, dtype=np.uint64).reshape(5, 64)
+assert (z.fft_batch(z.ifft_batch(x, ctx), ctx) == x).all()
+z.coset_lde_batch(x, 2, ctx)
+t = z.MerkleTree.new(np.arange(64 * 7, dtype=np.uint64).reshape(64, 7), 2, ctx=ctx)
+t.prove(5); t.digests
+z.PoseidonHash.hash_no_pad_batch(np.arange(40, dtype=np.uint64).reshape(4, 10), ctx)
+print("sanitize smoke ok, launches:", ctx.launch_count)
+ctx.close()
