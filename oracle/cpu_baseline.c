@@ -60,8 +60,10 @@ static inline void mds(uint64_t s[WIDTH], const uint64_t* addc) {
      * mds_row_shf works on the same idea); doubled array avoids the index wrap */
     uint64_t lo[2 * WIDTH], hi[2 * WIDTH];
     for (int i = 0; i < WIDTH; i++) { lo[i] = lo[i + WIDTH] = (uint32_t)s[i]; hi[i] = hi[i + WIDTH] = s[i] >> 32; }
+#pragma GCC unroll 12
     for (int r = 0; r < WIDTH; r++) {
         uint64_t L = 0, H = 0;
+#pragma GCC unroll 12
         for (int i = 0; i < WIDTH; i++) { L += lo[i + r] * CIRC[i]; H += hi[i + r] * CIRC[i]; }
         if (r == 0) { L += lo[0] * 8; H += hi[0] * 8; }
         u128 acc = (u128)L + ((u128)H << 32);
@@ -72,6 +74,7 @@ static inline void mds(uint64_t s[WIDTH], const uint64_t* addc) {
 void cpub_permute(uint64_t s[WIDTH]) {
     for (int i = 0; i < WIDTH; i++) s[i] = red128((u128)s[i] + RC_FULL[i]);
     for (int r = 0; r < 4; r++) {
+#pragma GCC unroll 12
         for (int i = 0; i < WIDTH; i++) s[i] = sbox(s[i]);
         mds(s, r < 3 ? &RC_FULL[(r + 1) * WIDTH] : FAST_FIRST);
     }
@@ -87,12 +90,15 @@ void cpub_permute(uint64_t s[WIDTH]) {
     for (int i = 0; i < 22; i++) {
         uint64_t s0 = red128((u128)sbox(s[0]) + FAST_POST[i]);
         acc160_t a = {(u128)s0 * 25, 0};
+#pragma GCC unroll 11
         for (int j = 0; j < WIDTH - 1; j++) acc_mac(&a, FAST_VHAT[i * (WIDTH - 1) + j], s[1 + j]);
+#pragma GCC unroll 11
         for (int j = 0; j < WIDTH - 1; j++) s[1 + j] = red128((u128)FAST_WHAT[i * (WIDTH - 1) + j] * s0 + s[1 + j]);
         s[0] = acc_reduce(&a);
     }
     for (int i = 0; i < WIDTH; i++) s[i] = red128((u128)s[i] + RC_FULL[4 * WIDTH + i]);
     for (int r = 4; r < 8; r++) {
+#pragma GCC unroll 12
         for (int i = 0; i < WIDTH; i++) s[i] = sbox(s[i]);
         mds(s, r < 7 ? &RC_FULL[(r + 1) * WIDTH] : NULL);
     }
