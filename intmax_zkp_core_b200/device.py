@@ -114,10 +114,37 @@ class ShardedCommitment:
     def local_columns(self) -> int:
         return max(self.col_end - self.col_begin, 0)
 
+    def run_from_host(self, host_values, staging, n_chunks: int = 4):
+        """End-to-end variant: `host_values` is this rank's pinned (kp, n) column shard, `staging` a (kp, n) device
+        tensor.  Column chunks cross PCIe on a side stream while the previous chunk is inverse-transformed."""
+        import torch
+        ctx, lib = self.ctx, self.ctx._lib
+        n = 1 << self.n_log
+        kl = self.local_columns
+        mine = self.coeffs_all[self.rank * self.kp:(self.rank + 1) * self.kp]
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=staging.device)
+        main = torch.cuda.current_stream()
+        self._copy_stream.wait_stream(main)          # staging may still be read by the previous step
+        per = max(1, (kl + n_chunks - 1) // n_chunks)
+        events = []
+        for c0 in range(0, kl, per):
+            c1 = min(kl, c0 + per)
+            with torch.cuda.stream(self._copy_stream):
+                staging[c0:c1].copy_(host_values[c0:c1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            events.append((c0, c1, ev))
+        for c0, c1, ev in events:
+            main.wait_event(ev)
+            # scratch: this chunk's share of the (still unused) LDE buffer
+            ctx.check(lib.b200zkp_dev_intt(ctx._h, C.c_void_p(staging.data_ptr() + 8 * n * c0), n,
+                                           C.c_void_p(mine.data_ptr() + 8 * n * c0), n,
+                                           C.c_void_p(self.lde.data_ptr() + 8 * n * c0), self.n_log, c1 - c0))
+        return self._finish()
+
     def run(self, values_local, is_coeffs: bool = False):
         """values_local: (kp, n) device tensor, this rank's columns (rows past local_columns ignored)."""
-        import torch
-        import torch.distributed as dist
         ctx, lib = self.ctx, self.ctx._lib
         n = 1 << self.n_log
         mine = self.coeffs_all[self.rank * self.kp:(self.rank + 1) * self.kp]
@@ -129,6 +156,15 @@ class ShardedCommitment:
                 # the LDE buffer is free until step 3: use it as the transform scratch
                 ctx.check(lib.b200zkp_dev_intt(ctx._h, _ptr(values_local), n, _ptr(mine), n, _ptr(self.lde),
                                                self.n_log, kl))
+        return self._finish()
+
+    def _finish(self):
+        """all-gather of the coefficients, this rank's coset blocks, its cap subtrees, all-gather of the cap."""
+        import torch
+        import torch.distributed as dist
+        ctx, lib = self.ctx, self.ctx._lib
+        n = 1 << self.n_log
+        mine = self.coeffs_all[self.rank * self.kp:(self.rank + 1) * self.kp]
         b0 = self.rank * self.blocks_per_rank
         b1 = b0 + self.blocks_per_rank
         N_loc = self.N_local
