@@ -113,6 +113,57 @@ int b200zkp_batch_lde_values(b200zkp_batch* b, uint64_t index, uint64_t step, ui
 int b200zkp_batch_device_ptrs(b200zkp_batch* b, const uint64_t** coeffs, const uint64_t** lde,
                               const uint64_t** digests, const uint64_t** cap);
 
+/* ---- openings (row N3): OpeningSet::new's evaluation loop ----------------------------------- */
+/* out[c] = p_c(zeta) for the k polynomials of the batch, zeta and the results in the quadratic extension
+ * F_p[X]/(X^2 - 7) as (real, imaginary) pairs: zeta[2] -> out[k*2].  Runs on the coefficients already in HBM. */
+int b200zkp_batch_eval_ext2(b200zkp_batch* b, const uint64_t zeta[2], uint64_t* out);
+/* same on caller-owned device buffers (coeffs [k][col_stride], out_dev k*2 on the device; async on the ctx stream) */
+int b200zkp_dev_eval_ext2(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t col_stride, uint32_t n_log, uint32_t k,
+                          const uint64_t zeta[2], uint64_t* out_dev);
+
+/* ---- opening proof (rows N2 + N3): PolynomialBatch::prove_openings / fri_proof ---------------- */
+/* Replaces the data-parallel steps of plonky2 @ f99ed9c  fri/oracle.rs `prove_openings`, fri/prover.rs
+ * `fri_committed_trees`, `fri_proof_of_work`, `fri_prover_query_round`; the Fiat-Shamir challenger stays with the caller,
+ * who feeds each challenge back in (alpha, the betas) exactly where plonky2 draws it.  All big data stays in HBM.
+ *
+ * b200zkp_fri_begin: final_poly = sum over opening points b of  alpha^(..) * (F_b(X) - F_b(z_b)) / (X - z_b),
+ * F_b = sum_j alpha^j f_bj (ReducingFactor::reduce_polys_base, divide_by_linear, shift_poly), multiplied by X when
+ * B200ZKP_FRI_MUL_BY_X is set (the 2022 plonky2 does), then its LDE on the coset 7<w_N> in bit-reversed
+ * order.  oracles: batches of equal n_log and rate_bits on this ctx; point b opens polynomials
+ * (poly_oracle[i], poly_index[i]) for the next point_n_polys[b] entries i of the concatenated lists;
+ * points: n_points * 2 words. */
+typedef struct b200zkp_fri b200zkp_fri;
+enum { B200ZKP_FRI_MUL_BY_X = 1 };
+int b200zkp_fri_begin(b200zkp_ctx* ctx, b200zkp_batch* const* oracles, uint32_t n_oracles, uint32_t n_points,
+                      const uint64_t* points, const uint32_t* point_n_polys, const uint32_t* poly_oracle,
+                      const uint32_t* poly_index, const uint64_t alpha[2], uint32_t flags, b200zkp_fri** out);
+/* same state from extension coefficients given by the caller: coeffs n * 2 words, (real, imaginary) interleaved */
+int b200zkp_fri_begin_from_coeffs(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t rate_bits,
+                                  b200zkp_fri** out);
+void b200zkp_fri_free(b200zkp_fri* f);
+/* shape: degree log n_log, rate_bits, log2 of the current (folded) LDE size, committed layers */
+int b200zkp_fri_shape(const b200zkp_fri* f, uint32_t shape[4]);
+/* current coefficients, zero-padded to the current LDE size: 2^shape[2] * 2 words interleaved */
+int b200zkp_fri_coeffs(b200zkp_fri* f, uint64_t* out);
+/* one reduction layer of fri_committed_trees: MerkleTree::new over the bit-reversed values chunked by 2^arity_bits
+ * (leaf = 2 * arity words); cap_out 4 * 2^cap_height.  Follow with b200zkp_fri_fold(beta): coefficients are folded
+ * (reduce_with_powers over chunks of arity), the coset shift is raised to the arity, values = coset_fft. */
+int b200zkp_fri_commit_layer(b200zkp_fri* f, uint32_t arity_bits, uint32_t cap_height, uint64_t* cap_out);
+int b200zkp_fri_fold(b200zkp_fri* f, const uint64_t beta[2]);
+/* final_poly: the current coefficients truncated to len >> rate_bits: (2^shape[2] >> rate_bits) * 2 words */
+int b200zkp_fri_final_poly(b200zkp_fri* f, uint64_t* out);
+/* FriQueryStep for leaves idx of committed layer `layer`: evals n_idx * 2 * arity words (tree.get),
+ * siblings n_idx * (log2 leaves - cap_height) * 4 (tree.prove); either may be NULL */
+int b200zkp_fri_query(b200zkp_fri* f, uint32_t layer, const uint64_t* idx, uint64_t n_idx, uint64_t* evals,
+                      uint64_t* siblings);
+/* fri_proof_of_work: the SMALLEST w < max_candidates (0: the whole field) for which
+ * permute(state with state[witness_pos] = w)[response_pos] has >= min_leading_zeros leading zero bits as a canonical
+ * u64 (plonky2 grinds with rayon find_any, so any witness verifies; the smallest makes proofs reproducible).
+ * hash_no_pad(current_hash || w).elements[0]: state = (h0..h3, 0 x 8), witness_pos 4, response_pos 0.
+ * Returns B200ZKP_ERR_UNSUPPORTED when no candidate below the bound qualifies. */
+int b200zkp_pow_grind(b200zkp_ctx* ctx, const uint64_t state[12], uint32_t witness_pos, uint32_t response_pos,
+                      uint32_t min_leading_zeros, uint64_t max_candidates, uint64_t* witness);
+
 /* ---- MerkleTree::new (host buffers) -------------------------------------------------------- */
 /* leaves: n_leaves rows of leaf_len elements, row-major.  hash_or_noop: leaf_len <= 4 is not hashed. */
 int b200zkp_merkle_new(b200zkp_ctx* ctx, const uint64_t* leaves, uint64_t n_leaves, uint32_t leaf_len,

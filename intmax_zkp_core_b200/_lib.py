@@ -83,6 +83,19 @@ _SIGS = {
     "b200zkp_batch_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zkp_batch_lde_values": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b200zkp_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "b200zkp_batch_eval_ext2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "b200zkp_dev_eval_ext2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200zkp_fri_begin": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "b200zkp_fri_begin_from_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "b200zkp_fri_free": (None, [C.c_void_p]),
+    "b200zkp_fri_shape": (C.c_int, [C.c_void_p, u32p]),
+    "b200zkp_fri_coeffs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_fri_commit_layer": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "b200zkp_fri_fold": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_fri_final_poly": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b200zkp_fri_query": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "b200zkp_pow_grind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u64p]),
     "b200zkp_merkle_new": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "b200zkp_tree_free": (None, [C.c_void_p]),
     "b200zkp_tree_cap": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -14,12 +14,16 @@
 
 #include "merkle_kernels.cuh"
 #include "ntt_kernels.cuh"
+#include "eval_kernels.cuh"
+#include "fri_kernels.cuh"
 #include "host_plan.hpp"
 
 using gl::u32;
 using gl::u64;
 
 // ------------------------------------------------------------------------------------------------
+static inline u64 gl_host_canon(u64 a) { return a >= hostgl::P ? a - hostgl::P : a; }
+
 struct TwoLevel {
     u64* lo = nullptr;
     u64* hi = nullptr;
@@ -42,6 +46,7 @@ struct b200zkp_ctx {
     std::map<u64, Images> twimg;                        // (n_log<<8 | dir<<1 | bitrev_out) -> twiddle image per pass
     std::map<u64, u64*> coset_scale;                    // (n_log<<8 | rate_bits) -> [2^rate_bits][n] shift powers
     std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
+    std::map<std::pair<u64, u32>, u64*> power_scale;    // (shift, bits) -> shift^i, i < 2^bits (FRI layer cosets)
     std::multimap<size_t, void*> pool;                  // cached device allocations
     std::vector<void*> table_allocs;
     // second, higher-priority stream: coset transforms run here while finished blocks are hashed on `stream`
@@ -931,6 +936,414 @@ extern "C" int b200zkp_batch_device_ptrs(b200zkp_batch* b, const uint64_t** coef
     if (lde) *lde = (const uint64_t*)b->lde;
     if (digests) *digests = (const uint64_t*)b->digests;
     if (cap) *cap = (const uint64_t*)b->cap;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ openings (N3)
+static int dev_eval_ext2_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 col_stride, u32 n_log, u32 k, const u64 zeta[2],
+                                u64* d_out /* k*2 */) {
+    if (!k) return 0;
+    if (n_log > 32) BAD(ctx, "n_log out of range");
+    u64 n = (u64)1 << n_log;
+    evalk::Ext2 z; z.a = gl_host_canon(zeta[0]); z.b = gl_host_canon(zeta[1]);
+    // segments: enough CTAs to fill the GPU (~4 per SM), at least 1024 coefficients each
+    u64 want = (4 * 148 + k - 1) / k;
+    u64 n_seg = 1;
+    while (n_seg < want && (n / (n_seg * 2)) >= 1024) n_seg *= 2;
+    u64 seg_len = n / n_seg;
+    void* d_part = nullptr; size_t part_b = (size_t)k * n_seg * sizeof(evalk::Ext2);
+    TRY(dev_alloc(ctx, part_b, &d_part));
+    dim3 grid((unsigned)n_seg, k);
+    evalk::eval_segments_kernel<<<grid, evalk::EVAL_THREADS, 0, ctx->stream>>>(coeffs, col_stride, n, seg_len, z, (evalk::Ext2*)d_part);
+    ctx->launches++;
+    evalk::eval_combine_kernel<<<(k + 127) / 128, 128, 0, ctx->stream>>>((const evalk::Ext2*)d_part, (u32)n_seg, seg_len, k, z, (evalk::Ext2*)d_out);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    dev_release(ctx, d_part, part_b);    // stream-ordered reuse on the same ctx
+    if (e != cudaSuccess) { ctx->err = std::string("eval: ") + cudaGetErrorString(e); return B200ZKP_ERR_CUDA; }
+    return 0;
+}
+
+extern "C" int b200zkp_dev_eval_ext2(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t col_stride, uint32_t n_log, uint32_t k,
+                                     const uint64_t zeta[2], uint64_t* out_dev) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!coeffs || !zeta || !out_dev) BAD(ctx, "null buffer");
+    return dev_eval_ext2_locked(ctx, (const u64*)coeffs, col_stride, n_log, k, (const u64*)zeta, (u64*)out_dev);
+}
+
+extern "C" int b200zkp_batch_eval_ext2(b200zkp_batch* b, const uint64_t zeta[2], uint64_t* out) {
+    if (!b || !zeta || !out) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_ctx* ctx = b->ctx;
+    Guard g(ctx);
+    void* d_out = nullptr; size_t out_b = (size_t)b->k * 16;
+    TRY(dev_alloc(ctx, out_b, &d_out));
+    int rc = dev_eval_ext2_locked(ctx, b->coeffs, (u64)1 << b->n_log, b->n_log, b->k, (const u64*)zeta, (u64*)d_out);
+    if (!rc) rc = d2h(ctx, out, d_out, out_b);
+    dev_release(ctx, d_out, out_b);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ opening proof (N2 + N3)
+struct HostExt { u64 a, b; };
+static inline u64 host_add(u64 x, u64 y) { u64 s = x + y; return (s < x || s >= hostgl::P) ? s - hostgl::P : s; }
+static inline HostExt host_ext_mul(HostExt x, HostExt y) {
+    HostExt r;
+    r.a = host_add(hostgl::mul(x.a, y.a), hostgl::mul(7, hostgl::mul(x.b, y.b)));
+    r.b = host_add(hostgl::mul(x.a, y.b), hostgl::mul(x.b, y.a));
+    return r;
+}
+static inline HostExt host_ext_pow(HostExt x, u64 e) {
+    HostExt r{1, 0};
+    while (e) { if (e & 1) r = host_ext_mul(r, x); x = host_ext_mul(x, x); e >>= 1; }
+    return r;
+}
+static inline evalk::Ext2 to_dev(HostExt x) { evalk::Ext2 r; r.a = x.a; r.b = x.b; return r; }
+
+struct FriLayer {
+    u64 *rows = nullptr, *digests = nullptr, *cap = nullptr;
+    size_t rows_b = 0, digests_b = 0, cap_b = 0;
+    u32 arity_bits = 0, cap_height = 0;
+    u64 n_leaves = 0;
+};
+
+struct b200zkp_fri {
+    b200zkp_ctx* ctx = nullptr;
+    u32 n_log = 0, rate_bits = 0;
+    u32 cur_log = 0;          // log2 of the current (folded) LDE size
+    u64 shift = 7;            // coset shift of the current values
+    u64* coef[2] = {};        // ping-pong coefficient planes; coef[i] = [2][cap_i], plane stride cap_i
+    size_t coef_b[2] = {};
+    u64 coef_stride[2] = {};
+    int cur = 0;
+    u64* values = nullptr;    // [2][N] planes, bit-reversed values of the current layer
+    size_t values_b = 0;
+    u64 N = 0;
+    bool values_ready = false;
+    int pending_arity_bits = -1;
+    std::vector<FriLayer> layers;
+};
+
+static void fri_release(b200zkp_fri* f) {
+    b200zkp_ctx* ctx = f->ctx;
+    for (int i = 0; i < 2; i++) dev_release(ctx, f->coef[i], f->coef_b[i]);
+    dev_release(ctx, f->values, f->values_b);
+    for (auto& L : f->layers) {
+        dev_release(ctx, L.rows, L.rows_b);
+        dev_release(ctx, L.digests, L.digests_b);
+        dev_release(ctx, L.cap, L.cap_b);
+    }
+    delete f;
+}
+
+static int fri_alloc_state(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, b200zkp_fri** out) {
+    if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "n_log + rate_bits exceeds two-adicity");
+    b200zkp_fri* f = new (std::nothrow) b200zkp_fri();
+    if (!f) return B200ZKP_ERR_OOM;
+    f->ctx = ctx; f->n_log = n_log; f->rate_bits = rate_bits; f->cur_log = n_log + rate_bits;
+    f->N = (u64)1 << f->cur_log;
+    f->coef_stride[0] = f->N; f->coef_stride[1] = std::max<u64>(f->N / 2, 1);
+    for (int i = 0; i < 2; i++) f->coef_b[i] = (size_t)2 * f->coef_stride[i] * 8;
+    f->values_b = (size_t)2 * f->N * 8;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, f->coef_b[0], (void**)&f->coef[0])) || (rc = dev_alloc(ctx, f->coef_b[1], (void**)&f->coef[1])) ||
+        (rc = dev_alloc(ctx, f->values_b, (void**)&f->values))) {
+        fri_release(f);
+        return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(f->coef[0], 0, f->coef_b[0], ctx->stream);
+    if (e != cudaSuccess) { ctx->err = std::string("fri: ") + cudaGetErrorString(e); fri_release(f); return B200ZKP_ERR_CUDA; }
+    *out = f;
+    return 0;
+}
+
+// powers shift^i, i < 2^bits (scale table of a coset transform), cached per ctx
+static int get_power_scale(b200zkp_ctx* ctx, u64 shift, u32 bits, const u64** out) {
+    auto key = std::make_pair(shift, bits);
+    auto it = ctx->power_scale.find(key);
+    if (it == ctx->power_scale.end()) {
+        TwoLevel t;
+        TRY(make_two_level(ctx, shift, bits, &t));
+        u64 n = (u64)1 << bits;
+        u64* d = nullptr;
+        TRY(table_alloc(ctx, n, &d));
+        ntt::build_powers_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, n, t.lo, t.hi, t.lo_bits);
+        LAUNCH_CHECK(ctx);
+        it = ctx->power_scale.emplace(key, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+// values = bit-reversed coset_fft(shift) of the current coefficients
+static int fri_compute_values(b200zkp_fri* f) {
+    b200zkp_ctx* ctx = f->ctx;
+    u64 M = (u64)1 << f->cur_log;
+    const u64* scale = nullptr;
+    TRY(get_power_scale(ctx, f->shift, f->cur_log, &scale));
+    TRY(run_transform(ctx, f->coef[f->cur], f->coef_stride[f->cur], f->values, M, nullptr, f->cur_log, 2, /*dir=*/0,
+                      /*bitrev_out=*/true, scale, 0, /*inverse_scale=*/false, /*canon_in=*/false));
+    f->values_ready = true;
+    return 0;
+}
+
+extern "C" int b200zkp_fri_begin(b200zkp_ctx* ctx, b200zkp_batch* const* oracles, uint32_t n_oracles, uint32_t n_points,
+                                 const uint64_t* points, const uint32_t* point_n_polys, const uint32_t* poly_oracle,
+                                 const uint32_t* poly_index, const uint64_t alpha_in[2], uint32_t flags, b200zkp_fri** out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!out) BAD(ctx, "null out");
+    *out = nullptr;
+    if (!oracles || !n_oracles || !n_points || !points || !point_n_polys || !poly_oracle || !poly_index || !alpha_in)
+        BAD(ctx, "null or empty argument");
+    u32 n_log = oracles[0] ? oracles[0]->n_log : 0, rate_bits = oracles[0] ? oracles[0]->rate_bits : 0;
+    for (u32 i = 0; i < n_oracles; i++) {
+        if (!oracles[i] || oracles[i]->ctx != ctx) BAD(ctx, "oracle belongs to another context");
+        if (oracles[i]->n_log != n_log || oracles[i]->rate_bits != rate_bits) BAD(ctx, "oracles differ in degree or rate");
+    }
+    u64 n = (u64)1 << n_log;
+    u32 total = 0, max_k = 0;
+    for (u32 b = 0; b < n_points; b++) { total += point_n_polys[b]; max_k = std::max(max_k, point_n_polys[b]); }
+    for (u32 i = 0; i < total; i++) {
+        if (poly_oracle[i] >= n_oracles) BAD(ctx, "oracle index out of range");
+        if (poly_index[i] >= oracles[poly_oracle[i]]->k) BAD(ctx, "polynomial index out of range");
+    }
+    if (!max_k) BAD(ctx, "no polynomial to open");
+    b200zkp_fri* f = nullptr;
+    TRY(fri_alloc_state(ctx, n_log, rate_bits, &f));
+    HostExt alpha{gl_host_canon(alpha_in[0]), gl_host_canon(alpha_in[1])};
+    u32 n_seg = (u32)((n + frik::SCAN_SEG - 1) / frik::SCAN_SEG);
+    void *d_ptrs = nullptr, *d_pw = nullptr, *d_comp = nullptr, *d_tot = nullptr, *d_carry = nullptr;
+    size_t ptrs_b = (size_t)max_k * 8, pw_b = (size_t)max_k * 16, comp_b = (size_t)2 * n * 8, seg_b = (size_t)n_seg * 16;
+    int rc = 0;
+    auto done = [&](int code) {
+        dev_release(ctx, d_ptrs, ptrs_b); dev_release(ctx, d_pw, pw_b); dev_release(ctx, d_comp, comp_b);
+        dev_release(ctx, d_tot, seg_b); dev_release(ctx, d_carry, seg_b);
+        if (code) fri_release(f); else *out = f;
+        return code;
+    };
+    if ((rc = dev_alloc(ctx, ptrs_b, &d_ptrs)) || (rc = dev_alloc(ctx, pw_b, &d_pw)) || (rc = dev_alloc(ctx, comp_b, &d_comp)) ||
+        (rc = dev_alloc(ctx, seg_b, &d_tot)) || (rc = dev_alloc(ctx, seg_b, &d_carry)))
+        return done(rc);
+    u64* fin_a = f->coef[0];
+    u64* fin_b = f->coef[0] + f->coef_stride[0];
+    u64* comp_a = (u64*)d_comp;
+    u64* comp_im = (u64*)d_comp + n;
+    std::vector<const u64*> ptrs(max_k);
+    u32 off = 0;
+    for (u32 b = 0; b < n_points; b++) {
+        u32 k = point_n_polys[b];
+        if (!k) continue;       // an empty batch contributes the zero polynomial and alpha^0
+        for (u32 i = 0; i < k; i++) ptrs[i] = oracles[poly_oracle[off + i]]->coeffs + (u64)poly_index[off + i] * n;
+        off += k;
+        if ((rc = h2d(ctx, d_ptrs, ptrs.data(), (size_t)k * 8))) return done(rc);
+        frik::ext_powers_kernel<<<(k + 127) / 128, 128, 0, ctx->stream>>>(to_dev(alpha), k, (evalk::Ext2*)d_pw);
+        ctx->launches++;
+        frik::reduce_polys_base_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+            (const u64* const*)d_ptrs, k, n, (const evalk::Ext2*)d_pw, comp_a, comp_im);
+        ctx->launches++;
+        HostExt z{gl_host_canon(points[2 * b]), gl_host_canon(points[2 * b + 1])};
+        frik::scan_totals_kernel<<<n_seg, frik::SCAN_THREADS, 0, ctx->stream>>>(comp_a, comp_im, n, to_dev(z), (evalk::Ext2*)d_tot);
+        ctx->launches++;
+        frik::scan_carries_kernel<<<1, 32, 0, ctx->stream>>>((const evalk::Ext2*)d_tot, n_seg, to_dev(z), (evalk::Ext2*)d_carry);
+        ctx->launches++;
+        // alpha.shift_poly(&mut final_poly): final_poly *= alpha^count, count = polynomials of this batch
+        frik::divide_by_linear_kernel<<<n_seg, frik::SCAN_THREADS, 0, ctx->stream>>>(
+            comp_a, comp_im, n, to_dev(z), (const evalk::Ext2*)d_carry, to_dev(host_ext_pow(alpha, k)),
+            (flags & B200ZKP_FRI_MUL_BY_X) ? 1u : 0u, fin_a, fin_b);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { ctx->err = std::string("fri_begin: ") + cudaGetErrorString(e); return done(B200ZKP_ERR_CUDA); }
+        // the pointer table is reused by the next batch: the copy above is stream-ordered after these kernels
+    }
+    if ((rc = fri_compute_values(f))) return done(rc);
+    return done(0);
+}
+
+extern "C" int b200zkp_fri_begin_from_coeffs(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t rate_bits,
+                                             b200zkp_fri** out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!out) BAD(ctx, "null out");
+    *out = nullptr;
+    if (!coeffs) BAD(ctx, "null buffer");
+    b200zkp_fri* f = nullptr;
+    TRY(fri_alloc_state(ctx, n_log, rate_bits, &f));
+    u64 n = (u64)1 << n_log;
+    // stage the interleaved input in the (still unused) values buffer
+    int rc = h2d(ctx, f->values, coeffs, (size_t)n * 16);
+    if (!rc) {
+        frik::deinterleave_kernel<<<(unsigned)((2 * n + 255) / 256), 256, 0, ctx->stream>>>(f->values, n, f->coef[0], f->coef[0] + f->coef_stride[0]);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "fri: deinterleave launch failed"; rc = B200ZKP_ERR_CUDA; }
+    }
+    if (!rc) rc = fri_compute_values(f);
+    if (rc) { fri_release(f); return rc; }
+    *out = f;
+    return 0;
+}
+
+extern "C" void b200zkp_fri_free(b200zkp_fri* f) {
+    if (!f) return;
+    Guard g(f->ctx);
+    cudaStreamSynchronize(f->ctx->stream);
+    fri_release(f);
+}
+
+extern "C" int b200zkp_fri_shape(const b200zkp_fri* f, uint32_t shape[4]) {
+    if (!f || !shape) return B200ZKP_ERR_BAD_ARG;
+    shape[0] = f->n_log; shape[1] = f->rate_bits; shape[2] = f->cur_log; shape[3] = (uint32_t)f->layers.size();
+    return 0;
+}
+
+static int fri_copy_coeffs(b200zkp_fri* f, u64 len, u64* out) {
+    b200zkp_ctx* ctx = f->ctx;
+    if (!len) return 0;
+    void* d = nullptr; size_t bytes = (size_t)len * 16;
+    TRY(dev_alloc(ctx, bytes, &d));
+    const u64* pa = f->coef[f->cur];
+    frik::interleave_kernel<<<(unsigned)((2 * len + 255) / 256), 256, 0, ctx->stream>>>(pa, pa + f->coef_stride[f->cur], len, (u64*)d);
+    ctx->launches++;
+    int rc = cudaGetLastError() == cudaSuccess ? 0 : B200ZKP_ERR_CUDA;
+    if (rc) ctx->err = "fri: interleave launch failed";
+    if (!rc) rc = d2h(ctx, out, d, bytes);
+    dev_release(ctx, d, bytes);
+    return rc;
+}
+
+extern "C" int b200zkp_fri_coeffs(b200zkp_fri* f, uint64_t* out) {
+    if (!f || !out) return B200ZKP_ERR_BAD_ARG;
+    Guard g(f->ctx);
+    return fri_copy_coeffs(f, (u64)1 << f->cur_log, (u64*)out);
+}
+
+extern "C" int b200zkp_fri_final_poly(b200zkp_fri* f, uint64_t* out) {
+    if (!f || !out) return B200ZKP_ERR_BAD_ARG;
+    Guard g(f->ctx);
+    if (f->pending_arity_bits >= 0) BAD(f->ctx, "a committed layer is waiting for its beta (b200zkp_fri_fold)");
+    return fri_copy_coeffs(f, ((u64)1 << f->cur_log) >> f->rate_bits, (u64*)out);
+}
+
+extern "C" int b200zkp_fri_commit_layer(b200zkp_fri* f, uint32_t arity_bits, uint32_t cap_height, uint64_t* cap_out) {
+    if (!f) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_ctx* ctx = f->ctx;
+    Guard g(ctx);
+    if (!cap_out) BAD(ctx, "null cap_out");
+    if (f->pending_arity_bits >= 0) BAD(ctx, "previous layer not folded yet");
+    if (arity_bits == 0 || arity_bits > f->cur_log) BAD(ctx, "arity_bits out of range");
+    if (cap_height > f->cur_log - arity_bits) BAD(ctx, "cap_height exceeds log2(number of leaves)");
+    u64 M = (u64)1 << f->cur_log;
+    FriLayer L;
+    L.arity_bits = arity_bits; L.cap_height = cap_height; L.n_leaves = M >> arity_bits;
+    L.rows_b = (size_t)M * 16;
+    L.digests_b = (size_t)2 * (L.n_leaves - ((u64)1 << cap_height)) * 32;
+    L.cap_b = ((size_t)32) << cap_height;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, L.rows_b, (void**)&L.rows)) || (rc = dev_alloc(ctx, L.digests_b, (void**)&L.digests)) ||
+        (rc = dev_alloc(ctx, L.cap_b, (void**)&L.cap))) {
+        dev_release(ctx, L.rows, L.rows_b); dev_release(ctx, L.digests, L.digests_b); dev_release(ctx, L.cap, L.cap_b);
+        return rc;
+    }
+    auto fail = [&](int code) { dev_release(ctx, L.rows, L.rows_b); dev_release(ctx, L.digests, L.digests_b); dev_release(ctx, L.cap, L.cap_b); return code; };
+    frik::interleave_kernel<<<(unsigned)((2 * M + 255) / 256), 256, 0, ctx->stream>>>(f->values, f->values + M, M, L.rows);
+    ctx->launches++;
+    if (cudaGetLastError() != cudaSuccess) { ctx->err = "fri: interleave launch failed"; return fail(B200ZKP_ERR_CUDA); }
+    u32 leaf_len = 2u << arity_bits;
+    if ((rc = dev_merkle_locked(ctx, L.rows, leaf_len, 1, leaf_len, L.n_leaves, cap_height, L.digests, L.cap))) return fail(rc);
+    if ((rc = d2h(ctx, cap_out, L.cap, L.cap_b))) return fail(rc);
+    f->layers.push_back(L);
+    f->pending_arity_bits = (int)arity_bits;
+    return 0;
+}
+
+extern "C" int b200zkp_fri_fold(b200zkp_fri* f, const uint64_t beta_in[2]) {
+    if (!f) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_ctx* ctx = f->ctx;
+    Guard g(ctx);
+    if (!beta_in) BAD(ctx, "null beta");
+    if (f->pending_arity_bits < 0) BAD(ctx, "no committed layer to fold");
+    u32 ab = (u32)f->pending_arity_bits;
+    u64 out_len = ((u64)1 << f->cur_log) >> ab;
+    int nxt = f->cur ^ 1;
+    HostExt beta{gl_host_canon(beta_in[0]), gl_host_canon(beta_in[1])};
+    const u64* ia = f->coef[f->cur];
+    u64* oa = f->coef[nxt];
+    frik::fold_kernel<<<(unsigned)((out_len + 127) / 128), 128, 0, ctx->stream>>>(
+        ia, ia + f->coef_stride[f->cur], out_len, 1u << ab, to_dev(beta), oa, oa + f->coef_stride[nxt]);
+    LAUNCH_CHECK(ctx);
+    f->cur = nxt;
+    f->cur_log -= ab;
+    for (u32 i = 0; i < ab; i++) f->shift = hostgl::mul(f->shift, f->shift);   // shift = shift^arity
+    f->pending_arity_bits = -1;
+    f->values_ready = false;
+    return fri_compute_values(f);
+}
+
+extern "C" int b200zkp_fri_query(b200zkp_fri* f, uint32_t layer, const uint64_t* idx, uint64_t n_idx, uint64_t* evals,
+                                 uint64_t* siblings) {
+    if (!f || (!idx && n_idx)) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_ctx* ctx = f->ctx;
+    Guard g(ctx);
+    if (layer >= f->layers.size()) BAD(ctx, "layer out of range");
+    const FriLayer& L = f->layers[layer];
+    if (!n_idx) return 0;
+    for (u64 i = 0; i < n_idx; i++) if (idx[i] >= L.n_leaves) BAD(ctx, "leaf index out of range");
+    u32 lg = 0;
+    while (((u64)1 << lg) < L.n_leaves) lg++;
+    u32 depth = lg - L.cap_height, row_len = 2u << L.arity_bits;
+    void *d_idx = nullptr, *d_rows = nullptr, *d_sib = nullptr;
+    size_t idx_b = n_idx * 8, rows_b = evals ? n_idx * row_len * 8 : 0, sib_b = (siblings && depth) ? n_idx * depth * 32 : 0;
+    int rc = 0;
+    auto done = [&](int code) { dev_release(ctx, d_idx, idx_b); dev_release(ctx, d_rows, rows_b); dev_release(ctx, d_sib, sib_b); return code; };
+    if ((rc = dev_alloc(ctx, idx_b, &d_idx)) || (rc = dev_alloc(ctx, rows_b, &d_rows)) || (rc = dev_alloc(ctx, sib_b, &d_sib))) return done(rc);
+    if ((rc = h2d(ctx, d_idx, idx, idx_b))) return done(rc);
+    if (rows_b) {
+        u64 cnt = n_idx * row_len;
+        frik::gather_rows_rm_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(L.rows, row_len, (const u64*)d_idx, n_idx, (u64*)d_rows);
+        ctx->launches++;
+        if ((rc = d2h(ctx, evals, d_rows, rows_b))) return done(rc);
+    }
+    if (sib_b) {
+        merkle::TreeShape shape; shape.sub_log = depth; shape.sub_digests = 2 * (((u64)1 << depth) - 1);
+        u64 cnt = n_idx * depth;
+        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(L.digests, shape, (const u64*)d_idx, n_idx, (u64*)d_sib);
+        ctx->launches++;
+        if ((rc = d2h(ctx, siblings, d_sib, sib_b))) return done(rc);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return done(B200ZKP_ERR_CUDA); }
+    return done(0);
+}
+
+extern "C" int b200zkp_pow_grind(b200zkp_ctx* ctx, const uint64_t state[12], uint32_t witness_pos, uint32_t response_pos,
+                                 uint32_t min_leading_zeros, uint64_t max_candidates, uint64_t* witness) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!state || !witness) BAD(ctx, "null buffer");
+    if (witness_pos >= 12 || response_pos >= 12 || min_leading_zeros > 64) BAD(ctx, "bad argument");
+    if (max_candidates == 0 || max_candidates > hostgl::P) max_candidates = hostgl::P;
+    void* d = nullptr; size_t bytes = 13 * 8;      // 12 state words + the running minimum
+    TRY(dev_alloc(ctx, bytes, &d));
+    u64 h[13];
+    for (int i = 0; i < 12; i++) h[i] = gl_host_canon(state[i]);
+    h[12] = ~(u64)0;
+    int rc = h2d(ctx, d, h, bytes);
+    u64 start = 0, window = (u64)1 << 18, best = ~(u64)0;
+    while (!rc && start < max_candidates) {
+        u64 count = std::min(window, max_candidates - start);
+        frik::pow_grind_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(
+            (const u64*)d, witness_pos, response_pos, min_leading_zeros, start, count, (unsigned long long*)d + 12);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "pow_grind launch failed"; rc = B200ZKP_ERR_CUDA; break; }
+        rc = d2h(ctx, &best, (u64*)d + 12, 8);
+        if (rc || best != ~(u64)0) break;
+        start += count;
+        if (window < ((u64)1 << 24)) window <<= 2;
+    }
+    dev_release(ctx, d, bytes);
+    if (rc) return rc;
+    if (best == ~(u64)0) { ctx->err = "proof of work: no witness below the bound"; return B200ZKP_ERR_UNSUPPORTED; }
+    *witness = best;
     return 0;
 }
 

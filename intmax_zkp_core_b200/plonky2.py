@@ -522,6 +522,14 @@ class PolynomialBatch:
                                                           _p(sib) if (sib is not None and sib.size) else None))
         return rows, sib
 
+    def eval_ext2(self, zeta) -> np.ndarray:
+        """OpeningSet::new's `p.to_extension().eval(zeta)` for every polynomial of the batch: zeta = (re, im) in
+        F_p[X]/(X^2 - 7); returns (k, 2).  Evaluated on the device from the resident coefficients."""
+        z = _u64(zeta, (2,))
+        out = np.empty((self.num_polys, 2), dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.b200zkp_batch_eval_ext2(self._h, _p(z), _p(out)))
+        return out
+
     def device_ptrs(self):
         ptrs = [C.c_void_p() for _ in range(4)]
         self._ctx.check(self._ctx._lib.b200zkp_batch_device_ptrs(self._h, *[C.byref(p) for p in ptrs]))

@@ -331,3 +331,20 @@ int orc_commit(const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k, ui
     free(col);
     return orc_merkle_new(leaves, N, (uint32_t)row, cap_height, digests, cap);
 }
+
+/* ------------------------------------------------------------------ openings (row N3)
+ * plonky2/src/plonk/proof.rs `OpeningSet::new` -> `eval_commitment`: p.to_extension().eval(z) for every polynomial of a
+ * batch, z in QuadraticExtension<GoldilocksField> = F_p[X]/(X^2 - W), W = 7 (field/src/extension/quadratic.rs,
+ * goldilocks_extensions.rs).  Horner from the top coefficient.  PARITY UNPINNED (no fixture in the reference). */
+void orc_eval_ext2(const uint64_t* coeffs, uint64_t n, const uint64_t zeta[2], uint64_t out[2]) {
+    gl_t za = gl_canon(zeta[0]), zb = gl_canon(zeta[1]);
+    gl_t a = 0, b = 0;
+    for (uint64_t i = n; i-- > 0;) {
+        /* (a + bX)(za + zbX) = (a za + 7 b zb) + (a zb + b za) X */
+        gl_t na = gl_add(gl_mul(a, za), gl_mul(7, gl_mul(b, zb)));
+        gl_t nb = gl_add(gl_mul(a, zb), gl_mul(b, za));
+        a = gl_add(na, gl_canon(coeffs[i]));
+        b = nb;
+    }
+    out[0] = a; out[1] = b;
+}

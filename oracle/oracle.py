@@ -56,6 +56,7 @@ def lib():
         _lib.orc_ifft.argtypes = [_u64p, C.c_uint]
         _lib.orc_coset_lde.argtypes = [_u64p, C.c_uint, C.c_uint, _u64p]
         _lib.orc_round_constants.argtypes = [_u64p]
+        _lib.orc_eval_ext2.argtypes = [_u64p, C.c_uint64, _u64p, _u64p]
     return _lib
 
 
@@ -137,6 +138,14 @@ def coset_lde(coeffs, rate_bits: int) -> np.ndarray:
 def eval_at_lde_point(coeffs, rate_bits: int, i: int) -> int:
     c = _u64(coeffs); n_log = int(c.size).bit_length() - 1
     return int(lib().orc_eval_at_lde_point(_ptr(c), n_log, rate_bits, i))
+
+
+def eval_ext2(coeffs, zeta) -> np.ndarray:
+    """p(zeta) in F_p[X]/(X^2 - 7); coeffs (n,), zeta (2,) -> (2,)."""
+    c, z = _u64(coeffs), _u64(zeta)
+    out = np.zeros(2, dtype=np.uint64)
+    lib().orc_eval_ext2(_ptr(c), c.size, _ptr(z), _ptr(out))
+    return out
 
 
 def merkle_new(leaves, cap_height: int):

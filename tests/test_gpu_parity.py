@@ -338,6 +338,19 @@ def test_full_size_properties(z, ctx, oracle):
     tctx.close()
 
 
+# ------------------------------------------------------------------------------------------------ openings (N3)
+@pytest.mark.parametrize("n_log,k", [(0, 3), (3, 5), (10, 135), (13, 20), (17, 7)])
+def test_eval_ext2_matches_oracle(z, ctx, oracle, n_log, k):
+    rng = np.random.default_rng(n_log + k)
+    v = rng.integers(0, 2**64, size=(k, 1 << n_log), dtype=np.uint64)
+    b = z.PolynomialBatch.from_coeffs(v, 1, False, 0, ctx=ctx)
+    for zeta in (rng.integers(0, 2**64, size=2, dtype=np.uint64), np.array([5, 0], np.uint64), np.array([0, 0], np.uint64),
+                 np.array([2**64 - 1, P - 1], np.uint64)):
+        got = b.eval_ext2(zeta)
+        for c in range(k):
+            assert (got[c] == oracle.eval_ext2(v[c], zeta)).all(), (c, zeta)
+
+
 # ------------------------------------------------------------------------------------------------ property-based
 def test_hypothesis_commit_shapes(z, ctx, oracle):
     """Random (n, k, rate_bits, cap_height, from_values / from_coeffs, salted) with full-range u64 inputs

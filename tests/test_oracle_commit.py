@@ -144,3 +144,24 @@ def test_cpu_baseline_matches_oracle(oracle, n_log, k, r, h):
     assert len(times) == 5 and times[4] >= 0
     c, _ = oracle.baseline_commit(a["coeffs"], r, h, is_coeffs=True)
     assert (c["cap"] == a["cap"]).all()
+
+
+def test_eval_ext2_matches_definition(oracle):
+    """Quadratic-extension evaluation (row N3) against Python integers: X^2 = 7."""
+    rng = np.random.default_rng(8)
+    for n in (1, 2, 7, 64):
+        c = [int(x) % P for x in rng.integers(0, 2**64, size=n, dtype=np.uint64)]
+        za, zb = (int(x) % P for x in rng.integers(0, 2**64, size=2, dtype=np.uint64))
+        ra, rb, pa, pb = 0, 0, 1, 0          # result, running power of zeta
+        for ci in c:
+            ra, rb = (ra + ci * pa) % P, (rb + ci * pb) % P
+            pa, pb = (pa * za + 7 * pb * zb) % P, (pa * zb + pb * za) % P
+        got = oracle.eval_ext2(np.array(c, dtype=np.uint64), np.array([za, zb], dtype=np.uint64))
+        assert [int(x) for x in got] == [ra, rb]
+    # a base-field point gives the base-field value: compare with the LDE (zeta = 7 * w_N^i)
+    c = rand_field(rng, 32)
+    lde = oracle.coset_lde(c, 2)
+    g2 = 1753635133440165772
+    x = 7 * pow(pow(g2, 1 << (32 - 7), P), 5, P) % P
+    got = oracle.eval_ext2(c, np.array([x, 0], dtype=np.uint64))
+    assert int(got[0]) == int(lde[5]) and int(got[1]) == 0
