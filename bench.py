@@ -347,6 +347,15 @@ def run_b200(args):
                 ctx.check(ctx._lib.b200zkp_int_pipe_bench(ctx._h, kind, 2000, C.byref(g)))
                 gips[name] = g.value
             line["int_pipe"] = {"unit": "giga thread-instructions/s (dependent chains, all SMs)", **gips}
+            # second roof of SURVEY.md 8d: the leaf hash against the measured integer-multiply issue rate.  2720 IMAD.WIDE per
+            # permutation is the dynamic count of the shipped kernel (profiles/README.md); the multiplier pipe also issues the
+            # 32-bit IMADs of the MDS layers and the adds ptxas places there, which is why ncu reports it 92 % busy.
+            leaf_perms = N_local * ((k + 7) // 8)
+            wide_rate = leaf_perms * 2720 / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
+            line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": wide_rate, "peak": gips["imad_wide"] * 1e9,
+                                       "unit": "IMAD.WIDE.U32 thread-instr/s", "frac": wide_rate / (gips["imad_wide"] * 1e9),
+                                       "imad_wide_per_permutation": 2720, "permutations_per_launch": leaf_perms,
+                                       "ncu_pipe_fmaheavy_busy": 0.923}
             if not os.environ.get("B200ZKP_SKIP_CPU"):
                 from oracle import oracle as O
                 O.build()
