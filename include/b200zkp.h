@@ -226,7 +226,8 @@ int b200zkp_field_op(b200zkp_ctx* ctx, int op, const uint64_t* a, const uint64_t
 /* integer-pipe micro-benchmark: runs `iters` dependent-chain rounds of the chosen
  * instruction mix on every SM and returns giga thread-instructions per second in *out_gips.
  * kind: 0 IMAD.WIDE.U32, 1 IADD3, 2 IMAD (32-bit), 3 alternating IMAD.WIDE/LOP3, 4 LOP3, 5 IMAD.HI.U32,
- *       6 alternating IMAD/LOP3, 7 IADD3 + IADD3.X carry pairs, 8 IMAD.WIDE.U32 without accumulator */
+ *       6 alternating IMAD/LOP3, 7 IADD3 + IADD3.X carry pairs, 8 IMAD.WIDE.U32 without accumulator,
+ *       9 DFMA, 10 alternating DFMA/IMAD.WIDE.U32, 11 alternating DFMA/IMAD, 12 alternating DFMA/LOP3 */
 int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips);
 
 #ifdef __cplusplus

@@ -1592,8 +1592,10 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
     u32 a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 77u;
     u64 w[8];
     u32 x[8];
+    double d[8];
+    const double dc = 1.0 + 1e-9 * (double)(b & 7);
 #pragma unroll
-    for (int i = 0; i < 8; i++) { w[i] = ((u64)(a + i) << 32) | (b * (i + 3)); x[i] = a * (2 * i + 1) + b; }
+    for (int i = 0; i < 8; i++) { w[i] = ((u64)(a + i) << 32) | (b * (i + 3)); x[i] = a * (2 * i + 1) + b; d[i] = 1.0 + 1e-6 * (double)(a & 1023) * (i + 1); }
     for (u32 it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
@@ -1618,15 +1620,26 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
                     else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
                 } else if (KIND == 7) {   // add with carry chain (IADD3 + IADD3.X)
                     asm volatile("{ add.cc.u32 %0, %0, %1; addc.u32 %0, %0, %2; }" : "+r"(x[i]) : "r"(x[j]), "r"(b));
-                } else {                  // KIND 8: IMAD.WIDE.U32 without an accumulator (32x32 -> 64, addend RZ)
+                } else if (KIND == 8) {   // IMAD.WIDE.U32 without an accumulator (32x32 -> 64, addend RZ)
                     asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mul.wide.u32 %0, lo, hi; }" : "=l"(w[i]) : "l"(w[j]));
+                } else if (KIND == 9) {   // DFMA (FP64 pipe)
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dc), "d"(d[j]));
+                } else if (KIND == 10) {  // alternating DFMA / IMAD.WIDE.U32: do the FP64 and multiplier pipes overlap?
+                    if (i & 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dc), "d"(d[(i + 2) & 7]));
+                    else asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[i]) : "l"(w[(i + 2) & 7]), "r"(b));
+                } else if (KIND == 11) {  // alternating DFMA / IMAD (32-bit)
+                    if (i & 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dc), "d"(d[(i + 2) & 7]));
+                    else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
+                } else {                  // KIND 12: alternating DFMA / LOP3
+                    if (i & 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dc), "d"(d[(i + 2) & 7]));
+                    else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
                 }
             }
         }
     }
     u64 ww = 0; u32 xx = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { ww ^= w[i]; xx ^= x[i]; }
+    for (int i = 0; i < 8; i++) { ww ^= w[i]; xx ^= x[i]; ww ^= (u64)__double_as_longlong(d[i]); }
     xx ^= (u32)ww ^ (u32)(ww >> 32);
     if (xx == 0xdeadbeefu && iters == 0xffffffffu) *sink = xx;   // keep the chains alive
 }
@@ -1634,7 +1647,7 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
 extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips) {
     if (!ctx) return B200ZKP_ERR_BAD_ARG;
     Guard g(ctx);
-    if (!out_gips || kind < 0 || kind > 8) BAD(ctx, "bad argument");
+    if (!out_gips || kind < 0 || kind > 12) BAD(ctx, "bad argument");
     int sms = 0;
     CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     u32* sink = nullptr;
@@ -1653,7 +1666,11 @@ extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters
             case 5: int_pipe_kernel<5><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
             case 6: int_pipe_kernel<6><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
             case 7: int_pipe_kernel<7><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
-            default: int_pipe_kernel<8><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 8: int_pipe_kernel<8><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 9: int_pipe_kernel<9><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 10: int_pipe_kernel<10><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 11: int_pipe_kernel<11><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            default: int_pipe_kernel<12><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
         }
         ctx->launches++;
     };
