@@ -215,6 +215,12 @@ int b200zkp_dev_lde_merkle(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t co
 int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k,
                        uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, uint64_t* coeffs,
                        uint64_t* lde, uint64_t* digests, uint64_t* cap);
+/* MerkleTree::get + MerkleTree::prove on caller-owned device buffers (e.g. one rank's leaf shard): element (row, c) at
+ * lde[c*col_stride + row]; idx_dev n_idx leaf indices on the device; rows_dev n_idx*row_len, siblings_dev
+ * n_idx*(log2 n_leaves - cap_height)*4, either may be NULL */
+int b200zkp_dev_gather(b200zkp_ctx* ctx, const uint64_t* lde, uint64_t col_stride, uint32_t row_len,
+                       const uint64_t* digests, uint64_t n_leaves, uint32_t cap_height, const uint64_t* idx_dev,
+                       uint64_t n_idx, uint64_t* rows_dev, uint64_t* siblings_dev);
 /* column-major [cols][col_stride] rows [row0,row0+n_rows) -> row-major [n_rows][cols] (device) */
 int b200zkp_dev_transpose_to_rows(b200zkp_ctx* ctx, const uint64_t* cm, uint64_t col_stride, uint32_t cols,
                                   uint64_t row0, uint64_t n_rows, uint64_t* rm);

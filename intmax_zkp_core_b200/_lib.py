@@ -85,6 +85,8 @@ _SIGS = {
     "b200zkp_batch_device_ptrs": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "b200zkp_batch_eval_ext2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "b200zkp_dev_eval_ext2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "b200zkp_dev_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
+                                     C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zkp_fri_begin": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
     "b200zkp_fri_begin_from_coeffs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),

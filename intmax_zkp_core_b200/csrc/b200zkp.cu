@@ -744,6 +744,15 @@ static int commit_host(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log
         u64* ld = b->lde + (u64)c0 * N;
         if (is_coeffs) rc = launch_canon_copy(ctx, src, cf, (u64)(c1 - c0) * n);
         else rc = dev_intt_locked(ctx, src, n, cf, n, /*scratch=*/ld, n_log, c1 - c0);     // this chunk's LDE columns are still free
+        if (!rc && cb && cb->coeffs) {
+            // copy-back: this chunk's coefficients go home while the later chunks are still being transformed
+            cudaEvent_t e_cf;
+            if ((rc = get_sync_event(ctx, 2 + n_chunks + c, &e_cf))) return fail(rc);
+            e = cudaEventRecord(e_cf, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, e_cf, 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cb->coeffs + (u64)c0 * n, cf, (size_t)(c1 - c0) * n * 8, cudaMemcpyDeviceToHost, ctx->stream2);
+            if (e != cudaSuccess) { ctx->err = std::string("copy-back: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return fail(B200ZKP_ERR_CUDA); }
+        }
         if (!rc) rc = dev_lde_locked(ctx, cf, n, ld, N, n_log, c1 - c0, rate_bits, 0, 1u << rate_bits);
         if (rc) return fail(rc);
     }
@@ -757,7 +766,6 @@ static int commit_host(b200zkp_ctx* ctx, const u64* in, int is_coeffs, u32 n_log
         if ((rc = get_sync_event(ctx, 1 + n_chunks, &e_lde))) return fail(rc);
         e = cudaEventRecord(e_lde, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream2, e_lde, 0);
-        if (e == cudaSuccess && cb->coeffs) e = cudaMemcpyAsync(cb->coeffs, b->coeffs, b->coeffs_b, cudaMemcpyDeviceToHost, ctx->stream2);
         if (e == cudaSuccess && cb->leaves) {
             u64 chunk_rows = std::min<u64>(N, std::max<u64>(1, ((u64)256 << 20) / ((u64)row * 8)));
             stage_b = (size_t)chunk_rows * row * 8;
@@ -936,6 +944,37 @@ extern "C" int b200zkp_batch_device_ptrs(b200zkp_batch* b, const uint64_t** coef
     if (lde) *lde = (const uint64_t*)b->lde;
     if (digests) *digests = (const uint64_t*)b->digests;
     if (cap) *cap = (const uint64_t*)b->cap;
+    return 0;
+}
+
+// MerkleTree::get + prove on caller-owned device buffers (a rank's leaf shard of a sharded commitment): asynchronous.
+extern "C" int b200zkp_dev_gather(b200zkp_ctx* ctx, const uint64_t* lde, uint64_t col_stride, uint32_t row_len,
+                                  const uint64_t* digests, uint64_t n_leaves, uint32_t cap_height, const uint64_t* idx_dev,
+                                  uint64_t n_idx, uint64_t* rows_dev, uint64_t* siblings_dev) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!n_idx) return 0;
+    if (!idx_dev) BAD(ctx, "null index buffer");
+    if (n_leaves == 0 || (n_leaves & (n_leaves - 1))) BAD(ctx, "number of leaves must be a power of two");
+    u32 lg = 0;
+    while (((u64)1 << lg) < n_leaves) lg++;
+    if (cap_height > lg) BAD(ctx, "cap_height exceeds log2(number of leaves)");
+    if (rows_dev) {
+        if (!lde) BAD(ctx, "null leaf buffer");
+        u64 cnt = n_idx * row_len;
+        if (cnt) {
+            merkle::gather_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const u64*)lde, col_stride, row_len, (const u64*)idx_dev, n_idx, (u64*)rows_dev);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    u32 depth = lg - cap_height;
+    if (siblings_dev && depth) {
+        if (!digests) BAD(ctx, "null digests buffer");
+        merkle::TreeShape shape; shape.sub_log = depth; shape.sub_digests = 2 * (((u64)1 << depth) - 1);
+        u64 cnt = n_idx * depth;
+        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const u64*)digests, shape, (const u64*)idx_dev, n_idx, (u64*)siblings_dev);
+        LAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 

@@ -192,3 +192,31 @@ class ShardedCommitment:
         else:
             self.cap.copy_(self.cap_local)
         return self.cap
+
+    def rows(self, indices):
+        """MerkleTree::get + MerkleTree::prove for GLOBAL leaf indices of the sharded commitment (what the FRI query rounds
+        open): the rank that owns a leaf gathers its row and sibling path from its shard, one all-reduce (sum with zeros from
+        the other ranks) hands every rank the full answer.  Returns (rows (q, k), siblings (q, log2 N - cap_height, 4))."""
+        import torch
+        import torch.distributed as dist
+        ctx, lib = self.ctx, self.ctx._lib
+        dev = self.lde.device
+        idx = torch.as_tensor(list(indices), dtype=torch.int64, device=dev)
+        q = idx.numel()
+        depth = log2_strict(self.N_local) - self.cap_height_local
+        rows = torch.zeros((q, self.k), dtype=torch.int64, device=dev)
+        sib = torch.zeros((q, depth, 4), dtype=torch.int64, device=dev)
+        if q == 0:
+            return rows, sib
+        if int(idx.min()) < 0 or int(idx.max()) >= self.N_local * self.world:
+            raise ValueError("leaf index out of range")
+        mine = (idx // self.N_local) == self.rank
+        local = torch.where(mine, idx % self.N_local, torch.zeros_like(idx)).contiguous()
+        ctx.check(lib.b200zkp_dev_gather(ctx._h, _ptr(self.lde), self.N_local, self.k, _ptr(self.digests), self.N_local,
+                                         self.cap_height_local, _ptr(local), q, _ptr(rows), _ptr(sib) if depth else None))
+        rows *= mine[:, None]
+        sib *= mine[:, None, None]
+        if self.world > 1:
+            dist.all_reduce(rows, group=self.group)
+            dist.all_reduce(sib, group=self.group)
+        return rows, sib

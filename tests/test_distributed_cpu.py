@@ -63,6 +63,22 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     ok &= bool((coeffs == full["coeffs"]).all())
     sub = 2 * ((N >> h) - 1)
     ok &= bool((dig == full["digests"][lay["cap_begin"] * sub:lay["cap_end"] * sub]).all())
+    # 5. openings of global leaf indices: the owner answers from its shard, a sum with zeros shares the answer
+    depth = (n_log + r) - h
+    idx = np.array([0, N // 2 - 1, N // 2, N - 1, 3 % N], dtype=np.int64)
+    rows = np.zeros((idx.size, k), np.uint64)
+    sib = np.zeros((idx.size, depth, 4), np.uint64)
+    for j, x in enumerate(idx):
+        if x // lay["N_local"] == rank:
+            xl = int(x % lay["N_local"])
+            rows[j] = local[xl]
+            sib[j] = O.merkle_prove(dig, lay["N_local"], lay["cap_height_local"], xl)
+    t_rows, t_sib = torch.from_numpy(rows.view(np.int64)), torch.from_numpy(sib.view(np.int64))
+    dist.all_reduce(t_rows)
+    dist.all_reduce(t_sib)
+    for j, x in enumerate(idx):
+        ok &= bool((t_rows.numpy().view(np.uint64)[j] == full["leaves"][x]).all())
+        ok &= bool(O.merkle_verify(t_rows.numpy().view(np.uint64)[j], int(x), t_sib.numpy().view(np.uint64)[j], full["cap"]))
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -46,6 +46,16 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     sub = 2 * (((n << r) >> h) - 1)
     ok &= bool((sh.digests.cpu().numpy().view(np.uint64)[:(lay["cap_end"] - lay["cap_begin"]) * sub]
                 == ref["digests"][lay["cap_begin"] * sub:lay["cap_end"] * sub]).all())
+    # (e) step 5: openings of global leaf indices, gathered by the owning rank and shared with one all-reduce
+    N = n << r
+    idx = [0, 5, N // 2 - 1, N // 2, N - 1, 17 % N]
+    rows, sib = sh.rows(idx)
+    torch.cuda.synchronize()
+    rows, sib = rows.cpu().numpy().view(np.uint64), sib.cpu().numpy().view(np.uint64)
+    for j, x in enumerate(idx):
+        ok &= bool((rows[j] == ref["leaves"][x]).all())
+        ok &= bool((sib[j] == O.merkle_prove(ref["digests"], N, h, x)).all())
+        ok &= bool(O.merkle_verify(rows[j], x, sib[j], ref["cap"]))
     q.put((rank, ok))
     dist.destroy_process_group()
 
