@@ -166,6 +166,14 @@ class PolynomialBatch {
         ctx_->check(b200zkp_batch_rows(h_.get(), &leaf_index, 1, row.data(), p.siblings.empty() ? nullptr : p.siblings[0].elements.data()));
         return {row, p};
     }
+    // OpeningSet::new's `p.to_extension().eval(zeta)` for every polynomial: zeta and results as (real, imaginary) pairs
+    std::vector<std::array<F, 2>> eval_ext2(const std::array<F, 2>& zeta) const {
+        std::vector<std::array<F, 2>> out(num_polys);
+        ctx_->check(b200zkp_batch_eval_ext2(h_.get(), zeta.data(), out[0].data()));
+        return out;
+    }
+    b200zkp_batch* raw() const { return h_.get(); }
+    const Context& context() const { return *ctx_; }
     MerkleCap cap;  // merkle_tree.cap
     size_t degree_log = 0, rate_bits = 0, cap_height = 0, num_polys = 0, salt_size = 0;
     bool blinding = false;

@@ -2,7 +2,7 @@
 // Merkle proofs.  Built and run by tests/test_host_cpp.py (gpu); exit code 0 = all checks passed.
 #include <cstdio>
 #include <cstdlib>
-#include "plonky2_api.hpp"
+#include "fri_api.hpp"
 
 using namespace plonky2;
 
@@ -51,6 +51,44 @@ int main() {
     threw = false;
     try { leaves.pop_back(); MerkleTree::new_(ctx, leaves, 2); } catch (const std::invalid_argument&) { threw = true; }
     CHECK(threw);
+    // opening proof (rows N2 + N3): two oracles of 2^6 coefficients, a small FRI configuration; the digest of the whole
+    // proof is compared with the Python mirror (itself bit-exact against oracle/fri_ref.py) by tests/test_host_cpp.py
+    {
+        const size_t fn = 64;
+        auto synth = [&](size_t kk, uint64_t seed) {
+            std::vector<std::vector<F>> v(kk, std::vector<F>(fn));
+            for (size_t c = 0; c < kk; c++)
+                for (size_t i = 0; i < fn; i++) { uint64_t x = splitmix64((seed << 48) + c * fn + i); v[c][i] = x >= GOLDILOCKS_ORDER ? x - GOLDILOCKS_ORDER : x; }
+            return v;
+        };
+        FriConfig cfg;
+        cfg.rate_bits = 2; cfg.cap_height = 1; cfg.proof_of_work_bits = 7; cfg.arity_bits = 2; cfg.final_poly_bits = 2; cfg.num_query_rounds = 5;
+        FriParams params = FriParams::from_config(cfg, 6);
+        CHECK(params.reduction_arity_bits.size() == 2);
+        PolynomialBatch o0 = PolynomialBatch::from_coeffs(ctx, synth(3, 5), cfg.rate_bits, false, cfg.cap_height);
+        PolynomialBatch o1 = PolynomialBatch::from_coeffs(ctx, synth(2, 6), cfg.rate_bits, false, cfg.cap_height);
+        Challenger ch(ctx);
+        ch.observe_cap(o0.cap);
+        ch.observe_cap(o1.cap);
+        FriInstanceInfo inst;
+        inst.batches.push_back({Ext{123456789ull, 987654321ull}, {{0, 0}, {0, 1}, {0, 2}, {1, 0}, {1, 1}}});
+        inst.batches.push_back({Ext{555ull, 777ull}, {{1, 0}, {1, 1}}});
+        FriProof proof = prove_openings(inst, {&o0, &o1}, ch, params);
+        CHECK(proof.commit_phase_merkle_caps.size() == 2 && proof.final_poly.size() == 4 && proof.query_round_proofs.size() == 5);
+        uint64_t d = 0xcbf29ce484222325ull;
+        auto mix = [&](uint64_t w) { d = (d ^ w) * 0x100000001b3ull; };
+        for (auto& cap : proof.commit_phase_merkle_caps) for (auto& hh : cap) for (F e : hh.elements) mix(e);
+        for (auto& e : proof.final_poly) { mix(e[0]); mix(e[1]); }
+        mix(proof.pow_witness);
+        for (auto& r : proof.query_round_proofs) {
+            for (auto& ip : r.initial_trees_proof) { for (F e : ip.first) mix(e); for (auto& sb : ip.second.siblings) for (F e : sb.elements) mix(e); }
+            for (auto& st : r.steps) { for (auto& e : st.evals) { mix(e[0]); mix(e[1]); } for (auto& sb : st.merkle_proof.siblings) for (F e : sb.elements) mix(e); }
+        }
+        mix(ch.get_challenge());
+        std::printf("fri digest %016llx pow %llu\n", (unsigned long long)d, (unsigned long long)proof.pow_witness);
+        auto ev = o1.eval_ext2(Ext{555ull, 777ull});
+        CHECK(ev.size() == 2);
+    }
     std::printf("host C++ API ok\n");
     return 0;
 }

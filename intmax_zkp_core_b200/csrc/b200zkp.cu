@@ -136,8 +136,9 @@ static int dev_alloc(b200zkp_ctx* ctx, size_t bytes, void** out) {
 }
 static void dev_release(b200zkp_ctx* ctx, void* p, size_t bytes) {
     if (!p) return;
-    // keep at most ~16 cached blocks; stream order makes reuse on the same ctx safe
-    if (ctx->pool.size() < 16) ctx->pool.emplace(bytes, p);
+    // cached for the next request of the same size (stream order makes reuse on the same ctx safe); an opening proof
+    // cycles through ~40 distinct sizes, so the cap is generous — dev_alloc drops the whole cache when cudaMalloc fails
+    if (ctx->pool.size() < 256) ctx->pool.emplace(bytes, p);
     else cudaFree(p);
 }
 
@@ -1184,7 +1185,7 @@ extern "C" int b200zkp_fri_begin(b200zkp_ctx* ctx, b200zkp_batch* const* oracles
         HostExt z{gl_host_canon(points[2 * b]), gl_host_canon(points[2 * b + 1])};
         frik::scan_totals_kernel<<<n_seg, frik::SCAN_THREADS, 0, ctx->stream>>>(comp_a, comp_im, n, to_dev(z), (evalk::Ext2*)d_tot);
         ctx->launches++;
-        frik::scan_carries_kernel<<<1, 32, 0, ctx->stream>>>((const evalk::Ext2*)d_tot, n_seg, to_dev(z), (evalk::Ext2*)d_carry);
+        frik::scan_carries_kernel<<<1, frik::SCAN_THREADS, 0, ctx->stream>>>((const evalk::Ext2*)d_tot, n_seg, to_dev(z), (evalk::Ext2*)d_carry);
         ctx->launches++;
         // alpha.shift_poly(&mut final_poly): final_poly *= alpha^count, count = polynomials of this batch
         frik::divide_by_linear_kernel<<<n_seg, frik::SCAN_THREADS, 0, ctx->stream>>>(

@@ -75,12 +75,31 @@ scan_totals_kernel(const u64* __restrict__ in_a, const u64* __restrict__ in_b, u
     if (t == 0) tot[blockIdx.x] = red[0];
 }
 
-// carry[s] = S[end of segment s] = sum_{s' > s} tot[s'] z^(SCAN_SEG (s' - s - 1));  one thread: n_seg is n / 1024.
-__global__ void scan_carries_kernel(const Ext2* __restrict__ tot, u32 n_seg, Ext2 z, Ext2* __restrict__ carry) {
-    if (blockIdx.x || threadIdx.x) return;
-    Ext2 step = ext_pow(z, SCAN_SEG);
-    Ext2 c = ext_zero();
-    for (u32 s = n_seg; s-- > 0;) {
+// carry[s] = S[end of segment s] = sum_{s' > s} tot[s'] z^(SCAN_SEG (s' - s - 1)).  One CTA: every thread owns a run of
+// `per` consecutive segments, the runs are combined with the same doubling scan as below.
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_carries_kernel(const Ext2* __restrict__ tot, u32 n_seg, Ext2 z, Ext2* __restrict__ carry) {
+    __shared__ Ext2 V[SCAN_THREADS + 1];
+    const u32 t = threadIdx.x;
+    const u32 per = (n_seg + SCAN_THREADS - 1) / SCAN_THREADS;
+    const u32 s0 = t * per, s1 = (s0 + per < n_seg) ? s0 + per : n_seg;
+    const Ext2 step = ext_pow(z, SCAN_SEG);
+    Ext2 h = ext_zero();
+    for (u32 s = s1; s-- > s0 && s < n_seg;) h = ext_add(ext_mul(h, step), tot[s]);     // (empty when s0 >= n_seg)
+    V[t] = h;
+    if (t == 0) V[SCAN_THREADS] = ext_zero();
+    __syncthreads();
+    Ext2 zp = ext_pow(step, per);
+    for (u32 d = 1; d < SCAN_THREADS; d <<= 1) {
+        Ext2 v = V[t];
+        if (t + d < SCAN_THREADS) v = ext_add(v, ext_mul(zp, V[t + d]));
+        __syncthreads();
+        V[t] = v;
+        __syncthreads();
+        zp = ext_mul(zp, zp);
+    }
+    Ext2 c = V[t + 1];                       // S at the end of this thread's run
+    for (u32 s = s1; s-- > s0 && s < n_seg;) {
         carry[s] = c;
         c = ext_add(ext_mul(c, step), tot[s]);
     }

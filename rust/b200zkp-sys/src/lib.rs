@@ -5,6 +5,7 @@ use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)] pub struct b200zkp_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct b200zkp_batch { _p: [u8; 0] }
+#[repr(C)] pub struct b200zkp_fri { _p: [u8; 0] }
 #[repr(C)] pub struct b200zkp_tree { _p: [u8; 0] }
 
 extern "C" {
@@ -33,4 +34,17 @@ extern "C" {
 
     pub fn b200zkp_hash_no_pad(ctx: *mut b200zkp_ctx, input: *const u64, count: u64, len: u32, out: *mut u64) -> c_int;
     pub fn b200zkp_two_to_one(ctx: *mut b200zkp_ctx, left: *const u64, right: *const u64, count: u64, out: *mut u64) -> c_int;
+    // opening proof (prove_openings / fri_proof): see include/b200zkp.h and INTEGRATION.md
+    pub fn b200zkp_batch_eval_ext2(b: *mut b200zkp_batch, zeta: *const u64, out: *mut u64) -> c_int;
+    pub fn b200zkp_fri_begin(ctx: *mut b200zkp_ctx, oracles: *const *mut b200zkp_batch, n_oracles: u32, n_points: u32,
+        points: *const u64, point_n_polys: *const u32, poly_oracle: *const u32, poly_index: *const u32, alpha: *const u64,
+        flags: u32, out: *mut *mut b200zkp_fri) -> c_int;
+    pub fn b200zkp_fri_free(f: *mut b200zkp_fri);
+    pub fn b200zkp_fri_shape(f: *const b200zkp_fri, shape: *mut u32) -> c_int;
+    pub fn b200zkp_fri_commit_layer(f: *mut b200zkp_fri, arity_bits: u32, cap_height: u32, cap_out: *mut u64) -> c_int;
+    pub fn b200zkp_fri_fold(f: *mut b200zkp_fri, beta: *const u64) -> c_int;
+    pub fn b200zkp_fri_final_poly(f: *mut b200zkp_fri, out: *mut u64) -> c_int;
+    pub fn b200zkp_fri_query(f: *mut b200zkp_fri, layer: u32, idx: *const u64, n_idx: u64, evals: *mut u64, siblings: *mut u64) -> c_int;
+    pub fn b200zkp_pow_grind(ctx: *mut b200zkp_ctx, state: *const u64, witness_pos: u32, response_pos: u32,
+        min_leading_zeros: u32, max_candidates: u64, witness: *mut u64) -> c_int;
 }
