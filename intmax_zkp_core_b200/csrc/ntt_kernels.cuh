@@ -72,7 +72,9 @@ GL_FN u32 bitrev(u32 x, u32 bits) { return bits ? (gl::brev32(x) >> (32 - bits))
 #endif
 
 // in-register DIF over 2^A elements x[j] <-> g = gbase + j*st ; stages sigma0 .. sigma0+A-1 of a 2^B transform
-template <int A>
+// LAST: the round that ends the 2^B-point transform (st == 1, ul == 0): the twiddle exponent is jl << (sigma0 + u), a
+// compile-time zero for jl == 0 — 7 of the 12 butterflies of a radix-8 group multiply by 1 and skip the product.
+template <int A, bool LAST>
 GL_FN void dif_group(u64 (&x)[1 << A], const u64* __restrict__ wt, u32 ul, u32 st, u32 sigma0) {
 #pragma unroll
     for (int u = 0; u < A; u++) {
@@ -81,18 +83,22 @@ GL_FN void dif_group(u64 (&x)[1 << A], const u64* __restrict__ wt, u32 ul, u32 s
         for (int j = 0; j < (1 << A); j++) {
             if (j & half) continue;
             u32 jl = j & (half - 1);
-            u32 e = (jl * st + ul) << (sigma0 + u);
             u64 a = x[j], b = x[j + half];
             x[j] = gl::add(a, b);
-            x[j + half] = gl::mul(gl::sub(a, b), wt[e]);
+            if (LAST && jl == 0) {
+                x[j + half] = gl::sub(a, b);
+            } else {
+                u32 e = LAST ? (jl << (sigma0 + u)) : ((jl * st + ul) << (sigma0 + u));
+                x[j + half] = gl::mul(gl::sub(a, b), wt[e]);
+            }
         }
     }
 }
 
-template <int A>
+template <int A, bool LAST = false>
 GL_FN void run_round(u64* __restrict__ tile, const u64* __restrict__ wt, u32 B, u32 T, u32 TP, u32 sigma0,
                      u32 tid) {
-    const u32 st_log = B - sigma0 - A;
+    const u32 st_log = LAST ? 0u : B - sigma0 - A;
     const u32 st = 1u << st_log;
     constexpr int UNITS_PER_THREAD = 8 >> A;
 #pragma unroll
@@ -104,7 +110,7 @@ GL_FN void run_round(u64* __restrict__ tile, const u64* __restrict__ wt, u32 B, 
         u64 x[1 << A];
 #pragma unroll
         for (int j = 0; j < (1 << A); j++) x[j] = tile[(gbase + j * st) * TP + t];
-        dif_group<A>(x, wt, ul, st, sigma0);
+        dif_group<A, LAST>(x, wt, ul, st, sigma0);
 #pragma unroll
         for (int j = 0; j < (1 << A); j++) tile[(gbase + j * st) * TP + t] = x[j];
     }
@@ -250,14 +256,19 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
     // ---- 2^B-point DIF, radix-8 in registers
     {
         u32 sigma = 0;
+        // the short round (B mod 3 levels) goes first so that the closing round is a full radix-8 group with unit stride:
+        // 7 of its 12 twiddles are 1 and known at compile time
+        if (B > 3 && B % 3 == 2) { NTT_FOR_THREADS(tid) { run_round<2>(tile, wt, B, T, TP, sigma, tid); } sigma += 2; NTT_SYNC(); }
+        if (B > 3 && B % 3 == 1) { NTT_FOR_THREADS(tid) { run_round<1>(tile, wt, B, T, TP, sigma, tid); } sigma += 1; NTT_SYNC(); }
 #pragma unroll 1   // one copy of the radix-8 round in the instruction cache; stride and twiddle step are run-time
-        for (int r = 0; r < B / 3; r++) {
+        for (int r = 0; r < B / 3 - 1; r++) {
             NTT_FOR_THREADS(tid) { run_round<3>(tile, wt, B, T, TP, sigma, tid); }
             sigma += 3;
             NTT_SYNC();
         }
-        if (B % 3 == 2) { NTT_FOR_THREADS(tid) { run_round<2>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
-        if (B % 3 == 1) { NTT_FOR_THREADS(tid) { run_round<1>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B >= 3) { NTT_FOR_THREADS(tid) { run_round<3, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B == 2) { NTT_FOR_THREADS(tid) { run_round<2, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B == 1) { NTT_FOR_THREADS(tid) { run_round<1, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
     }
 
     // ---- twiddle + store

@@ -243,3 +243,57 @@ def test_fri_argument_checks(zf, ctx):
     inst = zf.FriInstanceInfo([zf.FriBatchInfo((1, 2), [zf.FriPolynomialInfo(0, 1)])])
     with pytest.raises(z.B200ZkpError):
         zf.FriCommitPhase.from_oracles(inst, [a], (5, 6), ctx=ctx)         # polynomial index out of range
+
+
+def test_hypothesis_opening_proofs(zf, ctx, oracle):
+    """Random (degree, oracle shapes, rate, cap height, reduction arities, X-factor convention, opening points incl. base-field
+    and zero ones) against the restated prover, bit for bit, and through the restated verifier."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from oracle import fri_ref as F
+    import intmax_zkp_core_b200 as z
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(1, 8), st.lists(st.integers(1, 5), min_size=1, max_size=3), st.integers(0, 3), st.integers(0, 3),
+           st.lists(st.integers(1, 4), max_size=3), st.booleans(), st.integers(0, 2**32 - 1), st.integers(0, 3))
+    def run(n_log, ks, r, h, arities, mul_by_x, seed, point_kind):
+        n = 1 << n_log
+        # keep every layer tree non-degenerate the way plonky2's strategies do: arity <= remaining LDE bits - cap height
+        arities, bits = list(arities), n_log + r
+        valid = []
+        for ab in arities:
+            if ab <= bits - h and ab <= n_log - sum(valid):
+                valid.append(ab)
+                bits -= ab
+        h = min(h, n_log + r)
+        rng = np.random.default_rng(seed)
+        data = [rand_field(rng, (k, n), canonical=False) for k in ks]
+        gpu = [z.PolynomialBatch.from_coeffs(d, r, False, h, ctx=ctx) for d in data]
+        cpu = [oracle.commit(d, r, h, is_coeffs=True) for d in data]
+        zeta = [rand_ext(rng), (int(rng.integers(1, P, dtype=np.uint64)), 0), (0, 0), (P - 1, P - 1)][point_kind]
+        batches = [(zeta, [(o, i) for o, k in enumerate(ks) for i in range(k)]),
+                   (F.escale(zeta, F.root(n_log)), [(len(ks) - 1, 0)])]
+        inst = zf.FriInstanceInfo([zf.FriBatchInfo(pt, [zf.FriPolynomialInfo(o, i) for o, i in polys]) for pt, polys in batches])
+        cfg = zf.FriConfig(rate_bits=r, cap_height=h, proof_of_work_bits=3, num_query_rounds=3)
+        params = zf.FriParams(config=cfg, hiding=False, degree_bits=n_log, reduction_arity_bits=valid)
+        ch_g, ch_c = zf.Challenger(ctx), F.Challenger()
+        for b, c in zip(gpu, cpu):
+            ch_g.observe_cap(b._cap)
+            ch_c.observe_cap(c["cap"])
+        got = zf.prove_openings(inst, gpu, ch_g, params, mul_by_x)
+        want = F.prove_openings(cpu, batches, ch_c, r, h, valid, 3, 3, mul_by_x)
+        form = proof_to_oracle_form(got)
+        assert form["final_poly"] == want["final_poly"] and form["pow_witness"] == want["pow_witness"]
+        assert all((a == b).all() for a, b in zip(form["caps"], want["caps"]))
+        for rg, rc in zip(form["rounds"], want["rounds"]):
+            assert all((a[0] == b[0]).all() and (a[1] == b[1]).all() for a, b in zip(rg["initial"], rc["initial"]))
+            assert all((a[0] == b[0]).all() and (a[1] == b[1]).all() for a, b in zip(rg["steps"], rc["steps"]))
+        # (x - z = 0 needs z on the LDE coset 7<w_N>: neither the random nor the special points above are)
+        openings = [[tuple(int(v) for v in oracle.eval_ext2(cpu[o]["coeffs"][i], np.array(pt, dtype=np.uint64))) for o, i in polys]
+                    for pt, polys in batches]
+        fresh = F.Challenger()
+        for c in cpu:
+            fresh.observe_cap(c["cap"])
+        if True:
+            assert F.verify(form, [c["cap"] for c in cpu], batches, openings, fresh, n_log, r, h, valid, 3, 3, mul_by_x)
+
+    run()
