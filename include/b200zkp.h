@@ -188,7 +188,7 @@ int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, 
 
 /* ---- device-resident stages (caller-owned device buffers; async on the ctx stream) --------- */
 /* values [k][in_stride] -> coeffs [k][out_stride], natural order.  scratch: k*n elements, may alias
- * nothing; needed when n_log > 8 (may be NULL otherwise). */
+ * nothing; needed when n_log > 10 (may be NULL otherwise). */
 int b200zkp_dev_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
                      uint64_t out_stride, uint64_t* scratch, uint32_t n_log, uint32_t k);
 /* coeffs [k][coeff_stride] -> lde [k][lde_stride] in leaf order, only leaf blocks

@@ -37,7 +37,7 @@ struct b200zkp_ctx {
     std::mutex mu;
     std::string err;
     u64 launches = 0;
-    u64* wtab[2][9] = {};                               // [dir][B] w_{2^B}^(+-e)
+    u64* wtab[2][ntt::MAX_PASS_BITS + 1] = {};          // [dir][B] w_{2^B}^(+-e)
     std::map<u32, TwoLevel> tw[2];                      // [dir][n_log] -> w_n^(+-e)
     std::map<u64, std::vector<TwoLevel>> coset;         // (n_log<<8 | rate_bits) -> per leaf block (builder input)
     std::map<u32, TwoLevel> shift7;                     // N_log -> 7^i (natural-order coset_lde helper, builder input)
@@ -190,14 +190,14 @@ static int get_coset(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const std::vect
 template <int B>
 static void launch_pass_b(const ntt::PassParams& p, dim3 grid, cudaStream_t s) {
     switch (ntt::pass_mode(p)) {
-        case ntt::MODE_MID_NATURAL: ntt::ntt_pass_kernel<B, ntt::MODE_MID_NATURAL><<<grid, ntt::THREADS, 0, s>>>(p); break;
-        case ntt::MODE_MID_BITREV: ntt::ntt_pass_kernel<B, ntt::MODE_MID_BITREV><<<grid, ntt::THREADS, 0, s>>>(p); break;
-        case ntt::MODE_FINAL_BITREV: ntt::ntt_pass_kernel<B, ntt::MODE_FINAL_BITREV><<<grid, ntt::THREADS, 0, s>>>(p); break;
-        default: ntt::ntt_pass_kernel<B, ntt::MODE_FINAL_NATURAL><<<grid, ntt::THREADS, 0, s>>>(p); break;
+        case ntt::MODE_MID_NATURAL: ntt::ntt_pass_kernel<B, ntt::MODE_MID_NATURAL><<<grid, ntt::threads_for(B), 0, s>>>(p); break;
+        case ntt::MODE_MID_BITREV: ntt::ntt_pass_kernel<B, ntt::MODE_MID_BITREV><<<grid, ntt::threads_for(B), 0, s>>>(p); break;
+        case ntt::MODE_FINAL_BITREV: ntt::ntt_pass_kernel<B, ntt::MODE_FINAL_BITREV><<<grid, ntt::threads_for(B), 0, s>>>(p); break;
+        default: ntt::ntt_pass_kernel<B, ntt::MODE_FINAL_NATURAL><<<grid, ntt::threads_for(B), 0, s>>>(p); break;
     }
 }
 static int launch_pass(b200zkp_ctx* ctx, const ntt::PassParams& p, u32 B, u32 n_blk) {
-    u64 T = ntt::TILE_ELEMS >> B;
+    u64 T = (u64)ntt::tile_elems_for((int)B) >> B;
     u64 total_batches = (u64)p.ncols << (p.n_log - B);
     u64 blocks = (total_batches + T - 1) / T;
     if (blocks == 0 || n_blk == 0) return 0;
@@ -212,6 +212,8 @@ static int launch_pass(b200zkp_ctx* ctx, const ntt::PassParams& p, u32 B, u32 n_
         case 6: launch_pass_b<6>(p, grid, ctx->stream); break;
         case 7: launch_pass_b<7>(p, grid, ctx->stream); break;
         case 8: launch_pass_b<8>(p, grid, ctx->stream); break;
+        case 9: launch_pass_b<9>(p, grid, ctx->stream); break;
+        case 10: launch_pass_b<10>(p, grid, ctx->stream); break;
         default: BAD(ctx, "internal: bad pass width");
     }
     LAUNCH_CHECK(ctx);
@@ -297,7 +299,7 @@ static int run_transform(b200zkp_ctx* ctx, const u64* in, u64 in_stride, u64* ou
         return 0;
     }
     if (n_log > 32) BAD(ctx, "n_log exceeds the field's two-adicity (32)");
-    if (!bitrev_out && n_log > 8 && !scratch) BAD(ctx, "scratch buffer required for n_log > 8");
+    if (!bitrev_out && n_log > (u32)ntt::MAX_PASS_BITS && !scratch) BAD(ctx, "scratch buffer required for multi-pass natural-order transforms");
     b200zkp_ctx::Images im;
     TRY(get_twiddle_images(ctx, n_log, dir, bitrev_out, &im));
     ntt::TransformTables tb{};
@@ -325,7 +327,7 @@ extern "C" int b200zkp_device_count(void) {
 
 static int ctx_init_tables(b200zkp_ctx* ctx) {
     for (int dir = 0; dir < 2; dir++)
-        for (u32 B = 1; B <= 8; B++) TRY(upload(ctx, hostgl::small_root_table(B, dir), &ctx->wtab[dir][B]));
+        for (u32 B = 1; B <= (u32)ntt::MAX_PASS_BITS; B++) TRY(upload(ctx, hostgl::small_root_table(B, dir), &ctx->wtab[dir][B]));
     return 0;
 }
 

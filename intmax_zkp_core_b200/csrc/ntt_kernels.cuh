@@ -7,7 +7,7 @@
 // A12.  Reached from the reference through PolynomialBatch::from_values / from_coeffs inside every
 // prove()/build(), e.g. /root/reference/src/transaction/circuits/mod.rs:158,453.
 //
-// A transform of 2^L points is split into P = ceil(L/8) passes (Cooley-Tukey / "4-step"):
+// A transform of 2^L points is split into P = ceil(L/8) passes, one pass for L <= 10 (Cooley-Tukey / "4-step"):
 //   pass p views a column as [A][2^B][C]; a CTA stages a tile of 2^B x T elements (T batches of the
 //   contiguous inner dimension, so every global access is a run of >= 64 B) in shared memory, runs the
 //   2^B-point decimation-in-frequency sub-transform with radix-8 butterflies held in registers (one
@@ -26,9 +26,17 @@ namespace ntt {
 using gl::u32;
 using gl::u64;
 
-static constexpr int TILE_ELEMS = 2048;  // elements staged per CTA
+static constexpr int TILE_ELEMS = 2048;  // elements staged per CTA (passes of up to 8 bits)
 static constexpr int THREADS = 256;      // 8 elements per thread
+static constexpr int MAX_PASS_BITS = 10; // 9- and 10-bit passes stage 4096 elements with 512 threads (>= 4 batches per tile)
 static constexpr int MAX_PASSES = 4;
+#ifdef __CUDACC__
+#define NTT_CONSTEXPR_FN __host__ __device__ constexpr
+#else
+#define NTT_CONSTEXPR_FN constexpr
+#endif
+NTT_CONSTEXPR_FN int tile_elems_for(int B) { return B >= 9 ? 2 * TILE_ELEMS : TILE_ELEMS; }
+NTT_CONSTEXPR_FN int threads_for(int B) { return B >= 9 ? 2 * THREADS : THREADS; }
 
 enum OutMode : u32 {
     OUT_INPLACE_NATURAL = 0,  // non-final pass, element k1 stored at (a, k1, c)
@@ -95,7 +103,7 @@ GL_FN void dif_group(u64 (&x)[1 << A], const u64* __restrict__ wt, u32 ul, u32 s
     }
 }
 
-template <int A, bool LAST = false>
+template <int A, int NTHREADS, bool LAST = false>
 GL_FN void run_round(u64* __restrict__ tile, const u64* __restrict__ wt, u32 B, u32 T, u32 TP, u32 sigma0,
                      u32 tid) {
     const u32 st_log = LAST ? 0u : B - sigma0 - A;
@@ -103,7 +111,7 @@ GL_FN void run_round(u64* __restrict__ tile, const u64* __restrict__ wt, u32 B, 
     constexpr int UNITS_PER_THREAD = 8 >> A;
 #pragma unroll
     for (int r = 0; r < UNITS_PER_THREAD; r++) {
-        u32 U = tid + r * THREADS;
+        u32 U = tid + r * NTHREADS;
         u32 t = U % T, w = U / T;
         u32 ul = w & (st - 1), uh = w >> st_log;
         u32 gbase = (uh << (st_log + A)) + ul;
@@ -150,6 +158,8 @@ static inline int pass_mode(const PassParams& p) {   // host side (launcher / em
 // B = bits of this pass (1..8, compile time so the rounds fully unroll); block = CTA index, blk = coset block
 template <int B, int MODE>
 GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
+    constexpr int TILE_ELEMS = tile_elems_for(B);        // (shadow the 8-bit defaults of the namespace)
+    constexpr int THREADS = threads_for(B);
     constexpr u32 T = TILE_ELEMS >> B;
     constexpr u32 TP = T + 1;
     constexpr u32 NPTS = 1u << B;
@@ -258,17 +268,17 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
         u32 sigma = 0;
         // the short round (B mod 3 levels) goes first so that the closing round is a full radix-8 group with unit stride:
         // 7 of its 12 twiddles are 1 and known at compile time
-        if (B > 3 && B % 3 == 2) { NTT_FOR_THREADS(tid) { run_round<2>(tile, wt, B, T, TP, sigma, tid); } sigma += 2; NTT_SYNC(); }
-        if (B > 3 && B % 3 == 1) { NTT_FOR_THREADS(tid) { run_round<1>(tile, wt, B, T, TP, sigma, tid); } sigma += 1; NTT_SYNC(); }
+        if (B > 3 && B % 3 == 2) { NTT_FOR_THREADS(tid) { run_round<2, THREADS>(tile, wt, B, T, TP, sigma, tid); } sigma += 2; NTT_SYNC(); }
+        if (B > 3 && B % 3 == 1) { NTT_FOR_THREADS(tid) { run_round<1, THREADS>(tile, wt, B, T, TP, sigma, tid); } sigma += 1; NTT_SYNC(); }
 #pragma unroll 1   // one copy of the radix-8 round in the instruction cache; stride and twiddle step are run-time
         for (int r = 0; r < B / 3 - 1; r++) {
-            NTT_FOR_THREADS(tid) { run_round<3>(tile, wt, B, T, TP, sigma, tid); }
+            NTT_FOR_THREADS(tid) { run_round<3, THREADS>(tile, wt, B, T, TP, sigma, tid); }
             sigma += 3;
             NTT_SYNC();
         }
-        if (B >= 3) { NTT_FOR_THREADS(tid) { run_round<3, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
-        if (B == 2) { NTT_FOR_THREADS(tid) { run_round<2, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
-        if (B == 1) { NTT_FOR_THREADS(tid) { run_round<1, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B >= 3) { NTT_FOR_THREADS(tid) { run_round<3, THREADS, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B == 2) { NTT_FOR_THREADS(tid) { run_round<2, THREADS, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
+        if (B == 1) { NTT_FOR_THREADS(tid) { run_round<1, THREADS, true>(tile, wt, B, T, TP, sigma, tid); } NTT_SYNC(); }
     }
 
     // ---- twiddle + store
@@ -358,7 +368,7 @@ GL_FN void pass_body(const PassParams& p, u32 block, u32 blk) {
 
 #ifndef B200ZKP_HOST_EMU
 template <int B, int MODE>
-__global__ void __launch_bounds__(THREADS, 4) ntt_pass_kernel(PassParams p) { pass_body<B, MODE>(p, blockIdx.x, blockIdx.y); }
+__global__ void __launch_bounds__(threads_for(B), B >= 9 ? 2 : 4) ntt_pass_kernel(PassParams p) { pass_body<B, MODE>(p, blockIdx.x, blockIdx.y); }
 
 // table builders (run once per (n_log, direction, rate_bits) and cached by the context)
 // out[i] = base^i for i < count, from the two-level power tables of `base`

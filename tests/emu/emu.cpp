@@ -14,7 +14,7 @@ using gl::u32;
 using gl::u64;
 
 static void run_pass(const ntt::PassParams& p, u32 B, u32 n_blk) {
-    u64 T = ntt::TILE_ELEMS >> B;
+    u64 T = (u64)ntt::tile_elems_for((int)B) >> B;
     u64 total_batches = (u64)p.ncols << (p.n_log - B);
     u64 blocks = (total_batches + T - 1) / T;
     for (u32 y = 0; y < n_blk; y++)
@@ -28,14 +28,14 @@ static void run_pass(const ntt::PassParams& p, u32 B, u32 n_blk) {
             default: ntt::pass_body<BB, ntt::MODE_FINAL_NATURAL>(p, (u32)blk, y); break;                       \
         }                                                                                                      \
         break;
-            switch (B) { EMU_PASS(1) EMU_PASS(2) EMU_PASS(3) EMU_PASS(4) EMU_PASS(5) EMU_PASS(6) EMU_PASS(7) EMU_PASS(8) }
+            switch (B) { EMU_PASS(1) EMU_PASS(2) EMU_PASS(3) EMU_PASS(4) EMU_PASS(5) EMU_PASS(6) EMU_PASS(7) EMU_PASS(8) EMU_PASS(9) EMU_PASS(10) }
 #undef EMU_PASS
         }
 }
 
 struct Tables {
-    std::vector<u64> w[2][9];
-    Tables() { for (int d = 0; d < 2; d++) for (u32 B = 1; B <= 8; B++) w[d][B] = hostgl::small_root_table(B, d); }
+    std::vector<u64> w[2][ntt::MAX_PASS_BITS + 1];
+    Tables() { for (int d = 0; d < 2; d++) for (u32 B = 1; B <= (u32)ntt::MAX_PASS_BITS; B++) w[d][B] = hostgl::small_root_table(B, d); }
 };
 static Tables g_tab;
 
@@ -65,8 +65,8 @@ static void transform(const u64* in, u64 in_stride, u64* out, u64 out_stride, u6
         return;
     }
     u64 n = (u64)1 << n_log;
-    u64* wt[9];
-    for (u32 B = 0; B <= 8; B++) wt[B] = B ? g_tab.w[dir][B].data() : nullptr;
+    u64* wt[ntt::MAX_PASS_BITS + 1];
+    for (u32 B = 0; B <= (u32)ntt::MAX_PASS_BITS; B++) wt[B] = B ? g_tab.w[dir][B].data() : nullptr;
     ntt::TwiddleImageShape shapes[ntt::MAX_PASSES];
     u32 n_img = ntt::twiddle_images(n_log, shapes);
     u64 n_inv = hostgl::inv(n % hostgl::P);

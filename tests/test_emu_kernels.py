@@ -79,7 +79,7 @@ def test_digest_slots_match_recursive_layout(emu, oracle):
             assert (cap[s] == layer[0]).all()
 
 
-@pytest.mark.parametrize("n_log", [0, 1, 2, 3, 4, 6, 8, 9, 11, 12, 16, 17])
+@pytest.mark.parametrize("n_log", [0, 1, 2, 3, 4, 6, 8, 9, 10, 11, 12, 16, 17, 19, 20])
 def test_ntt_pass_bodies(emu, oracle, n_log):
     rng = np.random.default_rng(100 + n_log)
     k = 3 if n_log < 14 else 1
