@@ -34,7 +34,7 @@ def golden():
     import json
     d = os.path.join(ROOT, "tests", "golden")
     out = {}
-    for name in ("reference_poseidon_kats", "commit_vectors"):
+    for name in ("reference_poseidon_kats", "commit_vectors", "opening_proof_vectors"):
         with open(os.path.join(d, name + ".json")) as f:
             out[name] = json.load(f)
     return out

@@ -10,6 +10,9 @@
    SplitMix64 inputs.  The reference holds no NTT / LDE / cap fixture, so these are oracle-derived
    ("parity unpinned"); they freeze the oracle's behaviour and are cross-checked against SURVEY.md App. C,
    which was derived independently from O(n^2) definitions.
+3. opening_proof_vectors.json — opening proofs (prove_openings / fri_proof) produced by the CPU restatement
+   oracle/fri_ref.py on SplitMix64 coefficients, accepted by its verifier at generation time.  Oracle-derived as well
+   ("parity unpinned": the reference holds no proof fixture); they freeze the restatement and are re-checked on the GPU.
 Nothing under tests/ reads /root/reference at run time; only this generator does.
 """
 import json
@@ -99,9 +102,73 @@ def commit_vectors():
     return {"_comment": "oracle-derived (oracle/oracle.c); the reference pins nothing here — parity unpinned", "cases": cases}
 
 
+def proof_words(proof):
+    """Every field element of a proof in a fixed order (caps, final_poly, witness, query answers)."""
+    words = []
+    for cap in proof["caps"]:
+        words += [int(x) for x in cap.reshape(-1)]
+    for a, b in proof["final_poly"]:
+        words += [int(a), int(b)]
+    words.append(int(proof["pow_witness"]))
+    for rnd in proof["rounds"]:
+        for row, sib in rnd["initial"]:
+            words += [int(x) for x in row] + [int(x) for x in sib.reshape(-1)]
+        for ev, sib in rnd["steps"]:
+            words += [int(x) for x in ev.reshape(-1)] + [int(x) for x in sib.reshape(-1)]
+    return words
+
+
+def fnv(words):
+    d = 0xcbf29ce484222325
+    for w in words:
+        d = ((d ^ w) * 0x100000001b3) % 2**64
+    return d
+
+
+def opening_proof_vectors():
+    import numpy as np
+    from oracle import oracle as O
+    from oracle import fri_ref as F
+    cases = []
+    for (n_log, ks, r, h, arities, pow_bits, nq, mul_by_x) in [
+            (5, (3, 2), 2, 1, (2, 1), 6, 4, True), (5, (3, 2), 2, 1, (2, 1), 6, 4, False),
+            (6, (4, 1, 2), 3, 2, (3, 2), 8, 5, True), (4, (2,), 3, 0, (), 4, 3, True), (8, (5, 3), 3, 4, (4,), 10, 6, True)]:
+        n = 1 << n_log
+        commits = [O.commit(O.synthetic_values(k, n, seed=o + 1), r, h, is_coeffs=True) for o, k in enumerate(ks)]
+        zeta = (int(O.splitmix64(np.array([1000 + n_log], dtype=np.uint64))[0]) % O.P,
+                int(O.splitmix64(np.array([2000 + n_log], dtype=np.uint64))[0]) % O.P)
+        gzeta = F.escale(zeta, F.root(n_log))
+        batches = [(zeta, [(o, i) for o, k in enumerate(ks) for i in range(k)]), (gzeta, [(len(ks) - 1, 0)])]
+        ch = F.Challenger()
+        for c in commits:
+            ch.observe_cap(c["cap"])
+        proof = F.prove_openings(commits, batches, ch, r, h, arities, pow_bits, nq, mul_by_x)
+        openings = [[tuple(int(v) for v in O.eval_ext2(commits[o]["coeffs"][i], np.array(pt, dtype=np.uint64))) for o, i in polys]
+                    for pt, polys in batches]
+        fresh = F.Challenger()
+        for c in commits:
+            fresh.observe_cap(c["cap"])
+        assert F.verify(proof, [c["cap"] for c in commits], batches, openings, fresh, n_log, r, h, arities, pow_bits, nq, mul_by_x)
+        cases.append({
+            "n_log": n_log, "ks": list(ks), "rate_bits": r, "cap_height": h, "arities": list(arities), "pow_bits": pow_bits,
+            "num_queries": nq, "mul_by_x": mul_by_x,
+            "input": "oracle o = from_coeffs(splitmix64(((o+1) << 48) + c*n + i) mod p); transcript = observe_cap of each oracle",
+            "zeta": list(zeta), "points": "batch 0: every polynomial at zeta; batch 1: polynomial 0 of the last oracle at w_n * zeta",
+            "final_poly": [[int(a), int(b)] for a, b in proof["final_poly"]],
+            "commit_phase_caps_row0": [[int(x) for x in cap[0]] for cap in proof["caps"]],
+            "pow_witness": int(proof["pow_witness"]),
+            "x_indices": [int(rnd["x_index"]) for rnd in proof["rounds"]],
+            "proof_fnv1a64": "%016x" % fnv(proof_words(proof)),
+        })
+    return {"_comment": "oracle-derived (oracle/fri_ref.py), accepted by its verifier; the reference pins nothing here — parity unpinned",
+            "cases": cases}
+
+
 if __name__ == "__main__":
     with open(os.path.join(HERE, "reference_poseidon_kats.json"), "w") as f:
         json.dump(reference_kats(), f, indent=1)
     with open(os.path.join(HERE, "commit_vectors.json"), "w") as f:
         json.dump(commit_vectors(), f, indent=1)
-    print("wrote reference_poseidon_kats.json, commit_vectors.json")
+    with open(os.path.join(HERE, "opening_proof_vectors.json"), "w") as f:
+        json.dump(opening_proof_vectors(), f, indent=1)
+    print("wrote reference_poseidon_kats.json, commit_vectors.json, opening_proof_vectors.json")

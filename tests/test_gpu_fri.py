@@ -297,3 +297,31 @@ def test_hypothesis_opening_proofs(zf, ctx, oracle):
             assert F.verify(form, [c["cap"] for c in cpu], batches, openings, fresh, n_log, r, h, valid, 3, 3, mul_by_x)
 
     run()
+
+
+def test_golden_opening_proof_vectors_on_gpu(zf, ctx, oracle, golden):
+    """The committed opening-proof vectors (tests/golden/opening_proof_vectors.json) reproduced through the C ABI."""
+    import os
+    import sys
+    import intmax_zkp_core_b200 as z
+    from oracle import fri_ref as F
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as G
+    for case in golden["opening_proof_vectors"]["cases"]:
+        n_log, ks, r, h = case["n_log"], case["ks"], case["rate_bits"], case["cap_height"]
+        gpu = [z.PolynomialBatch.from_coeffs(oracle.synthetic_values(k, 1 << n_log, seed=o + 1), r, False, h, ctx=ctx)
+               for o, k in enumerate(ks)]
+        zeta = tuple(case["zeta"])
+        inst = zf.FriInstanceInfo([
+            zf.FriBatchInfo(zeta, [zf.FriPolynomialInfo(o, i) for o, k in enumerate(ks) for i in range(k)]),
+            zf.FriBatchInfo(F.escale(zeta, F.root(n_log)), [zf.FriPolynomialInfo(len(ks) - 1, 0)])])
+        cfg = zf.FriConfig(rate_bits=r, cap_height=h, proof_of_work_bits=case["pow_bits"], num_query_rounds=case["num_queries"])
+        params = zf.FriParams(config=cfg, hiding=False, degree_bits=n_log, reduction_arity_bits=list(case["arities"]))
+        ch = zf.Challenger(ctx)
+        for b in gpu:
+            ch.observe_cap(b._cap)
+        proof = proof_to_oracle_form(zf.prove_openings(inst, gpu, ch, params, case["mul_by_x"]))
+        assert [list(e) for e in proof["final_poly"]] == case["final_poly"]
+        assert proof["pow_witness"] == case["pow_witness"]
+        assert [[int(x) for x in cap[0]] for cap in proof["caps"]] == case["commit_phase_caps_row0"]
+        assert "%016x" % G.fnv(G.proof_words(proof)) == case["proof_fnv1a64"]

@@ -101,3 +101,33 @@ def test_challenger_matches_sponge_definition(oracle):
     ch.observe_element(5)                                   # partial buffer: overwrite word 0 only, then permute
     st2 = out.copy(); st2[0] = 5
     assert ch.get_challenge() == int(oracle.permute(st2)[7])
+
+
+def golden_case_inputs(O, F, case):
+    n = 1 << case["n_log"]
+    coeffs = [O.synthetic_values(k, n, seed=o + 1) for o, k in enumerate(case["ks"])]
+    zeta = tuple(case["zeta"])
+    ks = case["ks"]
+    batches = [(zeta, [(o, i) for o, k in enumerate(ks) for i in range(k)]),
+               (F.escale(zeta, F.root(case["n_log"])), [(len(ks) - 1, 0)])]
+    return coeffs, batches
+
+
+def test_golden_opening_proof_vectors(oracle, golden):
+    """The committed vectors (tests/golden/make_golden.py) freeze the restatement: regenerate and compare."""
+    from oracle import fri_ref as F
+    sys_path_golden = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+    __import__("sys").path.insert(0, sys_path_golden)
+    import make_golden as G
+    for case in golden["opening_proof_vectors"]["cases"]:
+        coeffs, batches = golden_case_inputs(oracle, F, case)
+        r, h = case["rate_bits"], case["cap_height"]
+        commits = [oracle.commit(c, r, h, is_coeffs=True) for c in coeffs]
+        ch = F.Challenger()
+        for c in commits:
+            ch.observe_cap(c["cap"])
+        proof = F.prove_openings(commits, batches, ch, r, h, case["arities"], case["pow_bits"], case["num_queries"], case["mul_by_x"])
+        assert [[int(a), int(b)] for a, b in proof["final_poly"]] == case["final_poly"]
+        assert proof["pow_witness"] == case["pow_witness"]
+        assert [rnd["x_index"] for rnd in proof["rounds"]] == case["x_indices"]
+        assert "%016x" % G.fnv(G.proof_words(proof)) == case["proof_fnv1a64"]
