@@ -347,16 +347,19 @@ def run_b200(args):
                 ctx.check(ctx._lib.b200zkp_int_pipe_bench(ctx._h, kind, 2000, C.byref(g)))
                 gips[name] = g.value
             line["int_pipe"] = {"unit": "giga thread-instructions/s (dependent chains, all SMs)", **gips}
-            # second roof of SURVEY.md 8d: the leaf hash against the measured integer-multiply issue rate.  2720 IMAD.WIDE per
-            # permutation is the dynamic count of the shipped kernel (profiles/README.md); the multiplier pipe also issues the
-            # 32-bit IMADs of the MDS layers and the adds ptxas places there, which is why ncu reports it 92 % busy.
+            # second roof of SURVEY.md 8d: the leaf hash against the measured issue rate of the integer-multiply (fmaheavy) pipe.
+            # Dynamic instruction mix per permutation of the shipped kernel (ncu source counters, profiles/README.md):
+            # 3089 IMAD.WIDE (2 pipe slots each: they issue at half the IMAD rate) + 9342 single-slot instructions on the same pipe
+            # (4270 IMAD of the MDS layers, 5072 IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL that ptxas places there).
             leaf_perms = N_local * ((k + 7) // 8)
-            wide_rate = leaf_perms * 2720 / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
-            wide_peak = max(gips["imad_wide"], gips["imad_wide_noacc"]) * 1e9
-            line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": wide_rate, "peak": wide_peak,
-                                       "unit": "IMAD.WIDE.U32 thread-instr/s", "frac": wide_rate / wide_peak,
-                                       "imad_wide_per_permutation": 2720, "permutations_per_launch": leaf_perms,
-                                       "ncu_pipe_fmaheavy_busy": 0.923}
+            slots_per_perm = 2 * 3089 + 9342
+            slot_rate = leaf_perms * slots_per_perm / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
+            slot_peak = gips["imad"] * 1e9
+            line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": slot_rate, "peak": slot_peak,
+                                       "unit": "IMAD-slot thread-instr/s (IMAD.WIDE = 2 slots)", "frac": slot_rate / slot_peak,
+                                       "slots_per_permutation": slots_per_perm, "imad_wide_per_permutation": 3089,
+                                       "algorithmic_multiplies_per_permutation": {"imad_wide": 3089, "imad": 4270},
+                                       "permutations_per_launch": leaf_perms, "ncu_pipe_fmaheavy_busy": 0.923}
             if not os.environ.get("B200ZKP_SKIP_CPU"):
                 from oracle import oracle as O
                 O.build()
