@@ -31,5 +31,19 @@ z.coset_lde_batch(x, 2, ctx)
 t = z.MerkleTree.new(np.arange(64 * 7, dtype=np.uint64).reshape(64, 7), 2, ctx=ctx)
 t.prove(5); t.digests
 z.PoseidonHash.hash_no_pad_batch(np.arange(40, dtype=np.uint64).reshape(4, 10), ctx)
+# opening proof (rows N2 + N3): evaluation, alpha-reduction, blocked suffix scan over > 1 segment, FRI layers, PoW, gathers
+import intmax_zkp_core_b200.fri as zf
+for (n_log, ks, r, h, arities, mul_by_x) in [(12, (3, 2), 1, 2, (4, 3), True), (5, (2,), 3, 0, (2, 1), False), (1, (1, 1), 0, 0, (), True)]:
+    batches = [z.PolynomialBatch.from_coeffs(O.synthetic_values(k, 1 << n_log, seed=3 + i), r, False, h, ctx=ctx) for i, k in enumerate(ks)]
+    batches[0].eval_ext2(np.array([5, 6], np.uint64))
+    inst = zf.FriInstanceInfo([zf.FriBatchInfo((11, 12), [zf.FriPolynomialInfo(o, i) for o, k in enumerate(ks) for i in range(k)]),
+                               zf.FriBatchInfo((13, 0), [zf.FriPolynomialInfo(0, 0)])])
+    cfg = zf.FriConfig(rate_bits=r, cap_height=h, proof_of_work_bits=5, num_query_rounds=4)
+    params = zf.FriParams(config=cfg, hiding=False, degree_bits=n_log, reduction_arity_bits=list(arities))
+    ch = zf.Challenger(ctx)
+    for b in batches:
+        ch.observe_cap(b._cap)
+    proof = zf.prove_openings(inst, batches, ch, params, mul_by_x)
+    assert len(proof.query_round_proofs) == 4
 print("sanitize smoke ok, launches:", ctx.launch_count)
 ctx.close()
