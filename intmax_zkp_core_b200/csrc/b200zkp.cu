@@ -47,6 +47,7 @@ struct b200zkp_ctx {
     std::map<u64, u64*> coset_scale;                    // (n_log<<8 | rate_bits) -> [2^rate_bits][n] shift powers
     std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
     std::map<std::pair<u64, u32>, u64*> power_scale;    // (shift, bits) -> shift^i, i < 2^bits (FRI layer cosets)
+    u64* round_add = nullptr;                           // poseidon_tables::ROUND_ADD in global memory (latency-form kernels)
     std::multimap<size_t, void*> pool;                  // cached device allocations
     std::vector<void*> table_allocs;
     // second, higher-priority stream: coset transforms run here while finished blocks are hashed on `stream`
@@ -326,6 +327,9 @@ extern "C" int b200zkp_device_count(void) {
 }
 
 static int ctx_init_tables(b200zkp_ctx* ctx) {
+    TRY(table_alloc(ctx, 360, &ctx->round_add));
+    CUDA_TRY(ctx, cudaMemcpyFromSymbolAsync(ctx->round_add, poseidon_tables::ROUND_ADD, 360 * sizeof(u64), 0,
+                                            cudaMemcpyDeviceToDevice, ctx->stream));
     for (int dir = 0; dir < 2; dir++)
         for (u32 B = 1; B <= (u32)ntt::MAX_PASS_BITS; B++) TRY(upload(ctx, hostgl::small_root_table(B, dir), &ctx->wtab[dir][B]));
     return 0;
@@ -506,10 +510,18 @@ static unsigned hash_block_threads(u64 n_items) {
     return t;
 }
 
+static constexpr u64 COOP_MAX_NODES = 2048;   // below this the latency form of the permutation wins (merkle_kernels.cuh)
+
 static int launch_leaf_hash(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 row0,
                             u64 n_rows, const merkle::TreeShape& shape, u64* digests, u64* cap) {
     if (!n_rows) return 0;
     StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
+    if (n_rows <= COOP_MAX_NODES) {
+        merkle::leaf_hash_coop_kernel<<<(unsigned)((n_rows * 16 + 127) / 128), 128, 0, ctx->stream>>>(
+            leaves, row_stride, col_stride, leaf_len, row0, n_rows, shape, digests, cap, 1u, ctx->round_add);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    }
     unsigned threads = hash_block_threads(n_rows);
     u64 blocks = (n_rows + threads - 1) / threads;
     merkle::leaf_hash_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(leaves, row_stride, col_stride, leaf_len,
@@ -522,9 +534,15 @@ static int launch_tree_levels(b200zkp_ctx* ctx, u64 n_leaves, const merkle::Tree
     StageTimer tm(ctx, B200ZKP_STAGE_TREE);
     for (u32 layer = 0; layer < shape.sub_log; layer++) {
         u64 n_parents = n_leaves >> (layer + 1);
-        unsigned threads = hash_block_threads(n_parents);
-        u64 blocks = (n_parents + threads - 1) / threads;
-        merkle::merkle_level_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
+        if (n_parents <= COOP_MAX_NODES) {
+            // too few nodes to fill the GPU: one node per 16 lanes, ~4x less latency per level
+            merkle::merkle_level_coop_kernel<<<(unsigned)((n_parents * 16 + 127) / 128), 128, 0, ctx->stream>>>(
+                digests, cap, shape, layer, n_parents, ctx->round_add);
+        } else {
+            unsigned threads = hash_block_threads(n_parents);
+            u64 blocks = (n_parents + threads - 1) / threads;
+            merkle::merkle_level_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(digests, cap, shape, layer, n_parents);
+        }
         LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -1477,7 +1495,10 @@ extern "C" int b200zkp_poseidon_permute(b200zkp_ctx* ctx, const uint64_t* in, ui
     if (!count) return 0;
     if (!in || !out) BAD(ctx, "null buffer");
     return with_io(ctx, in, count * 96, out, count * 96, [&](u64* di, u64* dout) -> int {
-        merkle::permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(di, dout, count);
+        if (count <= COOP_MAX_NODES)
+            merkle::permute_coop_kernel<<<(unsigned)((count * 16 + 127) / 128), 128, 0, ctx->stream>>>(di, nullptr, dout, count, 0u, ctx->round_add);
+        else
+            merkle::permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(di, dout, count);
         LAUNCH_CHECK(ctx);
         return 0;
     });
@@ -1488,7 +1509,10 @@ static int hash_rows(b200zkp_ctx* ctx, const u64* in, u64 count, u32 len, u64* o
     if ((!in && len) || !out) BAD(ctx, "null buffer");
     return with_io(ctx, in, count * len * 8, out, count * 32, [&](u64* di, u64* dout) -> int {
         merkle::TreeShape shape; shape.sub_log = 0; shape.sub_digests = 0;
-        merkle::leaf_hash_kernel<<<(unsigned)((count + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS), B200ZKP_HASH_THREADS, 0, ctx->stream>>>(di, len, 1, len, 0, count, shape, nullptr, dout, noop_short ? 1u : 0u);
+        if (count <= COOP_MAX_NODES)
+            merkle::leaf_hash_coop_kernel<<<(unsigned)((count * 16 + 127) / 128), 128, 0, ctx->stream>>>(di, len, 1, len, 0, count, shape, nullptr, dout, noop_short ? 1u : 0u, ctx->round_add);
+        else
+            merkle::leaf_hash_kernel<<<(unsigned)((count + B200ZKP_HASH_THREADS - 1) / B200ZKP_HASH_THREADS), B200ZKP_HASH_THREADS, 0, ctx->stream>>>(di, len, 1, len, 0, count, shape, nullptr, dout, noop_short ? 1u : 0u);
         LAUNCH_CHECK(ctx);
         return 0;
     });
@@ -1514,7 +1538,10 @@ extern "C" int b200zkp_two_to_one(b200zkp_ctx* ctx, const uint64_t* left, const 
     TRY(dev_alloc(ctx, count * 32, &d_r));
     int rc = h2d(ctx, d_r, right, count * 32);
     if (!rc) rc = with_io(ctx, left, count * 32, out, count * 32, [&](u64* dl, u64* dout) -> int {
-        merkle::two_to_one_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(dl, (const u64*)d_r, dout, count);
+        if (count <= COOP_MAX_NODES)
+            merkle::permute_coop_kernel<<<(unsigned)((count * 16 + 127) / 128), 128, 0, ctx->stream>>>(dl, (const u64*)d_r, dout, count, 1u, ctx->round_add);
+        else
+            merkle::two_to_one_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(dl, (const u64*)d_r, dout, count);
         LAUNCH_CHECK(ctx);
         return 0;
     });
@@ -1636,6 +1663,7 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
     u32 x[8];
     double d[8];
     const double dc = 1.0 + 1e-9 * (double)(b & 7);
+    const u32 uz = poseidon::OPAQUE_ZERO;
 #pragma unroll
     for (int i = 0; i < 8; i++) { w[i] = ((u64)(a + i) << 32) | (b * (i + 3)); x[i] = a * (2 * i + 1) + b; d[i] = 1.0 + 1e-6 * (double)(a & 1023) * (i + 1); }
     for (u32 it = 0; it < iters; it++) {
@@ -1672,9 +1700,32 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
                 } else if (KIND == 11) {  // alternating DFMA / IMAD (32-bit)
                     if (i & 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dc), "d"(d[(i + 2) & 7]));
                     else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
-                } else {                  // KIND 12: alternating DFMA / LOP3
+                } else if (KIND == 12) {  // alternating DFMA / LOP3
                     if (i & 1) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dc), "d"(d[(i + 2) & 7]));
                     else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
+                } else if (KIND == 13) {  // alternating IMAD.WIDE.U32 (accumulating) / IMAD: both on the multiplier pipe
+                    if (i & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
+                    else asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[i]) : "l"(w[(i + 2) & 7]), "r"(b));
+                } else if (KIND == 14) {  // alternating IMAD.WIDE.U32 without accumulator / LOP3
+                    if (i & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
+                    else asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mul.wide.u32 %0, lo, hi; }" : "=l"(w[i]) : "l"(w[(i + 2) & 7]));
+                } else if (KIND == 15) {  // IMAD.WIDE.U32 (accumulating) : LOP3 = 1 : 3
+                    if (i & 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                    else asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[i]) : "l"(w[(i + 4) & 7]), "r"(b));
+                } else if (KIND == 16) {  // three-input IADD3 with a uniform-register operand (the pinned adds of the MDS layer)
+                    x[i] = x[i] + x[j] + uz;
+                } else if (KIND == 17) {  // alternating three-input IADD3 / IMAD
+                    if (i & 1) x[i] = x[i] + x[(i + 2) & 7] + uz;
+                    else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[(i + 2) & 7]), "r"(b));
+                } else if (KIND == 18) {  // IMAD.WIDE (accumulating) : IMAD : LOP3 : IADD3 = 1 : 2 : 2 : 3, roughly the permutation's mix
+                    if (i == 0) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[0]) : "l"(w[r & 7]), "r"(b));
+                    else if (i == 1 || i == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                    else if (i == 2 || i == 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                    else x[i] = x[i] + x[j] + uz;
+                } else {                  // KIND 19: IMAD.WIDE.U32 (accumulating) : LOP3 : IMAD = 1 : 2 : 1
+                    if (i == 0 || i == 4) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %1; mad.wide.u32 %0, lo, %2, %0; }" : "+l"(w[i]) : "l"(w[(i + 4) & 7]), "r"(b));
+                    else if (i & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
+                    else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
                 }
             }
         }
@@ -1689,7 +1740,7 @@ __global__ void __launch_bounds__(256) int_pipe_kernel(u32 iters, u32* sink) {
 extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips) {
     if (!ctx) return B200ZKP_ERR_BAD_ARG;
     Guard g(ctx);
-    if (!out_gips || kind < 0 || kind > 12) BAD(ctx, "bad argument");
+    if (!out_gips || kind < 0 || kind > 19) BAD(ctx, "bad argument");
     int sms = 0;
     CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
     u32* sink = nullptr;
@@ -1712,7 +1763,14 @@ extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters
             case 9: int_pipe_kernel<9><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
             case 10: int_pipe_kernel<10><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
             case 11: int_pipe_kernel<11><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
-            default: int_pipe_kernel<12><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 12: int_pipe_kernel<12><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 13: int_pipe_kernel<13><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 14: int_pipe_kernel<14><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 15: int_pipe_kernel<15><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 16: int_pipe_kernel<16><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 17: int_pipe_kernel<17><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            case 18: int_pipe_kernel<18><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
+            default: int_pipe_kernel<19><<<blocks, 256, 0, ctx->stream>>>(n, sink); break;
         }
         ctx->launches++;
     };

@@ -125,6 +125,119 @@ merkle_level_kernel(u64* __restrict__ digests, u64* __restrict__ cap, TreeShape 
     else store_digest(digests + 4 * node_slot(shape, subtree, layer + 1, m), s);
 }
 
+// ---------------------------------------------------------------- latency form of the permutation
+// One state per 16-lane group, word i in lane i (lanes 12..15 idle), for launches too small to fill the GPU: the top
+// levels of every tree, single compressions, the Fiat-Shamir transcript.  A thread of the throughput form runs ~22 k
+// dependent-ish instructions per permutation (~25 us alone on an SM); here a lane runs one S-box and one MDS row per round
+// (~150 instructions, the 11 foreign words arrive by warp shuffle), ~4x less latency for 3.6x more total work — a good
+// trade only while the machine is otherwise idle (launch_tree_levels switches at 2048 nodes).
+// Same arithmetic as poseidon::permute (pushed-constant schedule ROUND_ADD), exact mod p, canonical output.
+// `ra` = ROUND_ADD in global memory (a lane-indexed read of the __constant__ copy would serialise).
+__device__ __forceinline__ u64 coop_permute(u64 s, u32 li, u32 grp_base, const u64* __restrict__ ra) {
+    constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    s = poseidon::add_const(s, __ldg(ra + li));
+    u64 nxt = __ldg(ra + 12 + li);
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        if (full || li == 0) s = poseidon::sbox(s);
+        // out[l] = sum_i in[(l + i) mod 12] * CIRC[i] + (l == 0) * 8 in[0], accumulated on 32-bit halves (each sum < 2^43)
+        u64 acc_lo = 0, acc_hi = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            u32 j = li + i;
+            j = j >= 12 ? j - 12 : j;
+            u64 v = __shfl_sync(0xffffffffu, s, (int)(grp_base + j));
+            acc_lo += (u64)(u32)v * CIRC[i];
+            acc_hi += (v >> 32) * CIRC[i];
+        }
+        if (li == 0) { acc_lo += (u64)(u32)s * 8u; acc_hi += (s >> 32) * 8u; }
+        u64 lo = acc_lo + (acc_hi << 32);
+        u64 hi = (acc_hi >> 32) + (lo < acc_lo ? 1u : 0u);
+        s = gl::reduce128(lo, hi);
+        if (r + 1 < 30) {
+            const bool next_full = (r + 1 < 4) || (r + 1 >= 26);
+            if (next_full || li == 0) s = poseidon::add_const(s, nxt);
+            if (r + 2 < 30) nxt = __ldg(ra + (r + 2) * 12 + li);
+        }
+    }
+    return gl::canon(s);
+}
+
+// parents of layer `layer`, one node per 16-lane group (see coop_permute); blockDim.x a multiple of 32
+__global__ void __launch_bounds__(128)
+merkle_level_coop_kernel(u64* __restrict__ digests, u64* __restrict__ cap, TreeShape shape, u32 layer, u64 n_parents,
+                         const u64* __restrict__ ra) {
+    const u32 lane = threadIdx.x & 31, l = lane & 15, grp_base = lane & 16;
+    const u32 li = l < 12 ? l : 0;
+    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = g < n_parents;
+    if (!live) g = 0;                                   // idle groups recompute node 0 and store nothing (shuffles stay full-warp)
+    u32 par_log = shape.sub_log - layer - 1;
+    u64 subtree = g >> par_log;
+    u64 m = g & (((u64)1 << par_log) - 1);
+    const u64* src = digests + 4 * node_slot(shape, subtree, layer, 2 * m);   // left || right child: 8 consecutive words
+    u64 s = (l < 8) ? src[l] : 0;
+    s = coop_permute(s, li, grp_base, ra);
+    if (live && l < 4) {
+        u64* dst = (par_log == 0) ? cap + 4 * subtree : digests + 4 * node_slot(shape, subtree, layer + 1, m);
+        dst[l] = s;
+    }
+}
+
+// hash_or_noop / hash_no_pad of one leaf per 16-lane group (small trees: FRI layers, tiny circuits); same arguments as
+// leaf_hash_kernel
+__global__ void __launch_bounds__(128)
+leaf_hash_coop_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 row0, u64 n_rows,
+                      TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap, u32 noop_short,
+                      const u64* __restrict__ ra) {
+    const u32 lane = threadIdx.x & 31, l = lane & 15, grp_base = lane & 16;
+    const u32 li = l < 12 ? l : 0;
+    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = g < n_rows;
+    if (!live) g = 0;
+    const u64 row = row0 + g;
+    const u64* p = leaves + row * row_stride;
+    u64 s = 0;
+    if (leaf_len <= 4 && noop_short) {
+        if (l < leaf_len) s = gl::canon(p[(u64)l * col_stride]);
+    } else {
+        for (u32 c = 0; c < leaf_len; c += poseidon::RATE) {        // overwrite mode: a short last chunk keeps the old rate words
+            if (l < poseidon::RATE && c + l < leaf_len) s = p[(u64)(c + l) * col_stride];
+            s = coop_permute(s, li, grp_base, ra);
+        }
+    }
+    if (live && l < 4) {
+        if (shape.sub_log == 0) cap[4 * row + l] = s;
+        else {
+            u64 subtree = row >> shape.sub_log;
+            u64 m = row & (((u64)1 << shape.sub_log) - 1);
+            digests[4 * node_slot(shape, subtree, 0, m) + l] = s;
+        }
+    }
+}
+
+// out[q] = permute(in[q]) (mode 0, 12 words in and out) or two_to_one(in[q][0..8]) (mode 1, 8 words in, 4 out), one state
+// per 16-lane group
+__global__ void __launch_bounds__(128)
+permute_coop_kernel(const u64* __restrict__ in, const u64* __restrict__ in2, u64* __restrict__ out, u64 count, u32 mode,
+                    const u64* __restrict__ ra) {
+    const u32 lane = threadIdx.x & 31, l = lane & 15, grp_base = lane & 16;
+    const u32 li = l < 12 ? l : 0;
+    u64 g = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool live = g < count;
+    if (!live) g = 0;
+    u64 s = 0;
+    if (mode == 0) { if (l < 12) s = in[g * 12 + l]; }
+    else if (l < 4) s = in[g * 4 + l];
+    else if (l < 8) s = in2[g * 4 + (l - 4)];
+    s = coop_permute(s, li, grp_base, ra);
+    if (live) {
+        if (mode == 0) { if (l < 12) out[g * 12 + l] = s; }
+        else if (l < 4) out[g * 4 + l] = s;
+    }
+}
+
 // ---------------------------------------------------------------- stateless Hasher helpers (tests, N4)
 // out[i] = permute(in[i]), states row-major 12 words each
 __global__ void __launch_bounds__(128)

@@ -9,9 +9,9 @@
 // Layout of the work: 4 full rounds, 22 partial rounds, 4 full rounds, S-box x^7,
 // MDS = circulant(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...).
 //   * S-box: 4 modular products of 16 SASS instructions each (4 IMAD.WIDE.U32 + carry chain + Solinas fold).
-//   * MDS: every word is cut into 22 + 21 + 21-bit limbs so that all products and 12-term sums fit 32 bits and run as
-//     32-bit IMADs (IMAD.WIDE issues at half their rate on B200); the 12x12 circulant is split by
-//     x^12 - 1 = (x^6 - 1)(x^6 + 1) into a cyclic and a negacyclic 6x6 product; limbs are recombined with one fold.
+//   * MDS: every word is cut into 22 + 21 + 21-bit limbs so that all 12-term sums fit 32 bits; the 12x12 circulant is
+//     split by x^12 - 1 = (x^3 - 1)(x^3 + 1)(x^6 + 1) into pieces whose constants are all +-2^j, so the layer is adds and
+//     shift-adds only, spread evenly over the ALU and the multiplier pipe; limbs are recombined with one fold.
 //   * partial rounds use the "pushed constant" form: the 11 idle words of every partial-round constant are pushed
 //     forward through the MDS, so a partial round is  s0 = (s0 + c)^7 ; s = MDS s  with the same MDS body.
 //   * one loop over all 30 rounds (single copy of the S-box row and of the MDS): ~25 KB of SASS, instruction-cache
@@ -78,16 +78,38 @@ GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc) {
 #endif
 }
 
-// MDS on three limbs (22 + 21 + 21 bits) so every product and 12-term sum fits 32 bits: the multiplies are
-// 32-bit IMADs (2 pipe cycles) instead of IMAD.WIDE (4), and the 12x12 circulant is split by
-// x^12 - 1 = (x^6 - 1)(x^6 + 1) into a cyclic and a negacyclic 6x6 product whose halved constants are
-//   P = (15, 24, 18, 17, 40, 14)   and   Q = (2, -4, 16, 1, -1, -1)      (all +-powers of two in Q)
+// MDS on three limbs (22 + 21 + 21 bits) so that every term and every 12-term sum fits 32 bits, and without a single
+// multiplication.  The 12x12 circulant is a product in Z[x] / (x^12 - 1); x^12 - 1 = (x^6 - 1)(x^6 + 1) splits it into a
+// cyclic and a negacyclic 6x6 product with halved constants
+//   P = (15, 24, 18, 17, 40, 14)   and   Q = (2, -4, 16, 1, -1, -1),
+// and x^6 - 1 = (x^3 - 1)(x^3 + 1) splits the cyclic one again into 3x3 products with
+//   P+ = (16, 32, 16) = 16 * (1, 2, 1)   and   P- = (-1, -8, 2).
+// Every constant is +-2^j (this is how the matrix was chosen: plonky2's MDS_FREQ_BLOCK_* hold the same numbers in the
+// frequency domain), so a layer is 71 adds / shift-adds per limb instead of 72 multiply-adds + 36 adds.
 // out[k] = A[k] + B[k], out[k+6] = A[k] - B[k]; arithmetic is mod 2^32 (exact: true sums < 2^31).
+//
+// Pipe steering.  B200 issues IMAD* on the multiplier pipe and IADD3 / LOP3 / SHF / LEA on the ALU pipe, one warp
+// instruction per two cycles each, and an IMAD.WIDE holds the multiplier pipe twice as long.  ptxas turns every two-input
+// add into IMAD.IADD, which left the multiplier pipe 92 % busy with the ALU half idle (profiles/README.md).  A third
+// operand that ptxas cannot prove to be zero (OPAQUE_ZERO, a __constant__ word) makes the add a three-input IADD3,
+// which only the ALU pipe has.  kAluSp/kAluUv/kAluC/kAluOut choose which groups of adds are pinned that way; the
+// setting below balances the two pipes for the whole permutation (tools/sass_mix.py: 12.1 k slots on either pipe,
+// down from 15.9 k on the multiplier pipe).
+#ifdef B200ZKP_HOST_EMU
+static const u32 OPAQUE_ZERO = 0;
+#else
+static __device__ __constant__ u32 OPAQUE_ZERO = 0;
+#endif
+#ifndef B200ZKP_MDS_ALU_MASK
+#define B200ZKP_MDS_ALU_MASK 13   // tuning builds only (tools/bench_variants.sh)
+#endif
+static constexpr bool kAluSp = B200ZKP_MDS_ALU_MASK & 1, kAluUv = B200ZKP_MDS_ALU_MASK & 2, kAluC = B200ZKP_MDS_ALU_MASK & 4,
+                      kAluOut = B200ZKP_MDS_ALU_MASK & 8;
+
 template <bool kAddConst>
 GL_FN void mds_layer(u64 (&s)[WIDTH], const unsigned long long* addc) {
-    constexpr u32 Pc[6] = {15, 24, 18, 17, 40, 14};
-    constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
     u32 o[3][WIDTH];
+    const u32 Z = OPAQUE_ZERO;
 #pragma unroll
     for (int L = 0; L < 3; L++) {
         u32 l[WIDTH];
@@ -96,18 +118,39 @@ GL_FN void mds_layer(u64 (&s)[WIDTH], const unsigned long long* addc) {
             l[i] = (L == 0) ? ((u32)s[i] & 0x3FFFFFu) : (L == 1) ? ((u32)(s[i] >> 22) & 0x1FFFFFu) : (u32)(s[i] >> 43);
         u32 sp[6], sm[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) { sp[i] = l[i] + l[i + 6]; sm[i] = l[i] - l[i + 6]; }
+        for (int i = 0; i < 6; i++) {
+            sp[i] = l[i] + l[i + 6] + (kAluSp ? Z : 0u);
+            sm[i] = l[i] - l[i + 6] + (kAluSp ? Z : 0u);
+        }
+        // cyclic half: A = sp (*) P mod (x^6 - 1), through (x^3 - 1)(x^3 + 1)
+        u32 u[3], v[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            u[i] = sp[i] + sp[i + 3] + (kAluUv ? Z : 0u);
+            v[i] = sp[i] - sp[i + 3] + (kAluUv ? Z : 0u);
+        }
+        const u32 T = u[0] + u[1] + u[2];
+        u32 Cq[3], D[3], A[6];                    // C = 16 * Cq = u (*) (16, 32, 16) mod (x^3 - 1)
+        Cq[0] = T + u[2] + (kAluC ? Z : 0u);
+        Cq[1] = T + u[0] + (kAluC ? Z : 0u);
+        Cq[2] = T + u[1] + (kAluC ? Z : 0u);
+        D[0] = 8u * v[2] - v[0] - 2u * v[1];      // D = v (*) (-1, -8, 2) mod (x^3 + 1)
+        D[1] = 0u - 8u * v[0] - v[1] - 2u * v[2];
+        D[2] = 2u * v[0] - 8u * v[1] - v[2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { A[k] = 16u * Cq[k] + D[k]; A[k + 3] = 16u * Cq[k] - D[k]; }
+        // negacyclic half: B = sm (*) Q mod (x^6 + 1)
+        constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            u32 A = 0, B = 0;
+            u32 B = 0;
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                A += sp[i] * Pc[(k - i + 6) % 6];
                 const int q = (k >= i) ? Qc[k - i] : -Qc[k - i + 6];
                 B += sm[i] * (u32)q;
             }
-            o[L][k] = A + B;
-            o[L][k + 6] = A - B;
+            o[L][k] = A[k] + B + (kAluOut ? Z : 0u);
+            o[L][k + 6] = A[k] - B + (kAluOut ? Z : 0u);
         }
         o[L][0] += 8u * l[0];     // diag(8, 0, ..., 0)
     }
