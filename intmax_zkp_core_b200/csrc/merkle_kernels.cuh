@@ -17,10 +17,10 @@
 #include "poseidon.cuh"
 
 #ifndef B200ZKP_HASH_MINBLOCKS
-#define B200ZKP_HASH_MINBLOCKS 2
+#define B200ZKP_HASH_MINBLOCKS 3
 #endif
 #ifndef B200ZKP_HASH_THREADS
-#define B200ZKP_HASH_THREADS 512
+#define B200ZKP_HASH_THREADS 256
 #endif
 #ifndef B200ZKP_HASH_PREFETCH
 #define B200ZKP_HASH_PREFETCH 0

@@ -101,61 +101,150 @@ static const u32 OPAQUE_ZERO = 0;
 static __device__ __constant__ u32 OPAQUE_ZERO = 0;
 #endif
 #ifndef B200ZKP_MDS_ALU_MASK
-#define B200ZKP_MDS_ALU_MASK 13   // tuning builds only (tools/bench_variants.sh)
+#define B200ZKP_MDS_ALU_MASK 61   // tuning builds only (tools/bench_variants.sh)
 #endif
 static constexpr bool kAluSp = B200ZKP_MDS_ALU_MASK & 1, kAluUv = B200ZKP_MDS_ALU_MASK & 2, kAluC = B200ZKP_MDS_ALU_MASK & 4,
-                      kAluOut = B200ZKP_MDS_ALU_MASK & 8;
+                      kAluOut = B200ZKP_MDS_ALU_MASK & 8, kAluNorm = B200ZKP_MDS_ALU_MASK & 16, kAluInj = B200ZKP_MDS_ALU_MASK & 32;
 
-template <bool kAddConst>
-GL_FN void mds_layer(u64 (&s)[WIDTH], const unsigned long long* addc) {
-    u32 o[3][WIDTH];
-    const u32 Z = OPAQUE_ZERO;
+// The state between two linear layers, in the split basis of Z[t] / (t^12 - 1) = (t^3 - 1)(t^3 + 1)(t^6 + 1): three limb
+// planes of U[3], V[3], W[6] (signed 32-bit; tools/poseidon_crt_model.py bounds every intermediate by interval arithmetic).
+struct SplitState {
+    int U[3][3], V[3][3], W[3][6];
+};
+
+GL_FN u32 limb_of(u64 x, int L) {
+    return (L == 0) ? ((u32)x & 0x3FFFFFu) : (L == 1) ? ((u32)(x >> 22) & 0x1FFFFFu) : (u32)(x >> 43);
+}
+
+// words -> split basis (the butterflies of the MDS layer); z8[L] = 8 * limb L of word 0 (the diag(8, 0, ..) term)
+GL_FN void split_forward(const u64 (&s)[WIDTH], SplitState& c, int (&z8)[3], u32 Z) {
 #pragma unroll
     for (int L = 0; L < 3; L++) {
         u32 l[WIDTH];
 #pragma unroll
-        for (int i = 0; i < WIDTH; i++)
-            l[i] = (L == 0) ? ((u32)s[i] & 0x3FFFFFu) : (L == 1) ? ((u32)(s[i] >> 22) & 0x1FFFFFu) : (u32)(s[i] >> 43);
-        u32 sp[6], sm[6];
+        for (int i = 0; i < WIDTH; i++) l[i] = limb_of(s[i], L);
+        u32 sp[6];
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             sp[i] = l[i] + l[i + 6] + (kAluSp ? Z : 0u);
-            sm[i] = l[i] - l[i + 6] + (kAluSp ? Z : 0u);
+            c.W[L][i] = (int)(l[i] - l[i + 6] + (kAluSp ? Z : 0u));
         }
-        // cyclic half: A = sp (*) P mod (x^6 - 1), through (x^3 - 1)(x^3 + 1)
-        u32 u[3], v[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-            u[i] = sp[i] + sp[i + 3] + (kAluUv ? Z : 0u);
-            v[i] = sp[i] - sp[i + 3] + (kAluUv ? Z : 0u);
+            c.U[L][i] = (int)(sp[i] + sp[i + 3] + (kAluUv ? Z : 0u));
+            c.V[L][i] = (int)(sp[i] - sp[i + 3] + (kAluUv ? Z : 0u));
         }
-        const u32 T = u[0] + u[1] + u[2];
-        u32 Cq[3], D[3], A[6];                    // C = 16 * Cq = u (*) (16, 32, 16) mod (x^3 - 1)
-        Cq[0] = T + u[2] + (kAluC ? Z : 0u);
-        Cq[1] = T + u[0] + (kAluC ? Z : 0u);
-        Cq[2] = T + u[1] + (kAluC ? Z : 0u);
-        D[0] = 8u * v[2] - v[0] - 2u * v[1];      // D = v (*) (-1, -8, 2) mod (x^3 + 1)
-        D[1] = 0u - 8u * v[0] - v[1] - 2u * v[2];
-        D[2] = 2u * v[0] - 8u * v[1] - v[2];
+        z8[L] = (int)(8u * l[0]);
+    }
+}
+
+// three signed limbs of one word back to 22 / 21 / 21 bits (+ a small signed excess), same value mod p:
+// carries upwards, then the part above 2^64 folds back through 2^64 = 2^32 - 1
+GL_FN void normalise(int& a0, int& a1, int& a2, u32 Z) {
+    const int zn = (int)(kAluNorm ? Z : 0u);
+    const int c0 = a0 >> 22, n0 = a0 & 0x3FFFFF;
+    const int t1 = a1 + c0 + zn;
+    const int c1 = t1 >> 21, n1 = t1 & 0x1FFFFF;
+    const int t2 = a2 + c1 + zn;
+    const int top = t2 >> 21, n2 = t2 & 0x1FFFFF;
+    a0 = n0 - top + zn;
+    a1 = n1 + top * 1024;
+    a2 = n2;
+}
+
+// the three ring products of one limb plane, unscaled:  Cq = U (*) (1, 2, 1),  D = V (*) (-1, -8, 2) mod t^3 + 1,
+// B = W (*) Q mod t^6 + 1;  the layer is  (64 Cq, 4 D, 2 B)  in the split basis and  16 Cq +- D +- B  in words
+GL_FN void ring_products(const int (&U)[3], const int (&V)[3], const int (&W)[6], int (&Cq)[3], int (&D)[3], int (&B)[6],
+                         u32 Z) {
+    const int T = U[0] + U[1] + U[2];
+    Cq[0] = T + U[2] + (int)(kAluC ? Z : 0u);
+    Cq[1] = T + U[0] + (int)(kAluC ? Z : 0u);
+    Cq[2] = T + U[1] + (int)(kAluC ? Z : 0u);
+    D[0] = 8 * V[2] - V[0] - 2 * V[1];
+    D[1] = -8 * V[0] - V[1] - 2 * V[2];
+    D[2] = 2 * V[0] - 8 * V[1] - V[2];
+    constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
 #pragma unroll
-        for (int k = 0; k < 3; k++) { A[k] = 16u * Cq[k] + D[k]; A[k + 3] = 16u * Cq[k] - D[k]; }
-        // negacyclic half: B = sm (*) Q mod (x^6 + 1)
-        constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
+    for (int k = 0; k < 6; k++) {
+        int acc = 0;
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            u32 B = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-                const int q = (k >= i) ? Qc[k - i] : -Qc[k - i + 6];
-                B += sm[i] * (u32)q;
-            }
-            o[L][k] = A[k] + B + (kAluOut ? Z : 0u);
-            o[L][k + 6] = A[k] - B + (kAluOut ? Z : 0u);
+        for (int i = 0; i < 6; i++) {
+            const int q = (k >= i) ? Qc[k - i] : -Qc[k - i + 6];
+            acc += W[i] * q;
         }
-        o[L][0] += 8u * l[0];     // diag(8, 0, ..., 0)
+        B[k] = acc;
+    }
+}
+
+// linear layer that stays in the split basis (the next round is a partial round), every word re-normalised
+GL_FN void layer_stay(SplitState& c, const int (&z8)[3], u32 Z) {
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+        int Cq[3], D[3], B[6];
+        ring_products(c.U[L], c.V[L], c.W[L], Cq, D, B, Z);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            c.U[L][k] = 64 * Cq[k] + (k == 0 ? z8[L] : 0);
+            c.V[L][k] = 4 * D[k] + (k == 0 ? z8[L] : 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) c.W[L][k] = 2 * B[k] + (k == 0 ? z8[L] : 0);
     }
 #pragma unroll
-    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], kAddConst ? (u64)addc[r] : 0ull);
+    for (int k = 0; k < 3; k++) {
+        normalise(c.U[0][k], c.U[1][k], c.U[2][k], Z);
+        normalise(c.V[0][k], c.V[1][k], c.V[2][k], Z);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) normalise(c.W[0][k], c.W[1][k], c.W[2][k], Z);
+}
+
+// linear layer back to words: out[k] = A[k] + B[k], out[k + 6] = A[k] - B[k] with A = 16 Cq +- D; `bias` (a multiple of
+// the opaque zero, see above) lifts limbs that may be negative after partial rounds; the constants that follow absorb it
+GL_FN void layer_leave(const SplitState& c, const int (&z8)[3], u64 (&s)[WIDTH], u32 bias, u32 Z) {
+    u32 o[3][WIDTH];
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+        int Cq[3], D[3], B[6], A[6];
+        ring_products(c.U[L], c.V[L], c.W[L], Cq, D, B, Z);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { A[k] = 16 * Cq[k] + D[k]; A[k + 3] = 16 * Cq[k] - D[k]; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            o[L][k] = (u32)(A[k] + B[k]) + bias;
+            o[L][k + 6] = (u32)(A[k] - B[k]) + bias;
+        }
+        o[L][0] += (u32)z8[L];
+    }
+#pragma unroll
+    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], 0ull);
+}
+
+// v / 4 mod p:  v = 4 q + r,  r / 4 = ((4 - r) << 62) - ((4 - r) << 30) + 1  (r = 0 gives p, which the carry fold removes)
+GL_FN u64 div4(u64 v) {
+    const u32 sh = (u32)v << 30;
+    const u64 t = ((u64)(~sh) << 32) | (u64)(sh + 1u);
+    return gl::add_nc(v >> 2, t);
+}
+
+// head of a partial round in the split basis: word 0 = (U0 + V0 + 2 W0) / 4 is packed, pushed through the S-box, and the
+// difference is put back into the three components; cst = round constant - 2^21 (1 + 2^22 + 2^43) (SPLIT_ADD)
+GL_FN void partial_head(SplitState& c, u64 cst, int (&z8)[3], u32 Z) {
+    const int zi = (int)(kAluInj ? Z : 0u);
+    u32 E[3];
+#pragma unroll
+    for (int L = 0; L < 3; L++) E[L] = (u32)(c.U[L][0] + c.V[L][0] + 2 * c.W[L][0] + (1 << 23));
+    const u64 e = div4(combine3(E[0], E[1], E[2], 0ull));
+    const u64 z = sbox(add_const(e, cst));
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+        const int zl = (int)limb_of(z, L);
+        const int d = zl - (int)limb_of(e, L) + (1 << 21);
+        c.U[L][0] += d + zi;
+        c.V[L][0] += d + zi;
+        c.W[L][0] += d + zi;
+        z8[L] = 8 * zl;
+    }
 }
 
 // s + w * x  (all arbitrary u64) -> arbitrary u64
@@ -165,31 +254,47 @@ GL_FN u64 mul_add_nc(u64 w, u64 x, u64 s) {
 }
 
 // In-place permutation; input words arbitrary u64, output canonical.
-// One loop over all 30 rounds with a single copy of the S-box row and of the MDS body: the whole permutation is
-// ~22 KB of SASS and stays resident in the instruction cache (the two-loop form was 59 KB and ncu showed
-// "no instruction" as the top stall with a 67 % instruction-cache hit rate).  The round kind is warp-uniform.
+// One loop over all 30 rounds with a single copy of every block (S-box row, butterflies, ring products, packing): the
+// whole permutation stays resident in the instruction cache (a two-loop form of 59 KB ran at a 67 % hit rate with "no
+// instruction" as the top stall).  The round kind is warp-uniform.  Rounds 3..24 leave the state in the split basis
+// (the next round is partial), every other round packs it back into words for the twelve S-boxes that follow.
 GL_FN void permute(u64 (&s)[WIDTH]) {
     using namespace poseidon_tables;
 #pragma unroll
-    for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], ROUND_ADD[i]);
+    for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], SPLIT_ADD[i]);
+    SplitState c;
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { c.U[L][k] = 0; c.V[L][k] = 0; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) c.W[L][k] = 0;
+    }
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
         const bool full = (r < 4) || (r >= 26);
+        const bool stay = (r >= 3) && (r < 25);
+        const u32 Z = OPAQUE_ZERO;
+        int z8[3];
         if (full) {
 #pragma unroll
             for (int i = 0; i < WIDTH; i++) s[i] = sbox(s[i]);
+            split_forward(s, c, z8, Z);
+            if (stay) {                     // r == 3: U holds sums of four limbs, too wide for the x256 of layer_stay
+#pragma unroll
+                for (int k = 0; k < 3; k++) normalise(c.U[0][k], c.U[1][k], c.U[2][k], Z);
+            }
         } else {
-            s[0] = sbox(s[0]);
+            partial_head(c, SPLIT_ADD[r * WIDTH], z8, Z);
         }
-        mds_layer<false>(s, nullptr);
-        if (r + 1 < 30) {
-            const unsigned long long* nxt = &ROUND_ADD[(r + 1) * WIDTH];
-            const bool next_full = (r + 1 < 4) || (r + 1 >= 26);
-            if (next_full) {
+        if (stay) {
+            layer_stay(c, z8, Z);
+        } else {
+            layer_leave(c, z8, s, (full ? 0u : (1u << 30)) + Z, Z);
+            if (r + 1 < 30) {
+                const unsigned long long* nxt = &SPLIT_ADD[(r + 1) * WIDTH];
 #pragma unroll
                 for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], nxt[i]);
-            } else {
-                s[0] = add_const(s[0], nxt[0]);
             }
         }
     }

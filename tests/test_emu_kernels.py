@@ -38,7 +38,11 @@ def test_permutation_body(emu, oracle):
     rng = np.random.default_rng(11)
     states = [np.zeros(12, np.uint64), np.arange(12, dtype=np.uint64), np.full(12, P - 1, np.uint64),
               np.full(12, 2**64 - 1, np.uint64), np.full(12, P, np.uint64)]
-    states += [rng.integers(0, 2**64, size=12, dtype=np.uint64) for _ in range(40)]
+    states += [rng.integers(0, 2**64, size=12, dtype=np.uint64) for _ in range(400)]
+    # words 0 / 6 / 3 / 9 feed the split-basis components with the largest gains
+    for w in (0, 3, 6, 9):
+        st = np.zeros(12, np.uint64); st[w] = 2**64 - 1; states.append(st)
+        st = np.full(12, 2**64 - 1, np.uint64); st[w] = 0; states.append(st)
     for st in states:
         got = st.copy()
         emu.emu_permute(ptr(got))

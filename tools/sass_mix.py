@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Static pipe model of a kernel from its SASS (no GPU needed).
 
-    python tools/sass_mix.py <lib.so|.cubin> <function substring> [--weights a-b:w,...] [--blocks]
+    python tools/sass_mix.py <lib.so|.cubin> <function substring> [--weights a:w,...] [--block-weights w0,w1,...] [--blocks]
 
 Splits the function into basic blocks, classifies every instruction by issue pipe (B200: the multiplier pipe "fmaheavy"
 takes IMAD* — an IMAD.WIDE / IMAD.HI holds it for two slots — the ALU pipe takes IADD3 / LOP3 / SHF / LEA / SEL / ISETP /
@@ -104,6 +104,10 @@ def main():
         for spec in sys.argv[sys.argv.index("--weights") + 1].split(","):
             rng, w = spec.split(":")
             weights[int(rng, 16)] = float(w)
+    if "--block-weights" in sys.argv:      # one execution count per basic block, in address order
+        ws = [float(x) for x in sys.argv[sys.argv.index("--block-weights") + 1].split(",")]
+        assert len(ws) == len(blocks), (len(ws), len(blocks))
+        weights = {b[0][0]: w for b, w in zip(blocks, ws)}
     auto = "--auto-perm" in sys.argv
     if auto:
         # largest backward branch = the round loop
