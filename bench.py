@@ -337,7 +337,7 @@ def run_b200(args):
             line["e2e_strict"] = e2e_strict
         if world == 1 and n_log == N_LOG and k == K:
             # dram__bytes_read.sum + dram__bytes_write.sum of the leaf hash at this size, ncu --set full capture
-            # profiles/r1_leaf_kernel_ncu_details.txt (9.09 GB + 0.27 GB)
+            # profiles/r1c_leaf_kernel_ncu_details.txt (9.08 GB + 0.27 GB)
             line["roofline"]["traffic"] = 9.36e9
         if world == 1:
             gips = {}
@@ -347,19 +347,26 @@ def run_b200(args):
                 ctx.check(ctx._lib.b200zkp_int_pipe_bench(ctx._h, kind, 2000, C.byref(g)))
                 gips[name] = g.value
             line["int_pipe"] = {"unit": "giga thread-instructions/s (dependent chains, all SMs)", **gips}
-            # second roof of SURVEY.md 8d: the leaf hash against the measured issue rate of the integer-multiply (fmaheavy) pipe.
-            # Dynamic instruction mix per permutation of the shipped kernel (ncu source counters, profiles/README.md):
-            # 3089 IMAD.WIDE (2 pipe slots each: they issue at half the IMAD rate) + 9342 single-slot instructions on the same pipe
-            # (4270 IMAD of the MDS layers, 5072 IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL that ptxas places there).
+            # second roof of SURVEY.md 8d: the leaf hash against the measured issue rate of the integer-multiply (fmaheavy) pipe,
+            # the busier of the two integer pipes.  Dynamic instruction mix per permutation of the shipped kernel (ncu source
+            # counters of profiles/r1c_leaf_kernel_ncu_details.txt, 19 352 warp-instructions per warp-permutation):
+            #   multiplier pipe: 2605 IMAD.WIDE (2 slots each: they issue at half the IMAD rate) + 6070 single-slot
+            #                    (2033 IMAD shift-adds of the linear layers, 4037 IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL)
+            #   ALU pipe:        9979 IADD3 / IADD3.X / LOP3 / SEL / LEA / SHF (one slot each)
             leaf_perms = N_local * ((k + 7) // 8)
-            slots_per_perm = 2 * 3089 + 9342
+            slots_per_perm = 2 * 2605 + 6070
+            alu_slots_per_perm = 9979
             slot_rate = leaf_perms * slots_per_perm / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
             slot_peak = gips["imad"] * 1e9
             line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": slot_rate, "peak": slot_peak,
                                        "unit": "IMAD-slot thread-instr/s (IMAD.WIDE = 2 slots)", "frac": slot_rate / slot_peak,
-                                       "slots_per_permutation": slots_per_perm, "imad_wide_per_permutation": 3089,
-                                       "algorithmic_multiplies_per_permutation": {"imad_wide": 3089, "imad": 4270},
-                                       "permutations_per_launch": leaf_perms, "ncu_pipe_fmaheavy_busy": 0.923}
+                                       "slots_per_permutation": slots_per_perm, "imad_wide_per_permutation": 2605,
+                                       "alu_slots_per_permutation": alu_slots_per_perm,
+                                       "alu_frac": (leaf_perms * alu_slots_per_perm / (leaf_ms_avg * 1e-3) / (gips["lop3"] * 1e9)) if leaf_ms_avg else 0.0,
+                                       "instructions_per_permutation": 19352,
+                                       "issue_frac": (leaf_perms * 19352 / (leaf_ms_avg * 1e-3) / (2 * gips["imad"] * 1e9)) if leaf_ms_avg else 0.0,
+                                       "permutations_per_launch": leaf_perms,
+                                       "ncu": {"pipe_fmaheavy_busy": 0.827, "pipe_alu_busy": 0.689, "issue_active": 0.687}}
             if not os.environ.get("B200ZKP_SKIP_CPU"):
                 from oracle import oracle as O
                 O.build()

@@ -30,8 +30,8 @@ static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 
 GL_FN u64 sbox(u64 x) {
-    u64 x2 = gl::mul_nc(x, x);
-    u64 x4 = gl::mul_nc(x2, x2);
+    u64 x2 = gl::sqr_nc(x);
+    u64 x4 = gl::sqr_nc(x2);
     u64 x3 = gl::mul_nc(x2, x);
     return gl::mul_nc(x3, x4);
 }
