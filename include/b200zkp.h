@@ -224,6 +224,26 @@ int b200zkp_dev_gather(b200zkp_ctx* ctx, const uint64_t* lde, uint64_t col_strid
 /* column-major [cols][col_stride] rows [row0,row0+n_rows) -> row-major [n_rows][cols] (device) */
 int b200zkp_dev_transpose_to_rows(b200zkp_ctx* ctx, const uint64_t* cm, uint64_t col_stride, uint32_t cols,
                                   uint64_t row0, uint64_t n_rows, uint64_t* rm);
+/* Row N1a — permutation argument: the Z and partial-product polynomials prove() commits after the wires.
+ * Replaces plonky2 @ f99ed9c plonky2/src/plonk/prover.rs `all_wires_permutation_partial_products` /
+ * `wires_permutation_partial_products_and_zs` (with `quotient_chunk_products`, `partial_products_and_z_gx`), reached from
+ * the reference through every prove() (/root/reference/src/transaction/circuits/mod.rs:453, src/zkdsa/circuits/mod.rs:326,
+ * src/rollup/circuits/mod.rs:1247).
+ * wires, sigmas: num_routed columns of n = 2^n_log values, column-major (the routed wires are the first columns of the
+ * witness matrix handed to commit_from_values; sigmas = ProverOnlyCircuitData::sigmas transposed); k_is[num_routed]
+ * (CommonCircuitData::k_is, 7^j), betas / gammas[num_challenges]; degree = quotient_degree_factor (chunk size).
+ * out: num_challenges * ceil(num_routed / degree) columns of n canonical values in the order of the committed batch:
+ * Z of every challenge, then the num_partial_products = ceil(num_routed / degree) - 1 partial products challenge by
+ * challenge.  The _dev_ form takes device pointers with column strides (so `out` can feed b200zkp_dev_commit directly);
+ * k_is / betas / gammas are always host arrays.  Errors: bad arg for zero sizes, more than 32 chunks, strides < n. */
+int b200zkp_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t n_log,
+                                    uint32_t num_routed, uint32_t degree, const uint64_t* k_is, const uint64_t* betas,
+                                    const uint64_t* gammas, uint32_t num_challenges, uint64_t* out);
+int b200zkp_dev_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires_dev, uint64_t wires_col_stride,
+                                        const uint64_t* sigmas_dev, uint64_t sigmas_col_stride, uint32_t n_log,
+                                        uint32_t num_routed, uint32_t degree, const uint64_t* k_is, const uint64_t* betas,
+                                        const uint64_t* gammas, uint32_t num_challenges, uint64_t* out_dev,
+                                        uint64_t out_col_stride);
 /* device field primitives, element-wise over `count` pairs (test probe for the carry / borrow paths):
  * op 0 mul, 1 add, 2 sub, 3 reduce128(lo = a, hi = b), 4 a + canon(b) lazily,
  * 5 limb recombination O0 + O1*2^22 + O2*2^43 + rc with O0 = a[0:31], O1 = a[32:63], O2 = b[0:31], rc = canon(b >> 1),

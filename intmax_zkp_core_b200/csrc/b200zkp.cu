@@ -16,6 +16,7 @@
 #include "ntt_kernels.cuh"
 #include "eval_kernels.cuh"
 #include "fri_kernels.cuh"
+#include "perm_kernels.cuh"
 #include "host_plan.hpp"
 
 using gl::u32;
@@ -1471,6 +1472,92 @@ extern "C" int b200zkp_tree_prove(b200zkp_tree* t, const uint64_t* idx, uint64_t
     if (!siblings && n_idx) BAD(t->ctx, "null out");
     return gather_locked(t->ctx, nullptr, t->n_leaves, 0, t->digests, lg - t->cap_height, (const u64*)idx, n_idx,
                          nullptr, (u64*)siblings);
+}
+
+// ------------------------------------------------------------------------------------------------ permutation argument (N1a)
+static int dev_partial_products_locked(b200zkp_ctx* ctx, const u64* wires, u64 wires_stride, const u64* sigmas, u64 sigmas_stride,
+                                       u32 n_log, u32 R, u32 degree, const u64* k_is, const u64* betas, const u64* gammas, u32 C,
+                                       u64* out, u64 out_stride) {
+    if (n_log > 32) BAD(ctx, "n_log out of range");
+    if (!R || !degree || !C) BAD(ctx, "num_routed, degree and num_challenges must be positive");
+    const u32 chunks = (R + degree - 1) / degree;
+    if (chunks > (u32)perm::MAX_CHUNKS) BAD(ctx, "more than 32 chunks of routed wires");
+    const u64 n = (u64)1 << n_log;
+    if (wires_stride < n || sigmas_stride < n || out_stride < n) BAD(ctx, "column stride smaller than n");
+    // small host vectors -> device (canonical)
+    std::vector<u64> small((size_t)R + 2 * C);
+    for (u32 j = 0; j < R; j++) small[j] = k_is[j] % hostgl::P;
+    for (u32 c = 0; c < C; c++) { small[R + c] = betas[c] % hostgl::P; small[R + C + c] = gammas[c] % hostgl::P; }
+    void *d_small = nullptr, *d_run = nullptr, *d_tot = nullptr;
+    const size_t small_b = small.size() * 8, run_b = (size_t)C * chunks * n * 8;
+    const u32 per = 4;
+    const u32 n_blocks = (u32)((n + (u64)perm::SCAN_THREADS * per - 1) / ((u64)perm::SCAN_THREADS * per));
+    const size_t tot_b = (size_t)C * n_blocks * 8;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, small_b, &d_small))) return rc;
+    if ((rc = dev_alloc(ctx, run_b, &d_run))) { dev_release(ctx, d_small, small_b); return rc; }
+    if ((rc = dev_alloc(ctx, tot_b, &d_tot))) { dev_release(ctx, d_small, small_b); dev_release(ctx, d_run, run_b); return rc; }
+    auto done = [&](int code) {
+        if (code == 0) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); code = B200ZKP_ERR_CUDA; } }
+        dev_release(ctx, d_small, small_b); dev_release(ctx, d_run, run_b); dev_release(ctx, d_tot, tot_b);
+        return code;
+    };
+    if ((rc = h2d(ctx, d_small, small.data(), small_b))) return done(rc);
+    {   // `small` is a pageable host vector
+        cudaError_t e0 = cudaStreamSynchronize(ctx->stream);
+        if (e0 != cudaSuccess) { ctx->err = cudaGetErrorString(e0); return done(B200ZKP_ERR_CUDA); }
+    }
+    perm::Params p;
+    p.wires = wires; p.wires_stride = wires_stride; p.sigmas = sigmas; p.sigmas_stride = sigmas_stride;
+    p.k_is = (const u64*)d_small; p.betas = (const u64*)d_small + R; p.gammas = (const u64*)d_small + R + C;
+    p.omega = hostgl::root(n_log); p.n = n; p.R = R; p.degree = degree; p.chunks = chunks; p.C = C;
+    perm::chunk_products_kernel<<<dim3((unsigned)((n + 127) / 128), C), 128, 0, ctx->stream>>>(p, (u64*)d_run);
+    ctx->launches++;
+    perm::block_totals_kernel<<<dim3(n_blocks, C), perm::SCAN_THREADS, 0, ctx->stream>>>((const u64*)d_run, n, chunks, per, (u64*)d_tot);
+    ctx->launches++;
+    perm::scan_totals_kernel<<<C, perm::SCAN_THREADS, 0, ctx->stream>>>((u64*)d_tot, n_blocks);
+    ctx->launches++;
+    perm::finish_kernel<<<dim3(n_blocks, C), perm::SCAN_THREADS, 0, ctx->stream>>>((const u64*)d_run, (const u64*)d_tot, n, chunks, per, C, out, out_stride);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return done(B200ZKP_ERR_CUDA); }
+    return done(0);
+}
+
+extern "C" int b200zkp_dev_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires_dev, uint64_t wires_col_stride,
+                                                   const uint64_t* sigmas_dev, uint64_t sigmas_col_stride, uint32_t n_log,
+                                                   uint32_t num_routed, uint32_t degree, const uint64_t* k_is,
+                                                   const uint64_t* betas, const uint64_t* gammas, uint32_t num_challenges,
+                                                   uint64_t* out_dev, uint64_t out_col_stride) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!wires_dev || !sigmas_dev || !k_is || !betas || !gammas || !out_dev) BAD(ctx, "null buffer");
+    return dev_partial_products_locked(ctx, (const u64*)wires_dev, wires_col_stride, (const u64*)sigmas_dev, sigmas_col_stride, n_log,
+                                       num_routed, degree, (const u64*)k_is, (const u64*)betas, (const u64*)gammas, num_challenges,
+                                       (u64*)out_dev, out_col_stride);
+}
+
+extern "C" int b200zkp_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires, const uint64_t* sigmas, uint32_t n_log,
+                                               uint32_t num_routed, uint32_t degree, const uint64_t* k_is, const uint64_t* betas,
+                                               const uint64_t* gammas, uint32_t num_challenges, uint64_t* out) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!wires || !sigmas || !k_is || !betas || !gammas || !out) BAD(ctx, "null buffer");
+    if (n_log > 32 || !num_routed || !degree || !num_challenges) BAD(ctx, "bad shape");
+    const u64 n = (u64)1 << n_log;
+    const u32 chunks = (num_routed + degree - 1) / degree;
+    const size_t in_b = (size_t)num_routed * n * 8, out_b = (size_t)num_challenges * chunks * n * 8;
+    void *d_w = nullptr, *d_s = nullptr, *d_o = nullptr;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, in_b, &d_w))) return rc;
+    if ((rc = dev_alloc(ctx, in_b, &d_s))) { dev_release(ctx, d_w, in_b); return rc; }
+    if ((rc = dev_alloc(ctx, out_b, &d_o))) { dev_release(ctx, d_w, in_b); dev_release(ctx, d_s, in_b); return rc; }
+    auto done = [&](int code) { dev_release(ctx, d_w, in_b); dev_release(ctx, d_s, in_b); dev_release(ctx, d_o, out_b); return code; };
+    if ((rc = h2d(ctx, d_w, wires, in_b)) || (rc = h2d(ctx, d_s, sigmas, in_b))) return done(rc);
+    rc = dev_partial_products_locked(ctx, (const u64*)d_w, n, (const u64*)d_s, n, n_log, num_routed, degree, (const u64*)k_is,
+                                     (const u64*)betas, (const u64*)gammas, num_challenges, (u64*)d_o, n);
+    if (!rc) rc = d2h(ctx, out, d_o, out_b);
+    return done(rc);
 }
 
 // ------------------------------------------------------------------------------------------------ Hasher / field helpers

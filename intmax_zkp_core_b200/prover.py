@@ -1,0 +1,96 @@
+"""Host mirror of the prover steps around the commitments: the permutation argument.
+
+plonky2 @ f99ed9c, plonky2/src/plonk/prover.rs:
+    all_wires_permutation_partial_products(witness, betas, gammas, prover_data, common_data)
+    wires_permutation_partial_products_and_zs(witness, beta, gamma, prover_data, common_data)
+reached from the reference through every prove() (/root/reference/src/transaction/circuits/mod.rs:453,
+src/zkdsa/circuits/mod.rs:326, src/rollup/circuits/mod.rs:1247).  prove() then moves every Z to the front of the batch
+(`zs_partial_products = [plonk_z_vecs, partial_products.concat()].concat()`) and commits it with
+PolynomialBatch::from_values; `zs_partial_products` below returns that batch directly, and on the device path it feeds
+the commitment without leaving HBM.  Same names and argument meaning as plonky2; no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .plonky2 import Context, P, _p, _u64, default_context, log2_strict
+
+MULTIPLICATIVE_GROUP_GENERATOR = 7
+
+
+def get_unique_coset_shifts(num_shifts: int) -> np.ndarray:
+    """CommonCircuitData::k_is: k_j = g^j (plonky2/src/plonk/permutation_argument.rs / plonk_common.rs)"""
+    out, x = [], 1
+    for _ in range(num_shifts):
+        out.append(x)
+        x = x * MULTIPLICATIVE_GROUP_GENERATOR % P
+    return np.array(out, dtype=np.uint64)
+
+
+def num_partial_products(num_routed_wires: int, quotient_degree_factor: int) -> int:
+    """CommonCircuitData::num_partial_products = ceil(num_routed_wires / quotient_degree_factor) - 1"""
+    return -(-num_routed_wires // quotient_degree_factor) - 1
+
+
+def zs_partial_products(wires, sigmas, k_is, betas: Sequence[int], gammas: Sequence[int], quotient_degree_factor: int,
+                        ctx: Optional[Context] = None) -> np.ndarray:
+    """The `Z + partial products` batch of prove(), ready for PolynomialBatch.from_values.
+
+    wires, sigmas: (num_routed_wires, n) — the routed wire columns of the witness and the sigma polynomials' values
+    on the subgroup; k_is: (num_routed_wires,); betas, gammas: one per challenge.
+    Returns (num_challenges * (1 + num_partial_products), n): row c = Z of challenge c, then the partial products of
+    challenge 0, of challenge 1, ..."""
+    ctx = ctx or default_context()
+    w, s = _u64(wires), _u64(sigmas)
+    if w.ndim != 2 or w.shape != s.shape or w.shape[0] == 0:
+        raise ValueError("wires and sigmas must be equal-shaped (num_routed_wires, n) arrays")
+    R, n = w.shape
+    n_log = log2_strict(n)
+    k = _u64(k_is)
+    b, g = _u64(np.asarray(betas, dtype=np.uint64)), _u64(np.asarray(gammas, dtype=np.uint64))
+    if k.shape != (R,) or b.shape != g.shape or b.ndim != 1 or b.size == 0:
+        raise ValueError("k_is must have one entry per routed wire, betas / gammas one per challenge")
+    chunks = -(-R // quotient_degree_factor)
+    out = np.empty((b.size * chunks, n), dtype=np.uint64)
+    ctx.check(ctx._lib.b200zkp_partial_products_and_zs(ctx._h, _p(w), _p(s), n_log, R, quotient_degree_factor, _p(k), _p(b), _p(g),
+                                                       b.size, _p(out)))
+    return out
+
+
+def wires_permutation_partial_products_and_zs(wires, sigmas, k_is, beta: int, gamma: int, quotient_degree_factor: int,
+                                              ctx: Optional[Context] = None) -> np.ndarray:
+    """plonky2's per-challenge form: rows [pp_0 .. pp_{num_prods-1}, Z] (Z last, as prover.rs returns it)."""
+    cols = zs_partial_products(wires, sigmas, k_is, [beta], [gamma], quotient_degree_factor, ctx)
+    return np.concatenate([cols[1:], cols[:1]], axis=0)
+
+
+def all_wires_permutation_partial_products(wires, sigmas, k_is, betas, gammas, quotient_degree_factor: int,
+                                           ctx: Optional[Context] = None):
+    """one wires_permutation_partial_products_and_zs result per challenge (one launch sequence for all of them)"""
+    cols = zs_partial_products(wires, sigmas, k_is, betas, gammas, quotient_degree_factor, ctx)
+    Cn = len(betas)
+    num_prods = cols.shape[0] // Cn - 1
+    return [np.concatenate([cols[Cn + c * num_prods:Cn + (c + 1) * num_prods], cols[c:c + 1]], axis=0) for c in range(Cn)]
+
+
+def zs_partial_products_device(ctx: Context, wires, sigmas, k_is, betas, gammas, quotient_degree_factor: int, out=None):
+    """Device-resident form on torch int64 tensors (uint64 bit patterns): wires / sigmas (num_routed, n) CUDA tensors
+    (rows may be a view of a wider witness matrix as long as each row is contiguous); returns the (C * chunks, n) batch
+    in HBM, ready for device.commit_device."""
+    import torch
+    R, n = wires.shape
+    n_log = log2_strict(n)
+    assert wires.is_cuda and sigmas.is_cuda and wires.stride(1) == 1 and sigmas.stride(1) == 1 and sigmas.shape == wires.shape
+    k = _u64(k_is)
+    b, g = _u64(np.asarray(betas, dtype=np.uint64)), _u64(np.asarray(gammas, dtype=np.uint64))
+    chunks = -(-R // quotient_degree_factor)
+    if out is None:
+        out = torch.empty((b.size * chunks, n), dtype=torch.int64, device=wires.device)
+    ctx.check(ctx._lib.b200zkp_dev_partial_products_and_zs(ctx._h, C.c_void_p(wires.data_ptr()), wires.stride(0),
+                                                           C.c_void_p(sigmas.data_ptr()), sigmas.stride(0), n_log, R,
+                                                           quotient_degree_factor, _p(k), _p(b), _p(g), b.size,
+                                                           C.c_void_p(out.data_ptr()), out.stride(0)))
+    return out

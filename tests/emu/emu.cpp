@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../intmax_zkp_core_b200/csrc/merkle_kernels.cuh"
+#include "../../intmax_zkp_core_b200/csrc/perm_kernels.cuh"
 #include "../../intmax_zkp_core_b200/csrc/host_plan.hpp"
 
 using gl::u32;
@@ -94,6 +95,18 @@ static void transform(const u64* in, u64 in_stride, u64* out, u64 out_stride, u6
 }
 
 extern "C" {
+u64 emu_inverse(u64 x) { return perm::inverse(x); }
+// rows of the permutation argument (perm::row_chunk_products): running[(c * chunks + l) * n + i]
+void emu_perm_rows(const u64* wires, const u64* sigmas, const u64* k_is, const u64* betas, const u64* gammas, u32 n_log, u32 R,
+                   u32 degree, u32 C, u64* running) {
+    perm::Params p;
+    p.n = (u64)1 << n_log;
+    p.wires = wires; p.wires_stride = p.n; p.sigmas = sigmas; p.sigmas_stride = p.n;
+    p.k_is = k_is; p.betas = betas; p.gammas = gammas; p.omega = hostgl::root(n_log);
+    p.R = R; p.degree = degree; p.chunks = (R + degree - 1) / degree; p.C = C;
+    for (u32 c = 0; c < C; c++)
+        for (u64 i = 0; i < p.n; i++) perm::row_chunk_products(p, i, c, running);
+}
 void emu_permute(u64* s) { u64 t[12]; memcpy(t, s, sizeof t); poseidon::permute(t); memcpy(s, t, sizeof t); }
 void emu_sponge(const u64* leaf, u64 col_stride, u32 len, u32 noop_short, u64* out4) {
     u64 s[12];

@@ -108,3 +108,35 @@ def test_ntt_hostile_columns(emu, oracle):
     out = np.zeros_like(v)
     emu.emu_intt(ptr(v), ptr(out), 6, v.shape[0])
     assert (out == np.stack([oracle.ifft(c) for c in v])).all()
+
+
+def test_permutation_argument_rows(emu):
+    """perm::row_chunk_products + perm::inverse (row N1a) against the pure-Python restatement oracle/perm_ref.py"""
+    from oracle import perm_ref as PR
+    import random
+    emu.emu_inverse.restype = C.c_uint64
+    emu.emu_inverse.argtypes = [C.c_uint64]
+    rnd = random.Random(3)
+    for x in [1, 2, P - 1, 7, 2**32, 2**32 - 1] + [rnd.randrange(1, P) for _ in range(50)]:
+        assert emu.emu_inverse(x) * x % P == 1
+    assert emu.emu_inverse(0) == 0
+    for R, degree, n_log, Cn in ((12, 8, 5, 2), (80, 8, 4, 2), (7, 3, 3, 1), (5, 8, 2, 3)):
+        wires, sigmas, k_is = PR.valid_permutation_instance(R, n_log, seed=R)
+        betas = [rnd.randrange(P) for _ in range(Cn)]
+        gammas = [rnd.randrange(P) for _ in range(Cn)]
+        n = 1 << n_log
+        chunks = (R + degree - 1) // degree
+        running = np.zeros(Cn * chunks * n, np.uint64)
+        w = np.array(wires, np.uint64)
+        s = np.array(sigmas, np.uint64)
+        emu.emu_perm_rows(ptr(w), ptr(s), ptr(np.array(k_is, np.uint64)), ptr(np.array(betas, np.uint64)),
+                          ptr(np.array(gammas, np.uint64)), n_log, R, degree, Cn, ptr(running))
+        running = running.reshape(Cn, chunks, n)
+        cols = PR.partial_products_and_zs(wires, sigmas, k_is, betas, gammas, degree)
+        num_prods = chunks - 1
+        for c in range(Cn):
+            z = cols[c]
+            for i in range(n):
+                for l in range(num_prods):
+                    assert int(running[c, l, i]) * z[i] % P == cols[Cn + c * num_prods + l][i]
+                assert int(running[c, chunks - 1, i]) * z[i] % P == (z[i + 1] if i + 1 < n else 1)
