@@ -47,4 +47,11 @@ extern "C" {
     pub fn b200zkp_fri_query(f: *mut b200zkp_fri, layer: u32, idx: *const u64, n_idx: u64, evals: *mut u64, siblings: *mut u64) -> c_int;
     pub fn b200zkp_pow_grind(ctx: *mut b200zkp_ctx, state: *const u64, witness_pos: u32, response_pos: u32,
         min_leading_zeros: u32, max_candidates: u64, witness: *mut u64) -> c_int;
+    // row N1a: prover.rs wires_permutation_partial_products_and_zs for every challenge, columns in committed order
+    pub fn b200zkp_partial_products_and_zs(ctx: *mut b200zkp_ctx, wires: *const u64, sigmas: *const u64, n_log: u32,
+        num_routed: u32, degree: u32, k_is: *const u64, betas: *const u64, gammas: *const u64, num_challenges: u32,
+        out: *mut u64) -> c_int;
+    pub fn b200zkp_dev_partial_products_and_zs(ctx: *mut b200zkp_ctx, wires_dev: *const u64, wires_col_stride: u64,
+        sigmas_dev: *const u64, sigmas_col_stride: u64, n_log: u32, num_routed: u32, degree: u32, k_is: *const u64,
+        betas: *const u64, gammas: *const u64, num_challenges: u32, out_dev: *mut u64, out_col_stride: u64) -> c_int;
 }
