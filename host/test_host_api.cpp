@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "fri_api.hpp"
+#include "prover_api.hpp"
 
 using namespace plonky2;
 
@@ -88,6 +89,29 @@ int main() {
         std::printf("fri digest %016llx pow %llu\n", (unsigned long long)d, (unsigned long long)proof.pow_witness);
         auto ev = o1.eval_ext2(Ext{555ull, 777ull});
         CHECK(ev.size() == 2);
+    }
+    {   // row N1a: identity permutation (sigma = k_j * w^i) makes every quotient 1, so Z and all partial products are 1;
+        // swapping two equal wires keeps the argument closed, a wrong sigma opens it
+        const size_t R = 16, nn = 32, deg = 8;
+        auto k_is = get_unique_coset_shifts(R);
+        CHECK(k_is[2] == 49 && num_partial_products(80, 8) == 9);
+        auto mulmod = [](F a, F b) { return (F)((unsigned __int128)a * b % GOLDILOCKS_ORDER); };
+        F w32 = 1753635133440165772ull;                      // generator of the 2^32 subgroup
+        for (int i = 5; i < 32; i++) w32 = mulmod(w32, w32);  // w_32
+        std::vector<std::vector<F>> wires(R, std::vector<F>(nn)), sigmas(R, std::vector<F>(nn));
+        for (size_t j = 0; j < R; j++) {
+            F x = 1;
+            for (size_t i = 0; i < nn; i++) { wires[j][i] = splitmix64(j * nn + i) % GOLDILOCKS_ORDER; sigmas[j][i] = mulmod(k_is[j], x); x = mulmod(x, w32); }
+        }
+        auto cols = zs_partial_products(ctx, wires, sigmas, k_is, {11, 22}, {33, 44}, deg);
+        CHECK(cols.size() == 4 && cols[0].size() == nn);
+        for (auto& col : cols) for (F v : col) CHECK(v == 1);
+        wires[3][7] = wires[9][20];                          // copy constraint (3, 7) <-> (9, 20)
+        std::swap(sigmas[3][7], sigmas[9][20]);
+        cols = zs_partial_products(ctx, wires, sigmas, k_is, {11, 22}, {33, 44}, deg);
+        CHECK(cols[0][0] == 1 && cols[0][8] != 1 && cols[0][21] == 1 && cols[1][31] == 1);
+        auto per = all_wires_permutation_partial_products(ctx, wires, sigmas, k_is, {11, 22}, {33, 44}, deg);
+        CHECK(per.size() == 2 && per[1].size() == 2 && per[1][1] == cols[1] && per[0][0] == cols[2]);
     }
     std::printf("host C++ API ok\n");
     return 0;

@@ -182,6 +182,10 @@ int b200zkp_two_to_one(b200zkp_ctx* ctx, const uint64_t* left, const uint64_t* r
 /* in-place transforms of k columns of 2^n_log elements (natural order in and out) */
 int b200zkp_ntt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k);
 int b200zkp_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k);
+/* PolynomialValues::coset_ifft(shift) (plonky2_field polynomial/mod.rs): k columns of values on shift * <w_n>, natural
+ * order, in place -> coefficients.  prove() runs it on the quotient values (compute_quotient_polys, shift = 7) before
+ * cutting them into degree-n chunks for PolynomialBatch::from_coeffs (row N1c).  Error: bad arg for shift = 0 mod p. */
+int b200zkp_coset_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k, uint64_t shift);
 /* coset LDE: coeffs k*n -> out k*N, out[c][i] = p_c(7 * w_N^i), natural order (A4) */
 int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,
                       uint32_t rate_bits, uint64_t* out);
@@ -191,6 +195,9 @@ int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, 
  * nothing; needed when n_log > 10 (may be NULL otherwise). */
 int b200zkp_dev_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
                      uint64_t out_stride, uint64_t* scratch, uint32_t n_log, uint32_t k);
+/* device form of b200zkp_coset_intt: values [k][in_stride] -> coeffs [k][out_stride]; scratch as for b200zkp_dev_intt */
+int b200zkp_dev_coset_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
+                           uint64_t out_stride, uint64_t* scratch, uint32_t n_log, uint32_t k, uint64_t shift);
 /* coeffs [k][coeff_stride] -> lde [k][lde_stride] in leaf order, only leaf blocks
  * [block_begin, block_end) of the 2^rate_bits coset blocks (block b = leaves [b*n, (b+1)*n), i.e. the
  * coset 7*w_N^bitrev(b)); block b is written at column offset (b - block_begin)*n. */

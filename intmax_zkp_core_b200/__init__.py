@@ -10,13 +10,13 @@ package is the host-side mirror of the reference interface.  There is no CPU fal
 from ._lib import B200ZkpError, build, lib  # noqa: F401
 from .plonky2 import (  # noqa: F401
     Context, HashOut, MerkleCap, MerkleProof, MerkleTree, PolynomialBatch, PolynomialCoeffs, PolynomialValues,
-    PoseidonHash, PoseidonPermutation, SALT_SIZE, coset_lde_batch, default_context, fft_batch, ifft_batch,
+    PoseidonHash, PoseidonPermutation, SALT_SIZE, coset_ifft_batch, coset_lde_batch, default_context, fft_batch, ifft_batch,
     log2_strict, reverse_bits, verify_merkle_proof_to_cap,
 )
 
 __all__ = [
     "B200ZkpError", "Context", "HashOut", "MerkleCap", "MerkleProof", "MerkleTree", "PolynomialBatch",
     "PolynomialCoeffs", "PolynomialValues", "PoseidonHash", "PoseidonPermutation", "SALT_SIZE", "build",
-    "coset_lde_batch", "default_context", "fft_batch", "ifft_batch", "lib", "log2_strict", "reverse_bits",
+    "coset_ifft_batch", "coset_lde_batch", "default_context", "fft_batch", "ifft_batch", "lib", "log2_strict", "reverse_bits",
     "verify_merkle_proof_to_cap",
 ]

@@ -1666,6 +1666,54 @@ extern "C" int b200zkp_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, ui
     return transform_host(ctx, (u64*)data, n_log, k, 1);
 }
 
+// PolynomialValues::coset_ifft(shift) (plonky2_field polynomial/mod.rs): values on shift * <w_n>, natural order ->
+// coefficients: inverse transform, then coefficient j times shift^-j.  prove() runs it on the quotient values
+// (compute_quotient_polys: quotient_values.coset_ifft(F::coset_shift()), row N1c).
+static int dev_coset_intt_locked(b200zkp_ctx* ctx, const u64* values, u64 in_stride, u64* coeffs, u64 out_stride, u64* scratch,
+                                 u32 n_log, u32 k, u64 shift) {
+    if (n_log > 32) BAD(ctx, "n_log exceeds two-adicity");
+    shift %= hostgl::P;
+    if (!shift) BAD(ctx, "coset shift must be non-zero");
+    if (!k) return 0;
+    TRY(dev_intt_locked(ctx, values, in_stride, coeffs, out_stride, scratch, n_log, k));
+    if (shift == 1 || n_log == 0) return 0;
+    const u64* pw = nullptr;
+    TRY(get_power_scale(ctx, hostgl::inv(shift), n_log, &pw));
+    u64 n = (u64)1 << n_log;
+    ntt::scale_columns_kernel<<<dim3((unsigned)((n + 255) / 256), k), 256, 0, ctx->stream>>>(coeffs, out_stride, n, pw);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" int b200zkp_dev_coset_intt(b200zkp_ctx* ctx, const uint64_t* values, uint64_t in_stride, uint64_t* coeffs,
+                                      uint64_t out_stride, uint64_t* scratch, uint32_t n_log, uint32_t k, uint64_t shift) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!values || !coeffs) BAD(ctx, "null buffer");
+    if (n_log > 10 && !scratch) BAD(ctx, "scratch required for n_log > 10");
+    return dev_coset_intt_locked(ctx, (const u64*)values, in_stride, (u64*)coeffs, out_stride, (u64*)scratch, n_log, k, shift);
+}
+
+extern "C" int b200zkp_coset_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k, uint64_t shift) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!k) return 0;
+    if (!data) BAD(ctx, "null buffer");
+    if (n_log > 32) BAD(ctx, "n_log exceeds two-adicity");
+    size_t bytes = ((size_t)k << n_log) * 8;
+    void *d = nullptr, *scratch = nullptr, *dout = nullptr;
+    int rc = 0;
+    if ((rc = dev_alloc(ctx, bytes, &d)) || (rc = dev_alloc(ctx, bytes, &scratch)) || (rc = dev_alloc(ctx, bytes, &dout))) {
+        dev_release(ctx, d, bytes); dev_release(ctx, scratch, bytes);
+        return rc;
+    }
+    auto done = [&](int code) { dev_release(ctx, d, bytes); dev_release(ctx, scratch, bytes); dev_release(ctx, dout, bytes); return code; };
+    if ((rc = h2d(ctx, d, data, bytes))) return done(rc);
+    u64 n = (u64)1 << n_log;
+    if ((rc = dev_coset_intt_locked(ctx, (const u64*)d, n, (u64*)dout, n, (u64*)scratch, n_log, k, shift))) return done(rc);
+    return done(d2h(ctx, data, dout, bytes));
+}
+
 // natural-order coset LDE (an independent route from the leaf-order dev_lde: zero-pad, scale by 7^i,
 // one size-N natural transform) — plonky2's own formulation of A4.
 extern "C" int b200zkp_coset_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint32_t n_log, uint32_t k,

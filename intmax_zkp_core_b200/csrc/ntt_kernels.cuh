@@ -400,6 +400,12 @@ __global__ void bitrev_copy_kernel(const u64* __restrict__ src, u64* __restrict_
     dst[c * dst_stride + j] = gl::canon(src[c * src_stride + i]);
 }
 
+// data[c][j] *= pw[j]  (coefficient scaling of a coset inverse transform); grid (ceil(n / 256), k)
+__global__ void scale_columns_kernel(u64* __restrict__ data, u64 stride, u64 n, const u64* __restrict__ pw) {
+    u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { u64* p = data + (u64)blockIdx.y * stride + j; *p = gl::mul(*p, gl::ldg(pw + j)); }
+}
+
 __global__ void canon_copy_kernel(const u64* __restrict__ src, u64* __restrict__ dst, u64 count) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g < count) dst[g] = gl::canon(src[g]);

@@ -339,6 +339,10 @@ class PolynomialValues:
     def ifft(self, ctx: Optional[Context] = None) -> "PolynomialCoeffs":
         return PolynomialCoeffs(ifft_batch(self.values.reshape(1, -1), ctx)[0])
 
+    def coset_ifft(self, shift: int, ctx: Optional[Context] = None) -> "PolynomialCoeffs":
+        """values on shift * <w_n> (natural order) -> coefficients (plonky2_field polynomial/mod.rs)"""
+        return PolynomialCoeffs(coset_ifft_batch(self.values.reshape(1, -1), shift, ctx)[0])
+
     def __len__(self):
         return self.values.size
 
@@ -375,6 +379,16 @@ def ifft_batch(values, ctx: Optional[Context] = None) -> np.ndarray:
     x = _u64(values).copy()
     k, n = x.shape
     ctx.check(ctx._lib.b200zkp_intt(ctx._h, _p(x), log2_strict(n), k))
+    return x
+
+
+def coset_ifft_batch(values, shift: int, ctx: Optional[Context] = None) -> np.ndarray:
+    """PolynomialValues::coset_ifft(shift) over the rows of a (k, n) array"""
+    ctx = ctx or default_context()
+    x = _u64(values).copy()
+    if x.ndim != 2:
+        raise ValueError("expected a (k, n) array")
+    ctx.check(ctx._lib.b200zkp_coset_intt(ctx._h, _p(x), log2_strict(x.shape[1]), x.shape[0], int(shift) % 2**64))
     return x
 
 

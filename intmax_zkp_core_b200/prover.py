@@ -16,7 +16,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .plonky2 import Context, P, _p, _u64, default_context, log2_strict
+from .plonky2 import Context, P, PolynomialBatch, _p, _u64, coset_ifft_batch, default_context, log2_strict
 
 MULTIPLICATIVE_GROUP_GENERATOR = 7
 
@@ -94,3 +94,43 @@ def zs_partial_products_device(ctx: Context, wires, sigmas, k_is, betas, gammas,
                                                            quotient_degree_factor, _p(k), _p(b), _p(g), b.size,
                                                            C.c_void_p(out.data_ptr()), out.stride(0)))
     return out
+
+
+def quotient_poly_chunks(quotient_values, degree_bits: int, ctx: Optional[Context] = None) -> np.ndarray:
+    """Tail of plonky2's compute_quotient_polys + the chunking in prove() (row N1c):
+
+        quotient_values.map(|v| v.coset_ifft(F::coset_shift()))            // one polynomial per challenge
+        quotient_poly.trim_to_len(quotient_degree); quotient_poly.chunks(degree)
+
+    quotient_values: (num_challenges, n * 2^quotient_degree_bits) values on the coset 7 <w>, natural order.
+    Returns (num_challenges * 2^quotient_degree_bits, n) coefficient chunks, the input of PolynomialBatch.from_coeffs."""
+    q = _u64(quotient_values)
+    if q.ndim != 2:
+        raise ValueError("expected (num_challenges, n << quotient_degree_bits)")
+    n = 1 << degree_bits
+    if q.shape[1] % n or q.shape[1] < n:
+        raise ValueError("quotient length must be a multiple of the degree")
+    coeffs = coset_ifft_batch(q, MULTIPLICATIVE_GROUP_GENERATOR, ctx)
+    return coeffs.reshape(q.shape[0] * (q.shape[1] // n), n)
+
+
+def commit_quotient(quotient_values, degree_bits: int, rate_bits: int, blinding: bool, cap_height: int, salt=None,
+                    ctx: Optional[Context] = None) -> PolynomialBatch:
+    """quotient_polys_commitment of prove(): PolynomialBatch::from_coeffs(all_quotient_poly_chunks, ...)"""
+    return PolynomialBatch.from_coeffs(quotient_poly_chunks(quotient_values, degree_bits, ctx), rate_bits, blinding, cap_height,
+                                       salt=salt, ctx=ctx)
+
+
+def commit_quotient_device(ctx: Context, quotient_values, degree_bits: int, rate_bits: int, cap_height: int):
+    """device-resident form: (C, n << q) CUDA tensor of quotient values -> DeviceCommitment of the C * 2^q chunks; the
+    coefficients never leave HBM"""
+    import torch
+    from .device import commit_device
+    Cn, total = quotient_values.shape
+    n = 1 << degree_bits
+    assert quotient_values.is_cuda and quotient_values.is_contiguous() and total % n == 0
+    coeffs = torch.empty_like(quotient_values)
+    scratch = torch.empty_like(quotient_values)
+    ctx.check(ctx._lib.b200zkp_dev_coset_intt(ctx._h, C.c_void_p(quotient_values.data_ptr()), total, C.c_void_p(coeffs.data_ptr()), total,
+                                              C.c_void_p(scratch.data_ptr()), log2_strict(total), Cn, MULTIPLICATIVE_GROUP_GENERATOR))
+    return commit_device(ctx, coeffs.view(Cn * (total // n), n), rate_bits, cap_height, is_coeffs=True)

@@ -104,3 +104,57 @@ def test_bad_arguments(ctx):
         Z.zs_partial_products(w, np.ones((4, 4), np.uint64), np.ones(4, np.uint64), [1], [1], 8, ctx)
     with pytest.raises(B200ZkpError):
         Z.zs_partial_products(np.ones((40, 8), np.uint64), np.ones((40, 8), np.uint64), np.ones(40, np.uint64), [1], [1], 1, ctx)
+
+
+def test_coset_ifft_inverts_the_coset_transform(ctx):
+    """PolynomialValues::coset_ifft: against the oracle's coset transform (shift 7) and the definition (other shifts)"""
+    import intmax_zkp_core_b200 as z
+    from oracle import oracle as O
+    for n_log, k in ((0, 2), (1, 3), (5, 4), (11, 3), (13, 2)):
+        c = O.synthetic_values(k, 1 << n_log, seed=n_log)
+        vals = np.stack([O.coset_lde(row, 0) for row in c])   # p(7 w^i), natural order, one polynomial per row
+        assert (z.coset_ifft_batch(vals, 7, ctx) == c).all()
+    rnd = random.Random(4)
+    n_log, shift = 4, 0xDEADBEEF12345
+    n = 1 << n_log
+    coeffs = [rnd.randrange(P) for _ in range(n)]
+    w = PR.root(n_log)
+    vals = []
+    for i in range(n):
+        x = shift * pow(w, i, P) % P
+        acc = 0
+        for cf in reversed(coeffs):
+            acc = (acc * x + cf) % P
+        vals.append(acc)
+    got = z.PolynomialValues(np.array(vals, np.uint64)).coset_ifft(shift, ctx)
+    assert [int(v) for v in got.coeffs] == coeffs
+    # a non-canonical shift is reduced first: 5 + p names the coset of 5
+    small = np.array([[3, 1, 4, 1, 5, 9, 2, 6]], np.uint64)
+    assert (z.coset_ifft_batch(small, 5 + P, ctx) == z.coset_ifft_batch(small, 5, ctx)).all()
+    from intmax_zkp_core_b200._lib import B200ZkpError
+    with pytest.raises(B200ZkpError):
+        z.coset_ifft_batch(np.ones((1, 4), np.uint64), P, ctx)
+
+
+def test_quotient_chunks_commitment(ctx):
+    """row N1c: quotient values on the 8n-point coset -> coset_ifft -> 8 chunks per challenge -> from_coeffs, host and device"""
+    import torch
+    import intmax_zkp_core_b200 as z
+    from intmax_zkp_core_b200 import device as D, prover as Z
+    from oracle import oracle as O
+    degree_bits, q_bits, Cn = 7, 3, 2
+    n = 1 << degree_bits
+    qpoly = O.synthetic_values(Cn, n << q_bits, seed=9)       # the quotient polynomials' coefficients
+    qvals = np.stack([O.coset_lde(row, 0) for row in qpoly])  # their values on 7 <w_8n>
+    chunks = Z.quotient_poly_chunks(qvals, degree_bits, ctx)
+    assert chunks.shape == (Cn << q_bits, n)
+    assert (chunks == qpoly.reshape(Cn << q_bits, n)).all()
+    batch = Z.commit_quotient(qvals, degree_bits, 3, False, 4, ctx=ctx)
+    ref = O.commit(qpoly.reshape(Cn << q_bits, n), 3, 4, is_coeffs=True)
+    assert (batch.merkle_tree.cap.elements == ref["cap"]).all()
+    tctx = D.torch_context(0)
+    dv = torch.from_numpy(qvals.view(np.int64)).cuda()
+    com = Z.commit_quotient_device(tctx, dv, degree_bits, 3, 4)
+    torch.cuda.synchronize()
+    assert (com.cap.cpu().numpy().view(np.uint64) == ref["cap"]).all()
+    assert (com.coeffs.cpu().numpy().view(np.uint64) == qpoly.reshape(Cn << q_bits, n)).all()

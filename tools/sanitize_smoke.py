@@ -45,5 +45,14 @@ for (n_log, ks, r, h, arities, mul_by_x) in [(12, (3, 2), 1, 2, (4, 3), True), (
         ch.observe_cap(b._cap)
     proof = zf.prove_openings(inst, batches, ch, params, mul_by_x)
     assert len(proof.query_round_proofs) == 4
+# permutation argument (row N1a): ragged last chunk, more than one scan block, a single row
+from intmax_zkp_core_b200 import prover as zp
+from oracle import perm_ref as PR
+for (R, deg, n_log, Cn) in [(13, 4, 11, 2), (80, 8, 5, 2), (3, 8, 0, 1)]:
+    wires, sigmas, k_is = PR.valid_permutation_instance(R, n_log, seed=R)
+    got = zp.zs_partial_products(np.array(wires, np.uint64), np.array(sigmas, np.uint64), np.array(k_is, np.uint64),
+                                 list(range(5, 5 + Cn)), list(range(9, 9 + Cn)), deg, ctx)
+    ref = PR.partial_products_and_zs(wires, sigmas, k_is, list(range(5, 5 + Cn)), list(range(9, 9 + Cn)), deg)
+    assert (got == np.array(ref, np.uint64)).all()
 print("sanitize smoke ok, launches:", ctx.launch_count)
 ctx.close()
