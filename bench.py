@@ -353,9 +353,12 @@ def run_b200(args):
             #   multiplier pipe: 2605 IMAD.WIDE (2 slots each: they issue at half the IMAD rate) + 6070 single-slot
             #                    (2033 IMAD shift-adds of the linear layers, 4037 IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL)
             #   ALU pipe:        9979 IADD3 / IADD3.X / LOP3 / SEL / LEA / SHF (one slot each)
+            # minus what folding the round constants into the limb packing removed after that capture (static SASS model,
+            # tools/sass_mix.py): 26 multiplier slots, 419 ALU slots, 445 instructions.
             leaf_perms = N_local * ((k + 7) // 8)
-            slots_per_perm = 2 * 2605 + 6070
-            alu_slots_per_perm = 9979
+            slots_per_perm = 2 * 2605 + 6070 - 26
+            alu_slots_per_perm = 9979 - 419
+            instr_per_perm = 19352 - 445
             slot_rate = leaf_perms * slots_per_perm / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
             slot_peak = gips["imad"] * 1e9
             line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": slot_rate, "peak": slot_peak,
@@ -363,8 +366,8 @@ def run_b200(args):
                                        "slots_per_permutation": slots_per_perm, "imad_wide_per_permutation": 2605,
                                        "alu_slots_per_permutation": alu_slots_per_perm,
                                        "alu_frac": (leaf_perms * alu_slots_per_perm / (leaf_ms_avg * 1e-3) / (gips["lop3"] * 1e9)) if leaf_ms_avg else 0.0,
-                                       "instructions_per_permutation": 19352,
-                                       "issue_frac": (leaf_perms * 19352 / (leaf_ms_avg * 1e-3) / (2 * gips["imad"] * 1e9)) if leaf_ms_avg else 0.0,
+                                       "instructions_per_permutation": instr_per_perm,
+                                       "issue_frac": (leaf_perms * instr_per_perm / (leaf_ms_avg * 1e-3) / (2 * gips["imad"] * 1e9)) if leaf_ms_avg else 0.0,
                                        "permutations_per_launch": leaf_perms,
                                        "ncu": {"pipe_fmaheavy_busy": 0.827, "pipe_alu_busy": 0.689, "issue_active": 0.687}}
             if not os.environ.get("B200ZKP_SKIP_CPU"):

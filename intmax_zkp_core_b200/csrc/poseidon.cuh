@@ -199,9 +199,10 @@ GL_FN void layer_stay(SplitState& c, const int (&z8)[3], u32 Z) {
     for (int k = 0; k < 6; k++) normalise(c.W[0][k], c.W[1][k], c.W[2][k], Z);
 }
 
-// linear layer back to words: out[k] = A[k] + B[k], out[k + 6] = A[k] - B[k] with A = 16 Cq +- D; `bias` (a multiple of
+// linear layer back to words: out[k] = A[k] + B[k], out[k + 6] = A[k] - B[k] with A = 16 Cq +- D, plus the next round's
+// constants `nxt` (they ride on the limb packing: 3 instructions per word instead of 6); `bias` (a multiple of
 // the opaque zero, see above) lifts limbs that may be negative after partial rounds; the constants that follow absorb it
-GL_FN void layer_leave(const SplitState& c, const int (&z8)[3], u64 (&s)[WIDTH], u32 bias, u32 Z) {
+GL_FN void layer_leave(const SplitState& c, const int (&z8)[3], u64 (&s)[WIDTH], u32 bias, u32 Z, const unsigned long long* nxt) {
     u32 o[3][WIDTH];
 #pragma unroll
     for (int L = 0; L < 3; L++) {
@@ -217,7 +218,7 @@ GL_FN void layer_leave(const SplitState& c, const int (&z8)[3], u64 (&s)[WIDTH],
         o[L][0] += (u32)z8[L];
     }
 #pragma unroll
-    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], 0ull);
+    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], (u64)nxt[r]);
 }
 
 // v / 4 mod p:  v = 4 q + r,  r / 4 = ((4 - r) << 62) - ((4 - r) << 30) + 1  (r = 0 gives p, which the carry fold removes)
@@ -290,12 +291,8 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
         if (stay) {
             layer_stay(c, z8, Z);
         } else {
-            layer_leave(c, z8, s, (full ? 0u : (1u << 30)) + Z, Z);
-            if (r + 1 < 30) {
-                const unsigned long long* nxt = &SPLIT_ADD[(r + 1) * WIDTH];
-#pragma unroll
-                for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], nxt[i]);
-            }
+            // the constants of the next round ride on the limb packing (row 30 of SPLIT_ADD is all zero)
+            layer_leave(c, z8, s, (full ? 0u : (1u << 30)) + Z, Z, &SPLIT_ADD[(r + 1) * WIDTH]);
         }
     }
 #pragma unroll
