@@ -11,8 +11,12 @@ import intmax_zkp_core_b200 as z
 from oracle import oracle as O
 
 ctx = z.Context(0)
-for (n_log, k, r, h, coeffs, salted) in [(0, 3, 3, 2, False, False), (3, 9, 3, 2, False, False), (7, 5, 1, 0, True, False),
-                                         (9, 20, 3, 4, False, True), (10, 135, 3, 4, False, False), (13, 4, 2, 6, False, False)]:
+ONLY = os.environ.get("SANITIZE_ONLY")      # "new": only the kernels added last (latency-form hashing, permutation argument, coset_ifft)
+shapes = [(0, 3, 3, 2, False, False), (3, 9, 3, 2, False, False), (7, 5, 1, 0, True, False),
+          (9, 20, 3, 4, False, True), (10, 135, 3, 4, False, False), (13, 4, 2, 6, False, False)]
+if ONLY == "new":
+    shapes = [(3, 9, 3, 2, False, False), (9, 20, 3, 4, False, False)]
+for (n_log, k, r, h, coeffs, salted) in shapes:
     v = O.synthetic_values(k, 1 << n_log, seed=1)
     salt = O.synthetic_values(4, 1 << (n_log + r), seed=2) if salted else None
     ctor = z.PolynomialBatch.from_coeffs if coeffs else z.PolynomialBatch.from_values
@@ -31,9 +35,13 @@ z.coset_lde_batch(x, 2, ctx)
 t = z.MerkleTree.new(np.arange(64 * 7, dtype=np.uint64).reshape(64, 7), 2, ctx=ctx)
 t.prove(5); t.digests
 z.PoseidonHash.hash_no_pad_batch(np.arange(40, dtype=np.uint64).reshape(4, 10), ctx)
+z.PoseidonHash.two_to_one_batch(np.arange(12, dtype=np.uint64).reshape(3, 4), np.arange(12, 24, dtype=np.uint64).reshape(3, 4), ctx)
+z.PoseidonPermutation.permute(np.arange(12, dtype=np.uint64), ctx)
+assert (z.coset_ifft_batch(np.stack([O.coset_lde(row, 0) for row in x]), 7, ctx) == x).all()
 # opening proof (rows N2 + N3): evaluation, alpha-reduction, blocked suffix scan over > 1 segment, FRI layers, PoW, gathers
 import intmax_zkp_core_b200.fri as zf
-for (n_log, ks, r, h, arities, mul_by_x) in [(12, (3, 2), 1, 2, (4, 3), True), (5, (2,), 3, 0, (2, 1), False), (1, (1, 1), 0, 0, (), True)]:
+fri_cases = [(12, (3, 2), 1, 2, (4, 3), True), (5, (2,), 3, 0, (2, 1), False), (1, (1, 1), 0, 0, (), True)]
+for (n_log, ks, r, h, arities, mul_by_x) in ([] if ONLY == "new" else fri_cases):
     batches = [z.PolynomialBatch.from_coeffs(O.synthetic_values(k, 1 << n_log, seed=3 + i), r, False, h, ctx=ctx) for i, k in enumerate(ks)]
     batches[0].eval_ext2(np.array([5, 6], np.uint64))
     inst = zf.FriInstanceInfo([zf.FriBatchInfo((11, 12), [zf.FriPolynomialInfo(o, i) for o, k in enumerate(ks) for i in range(k)]),
