@@ -21,6 +21,11 @@
 #include "goldilocks.cuh"
 #include "poseidon_tables.cuh"
 
+// which groups of integer operations are pinned to the ALU pipe (see "Pipe steering" below); tuning builds override it
+#ifndef B200ZKP_MDS_ALU_MASK
+#define B200ZKP_MDS_ALU_MASK 61   // tuning builds only (tools/bench_variants.sh)
+#endif
+
 namespace poseidon {
 
 using gl::u32;
@@ -40,7 +45,7 @@ GL_FN u64 sbox(u64 x) {
 GL_FN u64 add_const(u64 a, u64 c) { return gl::add_nc(a, c); }
 
 // value = O0 + O1 * 2^22 + O2 * 2^43 + rc  with O_i < 2^31, rc canonical  ->  arbitrary u64 congruent mod p
-GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc) {
+GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc, u32 zero = 0u) {
 #ifdef B200ZKP_HOST_EMU
     unsigned __int128 v = (unsigned __int128)O0 + ((unsigned __int128)O1 << 22) + ((unsigned __int128)O2 << 43) + rc;
     u64 lo = (u64)v;
@@ -54,9 +59,17 @@ GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc) {
         ".reg .u32 a, b, c, d, w0, w1, top, rc0, rc1, m;\n\t"
         ".reg .u64 t, u;\n\t"
         "mov.b64 {rc0, rc1}, %4;\n\t"
+#if B200ZKP_MDS_ALU_MASK & 128
+        "shf.l.wrap.b32 a, %5, %2, 22;\n\t"    // a funnel shift with an opaque-zero low word stays on the ALU pipe (SHF)
+#else
         "shl.b32 a, %2, 22;\n\t"
+#endif
         "shr.u32 b, %2, 10;\n\t"
+#if B200ZKP_MDS_ALU_MASK & 128
+        "shf.l.wrap.b32 c, %5, %3, 11;\n\t"
+#else
         "shl.b32 c, %3, 11;\n\t"
+#endif
         "shr.u32 d, %3, 21;\n\t"
         "add.cc.u32 w0, %1, a;\n\t"
         "addc.cc.u32 w1, b, c;\n\t"
@@ -73,7 +86,7 @@ GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc) {
         "subc.u32 w1, w1, 0;\n\t"
         "add.u32 w1, w1, m;\n\t"
         "mov.b64 %0, {w0, w1};\n\t"
-        "}" : "=l"(r) : "r"(O0), "r"(O1), "r"(O2), "l"(rc));
+        "}" : "=l"(r) : "r"(O0), "r"(O1), "r"(O2), "l"(rc), "r"(zero));
     return r;
 #endif
 }
@@ -100,11 +113,9 @@ static const u32 OPAQUE_ZERO = 0;
 #else
 static __device__ __constant__ u32 OPAQUE_ZERO = 0;
 #endif
-#ifndef B200ZKP_MDS_ALU_MASK
-#define B200ZKP_MDS_ALU_MASK 61   // tuning builds only (tools/bench_variants.sh)
-#endif
 static constexpr bool kAluSp = B200ZKP_MDS_ALU_MASK & 1, kAluUv = B200ZKP_MDS_ALU_MASK & 2, kAluC = B200ZKP_MDS_ALU_MASK & 4,
-                      kAluOut = B200ZKP_MDS_ALU_MASK & 8, kAluNorm = B200ZKP_MDS_ALU_MASK & 16, kAluInj = B200ZKP_MDS_ALU_MASK & 32;
+                      kAluOut = B200ZKP_MDS_ALU_MASK & 8, kAluNorm = B200ZKP_MDS_ALU_MASK & 16, kAluInj = B200ZKP_MDS_ALU_MASK & 32,
+                      kAluRing = B200ZKP_MDS_ALU_MASK & 64, kAluShift = B200ZKP_MDS_ALU_MASK & 128;
 
 // The state between two linear layers, in the split basis of Z[t] / (t^12 - 1) = (t^3 - 1)(t^3 + 1)(t^6 + 1): three limb
 // planes of U[3], V[3], W[6] (signed 32-bit; tools/poseidon_crt_model.py bounds every intermediate by interval arithmetic).
@@ -160,13 +171,14 @@ GL_FN void ring_products(const int (&U)[3], const int (&V)[3], const int (&W)[6]
     Cq[0] = T + U[2] + (int)(kAluC ? Z : 0u);
     Cq[1] = T + U[0] + (int)(kAluC ? Z : 0u);
     Cq[2] = T + U[1] + (int)(kAluC ? Z : 0u);
-    D[0] = 8 * V[2] - V[0] - 2 * V[1];
-    D[1] = -8 * V[0] - V[1] - 2 * V[2];
-    D[2] = 2 * V[0] - 8 * V[1] - V[2];
+    const int zr = (int)(kAluRing ? Z : 0u);
+    D[0] = 8 * V[2] - V[0] - 2 * V[1] + zr;
+    D[1] = -8 * V[0] - V[1] - 2 * V[2] + zr;
+    D[2] = 2 * V[0] - 8 * V[1] - V[2] + zr;
     constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        int acc = 0;
+        int acc = zr;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             const int q = (k >= i) ? Qc[k - i] : -Qc[k - i + 6];
@@ -218,7 +230,7 @@ GL_FN void layer_leave(const SplitState& c, const int (&z8)[3], u64 (&s)[WIDTH],
         o[L][0] += (u32)z8[L];
     }
 #pragma unroll
-    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], (u64)nxt[r]);
+    for (int r = 0; r < WIDTH; r++) s[r] = combine3(o[0][r], o[1][r], o[2][r], (u64)nxt[r], Z);
 }
 
 // v / 4 mod p:  v = 4 q + r,  r / 4 = ((4 - r) << 62) - ((4 - r) << 30) + 1  (r = 0 gives p, which the carry fold removes)
@@ -235,7 +247,7 @@ GL_FN void partial_head(SplitState& c, u64 cst, int (&z8)[3], u32 Z) {
     u32 E[3];
 #pragma unroll
     for (int L = 0; L < 3; L++) E[L] = (u32)(c.U[L][0] + c.V[L][0] + 2 * c.W[L][0] + (1 << 23));
-    const u64 e = div4(combine3(E[0], E[1], E[2], 0ull));
+    const u64 e = div4(combine3(E[0], E[1], E[2], 0ull, Z));
     const u64 z = sbox(add_const(e, cst));
 #pragma unroll
     for (int L = 0; L < 3; L++) {
