@@ -353,12 +353,13 @@ def run_b200(args):
             #   multiplier pipe: 2605 IMAD.WIDE (2 slots each: they issue at half the IMAD rate) + 6070 single-slot
             #                    (2033 IMAD shift-adds of the linear layers, 4037 IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL)
             #   ALU pipe:        9979 IADD3 / IADD3.X / LOP3 / SEL / LEA / SHF (one slot each)
-            # minus what folding the round constants into the limb packing removed after that capture (static SASS model,
-            # tools/sass_mix.py): 26 multiplier slots, 419 ALU slots, 445 instructions.
+            # minus what two later changes removed (static SASS model, tools/sass_mix.py): folding the round constants into the
+            # limb packing (26 multiplier slots, 419 ALU slots, 445 instructions) and the single signed fold of reduce128
+            # (472 multiplier slots, 472 ALU slots, 945 instructions: two per modular product).
             leaf_perms = N_local * ((k + 7) // 8)
-            slots_per_perm = 2 * 2605 + 6070 - 26
-            alu_slots_per_perm = 9979 - 419
-            instr_per_perm = 19352 - 445
+            slots_per_perm = 2 * 2605 + 6070 - 26 - 472
+            alu_slots_per_perm = 9979 - 419 - 472
+            instr_per_perm = 19352 - 445 - 945
             slot_rate = leaf_perms * slots_per_perm / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
             slot_peak = gips["imad"] * 1e9
             line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": slot_rate, "peak": slot_peak,

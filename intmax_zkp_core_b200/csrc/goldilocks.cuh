@@ -68,28 +68,29 @@ GL_FN u64 add_nc(u64 a, u64 c) {
 #else
 // ---- sm_100a versions: IADD3 carry chains written in PTX.  ptxas fuses `mul.wide.u32 + add.cc.u64` into
 // one IMAD.WIDE.U32 with a carry-out predicate, and `subc 0,0` turns a carry/borrow into a 0 / 0xFFFFFFFF
-// mask without compare+select (16 SASS instructions per modular product instead of 23).
+// mask without compare+select.  A modular product is 14 SASS instructions (23 as compiled from C): 7 for the 128-bit
+// product, 7 for the fold below.
 // (hi:lo) 128-bit -> u64 congruent mod p, NOT necessarily canonical.
 GL_FN u64 reduce128(u64 lo, u64 hi) {
+    // r = lo - x3 + x2 * EPS lies in (-2^32, 2^65): one signed wrap count k = carry - borrow in {-1, 0, 1}, one fold of k * 2^64 = k * EPS
     u64 r;
     asm("{\n\t"
-        ".reg .u32 l0, l1, x2, x3, b, m;\n\t"
+        ".reg .u32 l0, l1, x2, x3, k, ks;\n\t"
         ".reg .u64 t, u;\n\t"
         "mov.b64 {l0, l1}, %1;\n\t"
         "mov.b64 {x2, x3}, %2;\n\t"
         "sub.cc.u32 l0, l0, x3;\n\t"          // lo - x3      (2^96 == -1)
         "subc.cc.u32 l1, l1, 0;\n\t"
-        "subc.u32 b, 0, 0;\n\t"               // b = 0xFFFFFFFF on borrow
-        "sub.cc.u32 l0, l0, b;\n\t"           // borrow: -2^64 == -EPS
-        "subc.u32 l1, l1, 0;\n\t"
+        "subc.u32 k, 0, 0;\n\t"               // k = -borrow
         "mov.b64 t, {l0, l1};\n\t"
         "mul.wide.u32 u, x2, 0xFFFFFFFF;\n\t" // x2 * EPS     (2^64 == EPS)
         "add.cc.u64 t, t, u;\n\t"
-        "addc.u32 m, 0, 0;\n\t"               // m = carry (0/1); NB: subc after add.cc has the wrong polarity
+        "addc.u32 k, k, 0;\n\t"               // k += carry
+        "shr.s32 ks, k, 31;\n\t"
         "mov.b64 {l0, l1}, t;\n\t"
-        "sub.cc.u32 l0, l0, m;\n\t"           // + m * EPS == + m * 2^32 - m (cannot carry twice)
-        "subc.u32 l1, l1, 0;\n\t"
-        "add.u32 l1, l1, m;\n\t"
+        "sub.cc.u32 l0, l0, k;\n\t"           // + k * EPS == + k * 2^32 - k  (cannot wrap again)
+        "subc.u32 l1, l1, ks;\n\t"
+        "add.u32 l1, l1, k;\n\t"
         "mov.b64 %0, {l0, l1};\n\t"
         "}" : "=l"(r) : "l"(lo), "l"(hi));
     return r;
