@@ -337,7 +337,7 @@ def run_b200(args):
             line["e2e_strict"] = e2e_strict
         if world == 1 and n_log == N_LOG and k == K:
             # dram__bytes_read.sum + dram__bytes_write.sum of the leaf hash at this size, ncu --set full capture
-            # profiles/r1c_leaf_kernel_ncu_details.txt (9.08 GB + 0.27 GB)
+            # profiles/r1e_leaf_kernel_ncu_details.txt (9.08 GB + 0.27 GB)
             line["roofline"]["traffic"] = 9.36e9
         if world == 1:
             gips = {}
@@ -349,17 +349,14 @@ def run_b200(args):
             line["int_pipe"] = {"unit": "giga thread-instructions/s (dependent chains, all SMs)", **gips}
             # second roof of SURVEY.md 8d: the leaf hash against the measured issue rate of the integer-multiply (fmaheavy) pipe,
             # the busier of the two integer pipes.  Dynamic instruction mix per permutation of the shipped kernel (ncu source
-            # counters of profiles/r1c_leaf_kernel_ncu_details.txt, 19 352 warp-instructions per warp-permutation):
-            #   multiplier pipe: 2605 IMAD.WIDE (2 slots each: they issue at half the IMAD rate) + 6070 single-slot
-            #                    (2033 IMAD shift-adds of the linear layers, 4037 IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL)
-            #   ALU pipe:        9979 IADD3 / IADD3.X / LOP3 / SEL / LEA / SHF (one slot each)
-            # minus what two later changes removed (static SASS model, tools/sass_mix.py): folding the round constants into the
-            # limb packing (26 multiplier slots, 419 ALU slots, 445 instructions) and the single signed fold of reduce128
-            # (472 multiplier slots, 472 ALU slots, 945 instructions: two per modular product).
+            # counters, profiles/r1e_leaf_instruction_mix.txt: 17 964 warp-instructions per warp-permutation):
+            #   multiplier pipe: 2605 IMAD.WIDE (2 slots each: they issue at half the IMAD rate) + 5574 single-slot
+            #                    (2033 IMAD shift-adds of the linear layers, the rest IMAD.IADD / IMAD.X / IMAD.MOV / IMAD.SHL)
+            #   ALU pipe:        9217 IADD3 / IADD3.X / LOP3 / SEL / LEA / SHF (one slot each)
             leaf_perms = N_local * ((k + 7) // 8)
-            slots_per_perm = 2 * 2605 + 6070 - 26 - 472
-            alu_slots_per_perm = 9979 - 419 - 472
-            instr_per_perm = 19352 - 445 - 945
+            slots_per_perm = 2 * 2605 + 5574
+            alu_slots_per_perm = 9217
+            instr_per_perm = 17964
             slot_rate = leaf_perms * slots_per_perm / (leaf_ms_avg * 1e-3) if leaf_ms_avg else 0.0
             slot_peak = gips["imad"] * 1e9
             line["roofline"]["int"] = {"bound": "integer multiply pipe (fmaheavy)", "achieved": slot_rate, "peak": slot_peak,
@@ -370,7 +367,7 @@ def run_b200(args):
                                        "instructions_per_permutation": instr_per_perm,
                                        "issue_frac": (leaf_perms * instr_per_perm / (leaf_ms_avg * 1e-3) / (2 * gips["imad"] * 1e9)) if leaf_ms_avg else 0.0,
                                        "permutations_per_launch": leaf_perms,
-                                       "ncu": {"pipe_fmaheavy_busy": 0.827, "pipe_alu_busy": 0.689, "issue_active": 0.687}}
+                                       "ncu": {"pipe_fmaheavy_busy": 0.843, "pipe_alu_busy": 0.666, "issue_active": 0.679}}
             if not os.environ.get("B200ZKP_SKIP_CPU"):
                 from oracle import oracle as O
                 O.build()
