@@ -58,8 +58,16 @@ GL_FN void sponge_leaf(const u64* __restrict__ p, u64 col_stride, u32 leaf_len, 
 #pragma unroll
         for (int i = 0; i < poseidon::RATE; i++)
             if (c + i < leaf_len) s[i] = p[(u64)(c + i) * col_stride];
+#ifdef B200ZKP_LEAN
+        poseidon::permute_nc(s);        // the state stays inside the sponge: only the digest is canonicalised, below
+#else
         poseidon::permute(s);
+#endif
     }
+#ifdef B200ZKP_LEAN
+#pragma unroll
+    for (int i = 0; i < 4; i++) s[i] = gl::canon(s[i]);
+#endif
 #else
     u64 nx[poseidon::RATE];
 #pragma unroll
@@ -120,7 +128,7 @@ merkle_level_kernel(u64* __restrict__ digests, u64* __restrict__ cap, TreeShape 
     ulonglong2 a = src[0], b = src[1], c = src[2], d = src[3];
     s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y; s[4] = c.x; s[5] = c.y; s[6] = d.x; s[7] = d.y;
     s[8] = s[9] = s[10] = s[11] = 0;
-    poseidon::permute(s);
+    poseidon::permute_digest(s);
     if (par_log == 0) store_digest(cap + 4 * subtree, s);
     else store_digest(digests + 4 * node_slot(shape, subtree, layer + 1, m), s);
 }
@@ -260,7 +268,7 @@ two_to_one_kernel(const u64* __restrict__ l, const u64* __restrict__ r, u64* __r
     u64 s[poseidon::WIDTH];
 #pragma unroll
     for (int i = 0; i < 4; i++) { s[i] = l[4 * g + i]; s[4 + i] = r[4 * g + i]; s[8 + i] = 0; }
-    poseidon::permute(s);
+    poseidon::permute_digest(s);
     store_digest(out + 4 * g, s);
 }
 

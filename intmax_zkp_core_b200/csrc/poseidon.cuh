@@ -121,6 +121,9 @@ static constexpr bool kAluSp = B200ZKP_MDS_ALU_MASK & 1, kAluUv = B200ZKP_MDS_AL
 // planes of U[3], V[3], W[6] (signed 32-bit; tools/poseidon_crt_model.py bounds every intermediate by interval arithmetic).
 struct SplitState {
     int U[3][3], V[3][3], W[3][6];
+#ifdef B200ZKP_LEAN
+    int X0[3];          // word 0 of the layer's output, limbs + 2^30 (see partial_head)
+#endif
 };
 
 GL_FN u32 limb_of(u64 x, int L) {
@@ -194,6 +197,9 @@ GL_FN void layer_stay(SplitState& c, const int (&z8)[3], u32 Z) {
     for (int L = 0; L < 3; L++) {
         int Cq[3], D[3], B[6];
         ring_products(c.U[L], c.V[L], c.W[L], Cq, D, B, Z);
+#ifdef B200ZKP_LEAN
+        c.X0[L] = 16 * Cq[0] + D[0] + B[0] + z8[L] + (1 << 30);      // = out[0] of layer_leave: no division by 4 next round
+#endif
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             c.U[L][k] = 64 * Cq[k] + (k == 0 ? z8[L] : 0);
@@ -244,15 +250,23 @@ GL_FN u64 div4(u64 v) {
 // difference is put back into the three components; cst = round constant - 2^21 (1 + 2^22 + 2^43) (SPLIT_ADD)
 GL_FN void partial_head(SplitState& c, u64 cst, int (&z8)[3], u32 Z) {
     const int zi = (int)(kAluInj ? Z : 0u);
+#ifdef B200ZKP_LEAN
+    // tuning build: word 0 comes packed from the previous layer's ring products (layer_stay: X0), cst = plain round constant
+    constexpr u64 X0_UNBIAS = 0xffeffdfec0000201ull;      // -(2^30 (1 + 2^22 + 2^43)) mod p
+    const u64 e = combine3((u32)c.X0[0], (u32)c.X0[1], (u32)c.X0[2], X0_UNBIAS, Z);
+    constexpr int kDBias = 0;
+#else
     u32 E[3];
 #pragma unroll
     for (int L = 0; L < 3; L++) E[L] = (u32)(c.U[L][0] + c.V[L][0] + 2 * c.W[L][0] + (1 << 23));
     const u64 e = div4(combine3(E[0], E[1], E[2], 0ull, Z));
+    constexpr int kDBias = 1 << 21;
+#endif
     const u64 z = sbox(add_const(e, cst));
 #pragma unroll
     for (int L = 0; L < 3; L++) {
         const int zl = (int)limb_of(z, L);
-        const int d = zl - (int)limb_of(e, L) + (1 << 21);
+        const int d = zl - (int)limb_of(e, L) + kDBias;
         c.U[L][0] += d + zi;
         c.V[L][0] += d + zi;
         c.W[L][0] += d + zi;
@@ -266,12 +280,12 @@ GL_FN u64 mul_add_nc(u64 w, u64 x, u64 s) {
     return gl::reduce128((u64)p, (u64)(p >> 64));
 }
 
-// In-place permutation; input words arbitrary u64, output canonical.
+// In-place permutation; input words arbitrary u64, output words arbitrary u64 (congruent; `permute` canonicalises).
 // One loop over all 30 rounds with a single copy of every block (S-box row, butterflies, ring products, packing): the
 // whole permutation stays resident in the instruction cache (a two-loop form of 59 KB ran at a 67 % hit rate with "no
 // instruction" as the top stall).  The round kind is warp-uniform.  Rounds 3..24 leave the state in the split basis
 // (the next round is partial), every other round packs it back into words for the twelve S-boxes that follow.
-GL_FN void permute(u64 (&s)[WIDTH]) {
+GL_FN void permute_nc(u64 (&s)[WIDTH]) {
     using namespace poseidon_tables;
 #pragma unroll
     for (int i = 0; i < WIDTH; i++) s[i] = add_const(s[i], SPLIT_ADD[i]);
@@ -282,6 +296,9 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
         for (int k = 0; k < 3; k++) { c.U[L][k] = 0; c.V[L][k] = 0; }
 #pragma unroll
         for (int k = 0; k < 6; k++) c.W[L][k] = 0;
+#ifdef B200ZKP_LEAN
+        c.X0[L] = 0;
+#endif
     }
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
@@ -298,7 +315,11 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
                 for (int k = 0; k < 3; k++) normalise(c.U[0][k], c.U[1][k], c.U[2][k], Z);
             }
         } else {
+#ifdef B200ZKP_LEAN
+            partial_head(c, ROUND_ADD[r * WIDTH], z8, Z);
+#else
             partial_head(c, SPLIT_ADD[r * WIDTH], z8, Z);
+#endif
         }
         if (stay) {
             layer_stay(c, z8, Z);
@@ -307,8 +328,24 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
             layer_leave(c, z8, s, (full ? 0u : (1u << 30)) + Z, Z, &SPLIT_ADD[(r + 1) * WIDTH]);
         }
     }
+}
+
+// In-place permutation; input words arbitrary u64, output canonical.
+GL_FN void permute(u64 (&s)[WIDTH]) {
+    permute_nc(s);
 #pragma unroll
     for (int i = 0; i < WIDTH; i++) s[i] = gl::canon(s[i]);
+}
+
+// permutation whose caller keeps only the digest words 0..3 (compressions, the last permutation of a sponge)
+GL_FN void permute_digest(u64 (&s)[WIDTH]) {
+#ifdef B200ZKP_LEAN
+    permute_nc(s);
+#pragma unroll
+    for (int i = 0; i < 4; i++) s[i] = gl::canon(s[i]);
+#else
+    permute(s);
+#endif
 }
 
 }  // namespace poseidon

@@ -234,8 +234,10 @@ def permute_model(state):
     return s
 
 
-def bounds():
-    """interval analysis of the limb pipeline: fixed point of the normalised-limb ranges over the rounds"""
+def bounds(lean=False):
+    """interval analysis of the limb pipeline: fixed point of the normalised-limb ranges over the rounds.
+    lean: the B200ZKP_LEAN tuning build (word 0 packed from the previous layer's ring products: the injected
+    difference carries no 2^21 offset, and X0 = leaving limb of word 0 + 2^30 must fit a signed 32-bit register)"""
     full = [Iv(0, M22), Iv(0, M21), Iv(0, M21)]
     # entry: time-domain limbs of arbitrary u64 words
     st = []
@@ -268,7 +270,7 @@ def bounds():
         report["4 x0 + bias"] = E
         assert all(e.lo >= 0 for e in E)
         for L in range(3):
-            d = full[L] - full[L] + (BIAS_X >> 2)
+            d = full[L] - full[L] + (0 if lean else (BIAS_X >> 2))
             for j in range(3):
                 st[L][j][0] = st[L][j][0] + d
         report["word 0 after injection"] = [st[L][0][0] for L in range(3)]
@@ -280,6 +282,8 @@ def bounds():
         report["leaving limb"] = o
         for L in range(3):
             assert o[L].lo + (1 << BIAS_OUT_LOG) >= 0 and o[L].hi + (1 << BIAS_OUT_LOG) < (1 << 32), o
+            if lean:
+                assert o[L].hi + (1 << BIAS_OUT_LOG) < (1 << 31), o      # X0 is kept in a signed register
         st = [mult_stay(*st[L], full[L] * 8) for L in range(3)]
         m = [st[L][0][0] for L in range(3)]
         for L in range(3):
@@ -301,5 +305,7 @@ def self_check(trials=6):
 if __name__ == "__main__":
     for k, v in bounds().items():
         print(f"{k:28s} {v}")
+    for k, v in bounds(lean=True).items():
+        print(f"lean: {k:22s} {v}")
     self_check()
     print("split-basis partial rounds == naive permutation on", 9, "vectors")
