@@ -47,6 +47,10 @@ extern "C" {
     pub fn b200zkp_fri_query(f: *mut b200zkp_fri, layer: u32, idx: *const u64, n_idx: u64, evals: *mut u64, siblings: *mut u64) -> c_int;
     pub fn b200zkp_pow_grind(ctx: *mut b200zkp_ctx, state: *const u64, witness_pos: u32, response_pos: u32,
         min_leading_zeros: u32, max_candidates: u64, witness: *mut u64) -> c_int;
+    // row N1c: PolynomialValues::coset_ifft(shift) in place, k columns of 2^n_log values
+    pub fn b200zkp_coset_intt(ctx: *mut b200zkp_ctx, data: *mut u64, n_log: u32, k: u32, shift: u64) -> c_int;
+    pub fn b200zkp_dev_coset_intt(ctx: *mut b200zkp_ctx, values: *const u64, in_stride: u64, coeffs: *mut u64, out_stride: u64,
+        scratch: *mut u64, n_log: u32, k: u32, shift: u64) -> c_int;
     // row N1a: prover.rs wires_permutation_partial_products_and_zs for every challenge, columns in committed order
     pub fn b200zkp_partial_products_and_zs(ctx: *mut b200zkp_ctx, wires: *const u64, sigmas: *const u64, n_log: u32,
         num_routed: u32, degree: u32, k_is: *const u64, betas: *const u64, gammas: *const u64, num_challenges: u32,
