@@ -58,4 +58,32 @@ inline std::vector<std::vector<std::vector<F>>> all_wires_permutation_partial_pr
     return res;
 }
 
+// PolynomialValues::coset_ifft(shift) over k vectors of n values (plonky2_field polynomial/mod.rs), row N1c
+inline std::vector<std::vector<F>> coset_ifft_batch(const Context& c, const std::vector<std::vector<F>>& values, F shift) {
+    if (values.empty()) return {};
+    const size_t k = values.size(), n = values[0].size(), n_log = log2_strict(n);
+    std::vector<F> flat(k * n);
+    for (size_t j = 0; j < k; j++) {
+        if (values[j].size() != n) throw std::invalid_argument("columns of different lengths");
+        std::copy(values[j].begin(), values[j].end(), flat.begin() + j * n);
+    }
+    c.check(b200zkp_coset_intt(c.raw(), flat.data(), (uint32_t)n_log, (uint32_t)k, shift));
+    std::vector<std::vector<F>> out(k);
+    for (size_t j = 0; j < k; j++) out[j].assign(flat.begin() + j * n, flat.begin() + (j + 1) * n);
+    return out;
+}
+
+// tail of compute_quotient_polys + the chunking in prove(): one vector of n << q quotient values per challenge (coset 7 <w>,
+// natural order) -> the degree-n coefficient chunks PolynomialBatch::from_coeffs takes
+inline std::vector<std::vector<F>> quotient_poly_chunks(const Context& c, const std::vector<std::vector<F>>& quotient_values,
+                                                        size_t degree) {
+    auto coeffs = coset_ifft_batch(c, quotient_values, 7);
+    std::vector<std::vector<F>> chunks;
+    for (auto& p : coeffs) {
+        if (degree == 0 || p.size() % degree) throw std::invalid_argument("quotient length must be a multiple of the degree");
+        for (size_t o = 0; o < p.size(); o += degree) chunks.emplace_back(p.begin() + o, p.begin() + o + degree);
+    }
+    return chunks;
+}
+
 }  // namespace plonky2
