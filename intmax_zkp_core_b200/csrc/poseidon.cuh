@@ -34,11 +34,44 @@ using gl::u64;
 static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 
+// 64 x 64 -> 128 product of the S-box.  B200ZKP_SBOX_ALU: the carries of the middle column are consumed by IADD3.X on the ALU
+// pipe (the compiler's own 128-bit product spends an IMAD.X, an IMAD.MOV and an accumulating IMAD.WIDE.X on them): same seven
+// instructions, three fewer slots on the multiplier pipe, which is the busier one in the hash kernels (not in the transforms,
+// which keep gl::mul_nc).
+GL_FN u64 mul_s(u64 a, u64 b) {
+#if defined(B200ZKP_SBOX_ALU) && !defined(B200ZKP_HOST_EMU)
+    u64 lo, hi;
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, p0, p1, m0, m1, h0, h1;\n\t"
+        ".reg .u64 p, m, t, h;\n\t"
+        "mov.b64 {a0, a1}, %2;\n\t"
+        "mov.b64 {b0, b1}, %3;\n\t"
+        "mul.wide.u32 p, a0, b0;\n\t"
+        "mul.wide.u32 h, a1, b1;\n\t"
+        "mov.b64 {h0, h1}, h;\n\t"
+        "mul.wide.u32 m, a0, b1;\n\t"
+        "mul.wide.u32 t, a1, b0;\n\t"
+        "add.cc.u64 m, m, t;\n\t"             // middle column a0 b1 + a1 b0: 65 bits
+        "addc.u32 h1, h1, 0;\n\t"             // its carry has weight 2^96
+        "mov.b64 {p0, p1}, p;\n\t"
+        "mov.b64 {m0, m1}, m;\n\t"
+        "add.cc.u32 p1, p1, m0;\n\t"
+        "addc.cc.u32 h0, h0, m1;\n\t"
+        "addc.u32 h1, h1, 0;\n\t"
+        "mov.b64 %0, {p0, p1};\n\t"
+        "mov.b64 %1, {h0, h1};\n\t"
+        "}" : "=l"(lo), "=l"(hi) : "l"(a), "l"(b));
+    return gl::reduce128(lo, hi);
+#else
+    return gl::mul_nc(a, b);
+#endif
+}
+
 GL_FN u64 sbox(u64 x) {
-    u64 x2 = gl::sqr_nc(x);
-    u64 x4 = gl::sqr_nc(x2);
-    u64 x3 = gl::mul_nc(x2, x);
-    return gl::mul_nc(x3, x4);
+    u64 x2 = mul_s(x, x);
+    u64 x4 = mul_s(x2, x2);
+    u64 x3 = mul_s(x2, x);
+    return mul_s(x3, x4);
 }
 
 // a arbitrary u64, c canonical constant -> arbitrary u64 congruent to a + c
