@@ -318,6 +318,75 @@ GL_FN u64 mul_add_nc(u64 w, u64 x, u64 s) {
 // whole permutation stays resident in the instruction cache (a two-loop form of 59 KB ran at a 67 % hit rate with "no
 // instruction" as the top stall).  The round kind is warp-uniform.  Rounds 3..24 leave the state in the split basis
 // (the next round is partial), every other round packs it back into words for the twelve S-boxes that follow.
+#if defined(B200ZKP_ALIAS_STATE) && !defined(B200ZKP_LEAN)
+// B200ZKP_ALIAS_STATE (tuning build): the loop carries one image of 36 registers that holds either the twelve words or the
+// split-basis limbs, instead of both forms (60 registers live across the back edge): 204 -> 48 bytes of spills at a
+// 64-register cap (256 x 4 CTAs), so the CTA shapes with more warps and the other tuning builds get room.
+GL_FN void st_load(const u32 (&st)[36], SplitState& c) {
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { c.U[L][k] = (int)st[L * 12 + k]; c.V[L][k] = (int)st[L * 12 + 3 + k]; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) c.W[L][k] = (int)st[L * 12 + 6 + k];
+    }
+}
+GL_FN void st_store(u32 (&st)[36], const SplitState& c) {
+#pragma unroll
+    for (int L = 0; L < 3; L++) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { st[L * 12 + k] = (u32)c.U[L][k]; st[L * 12 + 3 + k] = (u32)c.V[L][k]; }
+#pragma unroll
+        for (int k = 0; k < 6; k++) st[L * 12 + 6 + k] = (u32)c.W[L][k];
+    }
+}
+
+GL_FN void permute_nc(u64 (&s)[WIDTH]) {
+    using namespace poseidon_tables;
+    // one register file image for both forms of the state: words (24 registers) or split-basis limbs (36)
+    u32 st[36];
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) {
+        const u64 v = add_const(s[i], SPLIT_ADD[i]);
+        st[2 * i] = (u32)v; st[2 * i + 1] = (u32)(v >> 32);
+    }
+#pragma unroll
+    for (int i = 24; i < 36; i++) st[i] = 0;
+#pragma unroll 1
+    for (int r = 0; r < 30; r++) {
+        const bool full = (r < 4) || (r >= 26);
+        const bool stay = (r >= 3) && (r < 25);
+        const u32 Z = OPAQUE_ZERO;
+        int z8[3];
+        SplitState c;
+        if (full) {
+            u64 w[WIDTH];
+#pragma unroll
+            for (int i = 0; i < WIDTH; i++) w[i] = sbox(((u64)st[2 * i + 1] << 32) | st[2 * i]);
+            split_forward(w, c, z8, Z);
+            if (stay) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) normalise(c.U[0][k], c.U[1][k], c.U[2][k], Z);
+            }
+        } else {
+            st_load(st, c);
+            partial_head(c, SPLIT_ADD[r * WIDTH], z8, Z);
+        }
+        if (stay) {
+            layer_stay(c, z8, Z);
+            st_store(st, c);
+        } else {
+            u64 w[WIDTH];
+            layer_leave(c, z8, w, (full ? 0u : (1u << 30)) + Z, Z, &SPLIT_ADD[(r + 1) * WIDTH]);
+#pragma unroll
+            for (int i = 0; i < WIDTH; i++) { st[2 * i] = (u32)w[i]; st[2 * i + 1] = (u32)(w[i] >> 32); }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < WIDTH; i++) s[i] = ((u64)st[2 * i + 1] << 32) | st[2 * i];
+}
+
+#else
 GL_FN void permute_nc(u64 (&s)[WIDTH]) {
     using namespace poseidon_tables;
 #pragma unroll
@@ -362,6 +431,8 @@ GL_FN void permute_nc(u64 (&s)[WIDTH]) {
         }
     }
 }
+
+#endif
 
 // In-place permutation; input words arbitrary u64, output canonical.
 GL_FN void permute(u64 (&s)[WIDTH]) {
