@@ -97,7 +97,7 @@ struct FriProof {
 // PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing).  mul_by_x: the pinned 2022 revision
 // multiplies final_poly by X (plonky2 PR 436); later revisions pad the quotient instead.
 inline FriProof prove_openings(const FriInstanceInfo& instance, const std::vector<const PolynomialBatch*>& oracles,
-                               Challenger& challenger, const FriParams& fri_params, bool mul_by_x = true) {
+                               Challenger& challenger, const FriParams& fri_params, bool mul_by_x) {
     if (oracles.empty()) throw std::invalid_argument("no oracle");
     const Context& c = oracles[0]->context();
     const FriConfig& cfg = fri_params.config;

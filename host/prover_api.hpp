@@ -75,13 +75,20 @@ inline std::vector<std::vector<F>> coset_ifft_batch(const Context& c, const std:
 
 // tail of compute_quotient_polys + the chunking in prove(): one vector of n << q quotient values per challenge (coset 7 <w>,
 // natural order) -> the degree-n coefficient chunks PolynomialBatch::from_coeffs takes
+// quotient_degree_factor (CommonCircuitData; need not be a power of two): prove() runs
+// `quotient_poly.trim_to_len(quotient_degree_factor * degree)`, which panics when a dropped coefficient is non-zero (the
+// witness does not satisfy the circuit), and commits exactly quotient_degree_factor chunks per challenge
 inline std::vector<std::vector<F>> quotient_poly_chunks(const Context& c, const std::vector<std::vector<F>>& quotient_values,
-                                                        size_t degree) {
+                                                        size_t degree, size_t quotient_degree_factor) {
     auto coeffs = coset_ifft_batch(c, quotient_values, 7);
     std::vector<std::vector<F>> chunks;
     for (auto& p : coeffs) {
         if (degree == 0 || p.size() % degree) throw std::invalid_argument("quotient length must be a multiple of the degree");
-        for (size_t o = 0; o < p.size(); o += degree) chunks.emplace_back(p.begin() + o, p.begin() + o + degree);
+        if (quotient_degree_factor == 0 || quotient_degree_factor * degree > p.size())
+            throw std::invalid_argument("quotient_degree_factor * degree exceeds the quotient length");
+        for (size_t i = quotient_degree_factor * degree; i < p.size(); i++)
+            if (p[i] != 0) throw std::runtime_error("Quotient has failed, the vanishing polynomial is not divisible by Z_H");
+        for (size_t o = 0; o < quotient_degree_factor * degree; o += degree) chunks.emplace_back(p.begin() + o, p.begin() + o + degree);
     }
     return chunks;
 }

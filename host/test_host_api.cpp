@@ -74,7 +74,7 @@ int main() {
         FriInstanceInfo inst;
         inst.batches.push_back({Ext{123456789ull, 987654321ull}, {{0, 0}, {0, 1}, {0, 2}, {1, 0}, {1, 1}}});
         inst.batches.push_back({Ext{555ull, 777ull}, {{1, 0}, {1, 1}}});
-        FriProof proof = prove_openings(inst, {&o0, &o1}, ch, params);
+        FriProof proof = prove_openings(inst, {&o0, &o1}, ch, params, /*mul_by_x=*/true);
         CHECK(proof.commit_phase_merkle_caps.size() == 2 && proof.final_poly.size() == 4 && proof.query_round_proofs.size() == 5);
         uint64_t d = 0xcbf29ce484222325ull;
         auto mix = [&](uint64_t w) { d = (d ^ w) * 0x100000001b3ull; };

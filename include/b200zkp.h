@@ -60,6 +60,12 @@ int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out);
 void b200zkp_ctx_destroy(b200zkp_ctx* ctx);
 const char* b200zkp_last_error(const b200zkp_ctx* ctx);
 int b200zkp_ctx_synchronize(b200zkp_ctx* ctx);
+/* freed device buffers are cached per ctx for reuse by the next request of the same size (a prover commits the same
+ * shapes over and over).  The cache holds at most `bytes` (default: 1/8 of the device memory, 22 GB on a B200 — one
+ * 2^20 x 135 batch); buffers that do not fit go straight back to the driver.  b200zkp_ctx_trim synchronises the stream
+ * and returns every cached buffer to the driver. */
+int b200zkp_ctx_set_pool_limit(b200zkp_ctx* ctx, uint64_t bytes);
+int b200zkp_ctx_trim(b200zkp_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx);
 /* per-stage device timing (CUDA events on the ctx stream around each stage; off by default).
@@ -224,7 +230,8 @@ int b200zkp_dev_commit(b200zkp_ctx* ctx, const uint64_t* in, int is_coeffs, uint
                        uint64_t* lde, uint64_t* digests, uint64_t* cap);
 /* MerkleTree::get + MerkleTree::prove on caller-owned device buffers (e.g. one rank's leaf shard): element (row, c) at
  * lde[c*col_stride + row]; idx_dev n_idx leaf indices on the device; rows_dev n_idx*row_len, siblings_dev
- * n_idx*(log2 n_leaves - cap_height)*4, either may be NULL */
+ * n_idx*(log2 n_leaves - cap_height)*4, either may be NULL.  The indices live on the device and cannot be validated by
+ * the host: each is reduced modulo n_leaves (never an out-of-range read) */
 int b200zkp_dev_gather(b200zkp_ctx* ctx, const uint64_t* lde, uint64_t col_stride, uint32_t row_len,
                        const uint64_t* digests, uint64_t n_leaves, uint32_t cap_height, const uint64_t* idx_dev,
                        uint64_t n_idx, uint64_t* rows_dev, uint64_t* siblings_dev);
@@ -251,21 +258,6 @@ int b200zkp_dev_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires_
                                         uint32_t num_routed, uint32_t degree, const uint64_t* k_is, const uint64_t* betas,
                                         const uint64_t* gammas, uint32_t num_challenges, uint64_t* out_dev,
                                         uint64_t out_col_stride);
-/* device field primitives, element-wise over `count` pairs (test probe for the carry / borrow paths):
- * op 0 mul, 1 add, 2 sub, 3 reduce128(lo = a, hi = b), 4 a + canon(b) lazily,
- * 5 limb recombination O0 + O1*2^22 + O2*2^43 + rc with O0 = a[0:31], O1 = a[32:63], O2 = b[0:31], rc = canon(b >> 1),
- * 6 a^7, 7 (a ^ b) + a * b; every result canonical */
-int b200zkp_field_op(b200zkp_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t count, uint64_t* out);
-/* integer-pipe micro-benchmark: runs `iters` dependent-chain rounds of the chosen
- * instruction mix on every SM and returns giga thread-instructions per second in *out_gips.
- * kind: 0 IMAD.WIDE.U32, 1 IADD3, 2 IMAD (32-bit), 3 alternating IMAD.WIDE/LOP3, 4 LOP3, 5 IMAD.HI.U32,
- *       6 alternating IMAD/LOP3, 7 IADD3 + IADD3.X carry pairs, 8 IMAD.WIDE.U32 without accumulator,
- *       9 DFMA, 10 alternating DFMA/IMAD.WIDE.U32, 11 alternating DFMA/IMAD, 12 alternating DFMA/LOP3,
- *       13 alternating IMAD.WIDE.U32/IMAD, 14 alternating IMAD.WIDE.U32 (no accumulator)/LOP3, 15 IMAD.WIDE.U32 : LOP3 = 1 : 3,
- *       16 three-input IADD3 with a uniform operand, 17 alternating three-input IADD3/IMAD,
- *       18 IMAD.WIDE : IMAD : LOP3 : IADD3 = 1 : 2 : 2 : 3, 19 IMAD.WIDE : LOP3 : IMAD = 1 : 2 : 1 */
-int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters, double* out_gips);
-
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200ZKP_LIB") or os.path.join(_HERE, "libb200zkp.so")
 SRC = os.path.join(_HERE, "csrc", "b200zkp.cu")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "b200zkp.h")
+TEST_HEADER = os.path.join(os.path.dirname(_HERE), "include", "b200zkp_test.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -34,7 +35,7 @@ class B200ZkpError(RuntimeError):
 
 def _sources():
     d = os.path.join(_HERE, "csrc")
-    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [HEADER]
+    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [HEADER, TEST_HEADER]
 
 
 def needs_build() -> bool:
@@ -83,6 +84,8 @@ _SIGS = {
     "b200zkp_last_error": (C.c_char_p, [C.c_void_p]),
     "b200zkp_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "b200zkp_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "b200zkp_ctx_trim": (C.c_int, [C.c_void_p]),
+    "b200zkp_ctx_set_pool_limit": (C.c_int, [C.c_void_p, C.c_uint64]),
     "b200zkp_ctx_set_overlap": (C.c_int, [C.c_void_p, C.c_int]),
     "b200zkp_ctx_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "b200zkp_ctx_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), u32p]),

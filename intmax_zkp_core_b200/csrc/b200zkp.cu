@@ -1,6 +1,7 @@
 // C ABI implementation (include/b200zkp.h): contexts, twiddle caches, pass scheduling, handles.
 // Product code: no CPU fallback, nothing from oracle/ is included, linked or executed here.
 #include "../../include/b200zkp.h"
+#include "../../include/b200zkp_test.h"
 
 #include <cuda_runtime.h>
 
@@ -49,7 +50,9 @@ struct b200zkp_ctx {
     std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
     std::map<std::pair<u64, u32>, u64*> power_scale;    // (shift, bits) -> shift^i, i < 2^bits (FRI layer cosets)
     u64* round_add = nullptr;                           // poseidon_tables::ROUND_ADD in global memory (latency-form kernels)
-    std::multimap<size_t, void*> pool;                  // cached device allocations
+    std::multimap<size_t, void*> pool;                  // cached device allocations (dev_release), at most pool_max_bytes
+    size_t pool_bytes = 0;
+    size_t pool_max_bytes = (size_t)16 << 30;         // reset to 1/8 of the device memory in ctx_create
     std::vector<void*> table_allocs;
     // second, higher-priority stream: coset transforms run here while finished blocks are hashed on `stream`
     cudaStream_t stream2 = nullptr;
@@ -116,17 +119,22 @@ struct b200zkp_tree {
 #define BAD(ctx, msg) do { (ctx)->err = (msg); return B200ZKP_ERR_BAD_ARG; } while (0)
 #define LAUNCH_CHECK(ctx) do { (ctx)->launches++; CUDA_TRY(ctx, cudaGetLastError()); } while (0)
 
+static void pool_drop(b200zkp_ctx* ctx) {
+    for (auto& kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
+}
+
 static int dev_alloc(b200zkp_ctx* ctx, size_t bytes, void** out) {
     *out = nullptr;
     if (bytes == 0) return 0;
     auto it = ctx->pool.find(bytes);
-    if (it != ctx->pool.end()) { *out = it->second; ctx->pool.erase(it); return 0; }
+    if (it != ctx->pool.end()) { *out = it->second; ctx->pool_bytes -= it->first; ctx->pool.erase(it); return 0; }
     cudaError_t e = cudaMalloc(out, bytes);
     if (e == cudaErrorMemoryAllocation) {
         // drop the cache and retry once
         (void)cudaGetLastError();
-        for (auto& kv : ctx->pool) cudaFree(kv.second);
-        ctx->pool.clear();
+        pool_drop(ctx);
         e = cudaMalloc(out, bytes);
     }
     if (e != cudaSuccess) {
@@ -139,9 +147,14 @@ static int dev_alloc(b200zkp_ctx* ctx, size_t bytes, void** out) {
 static void dev_release(b200zkp_ctx* ctx, void* p, size_t bytes) {
     if (!p) return;
     // cached for the next request of the same size (stream order makes reuse on the same ctx safe); an opening proof
-    // cycles through ~40 distinct sizes, so the cap is generous — dev_alloc drops the whole cache when cudaMalloc fails
-    if (ctx->pool.size() < 256) ctx->pool.emplace(bytes, p);
-    else cudaFree(p);
+    // cycles through ~40 distinct sizes.  The cache is capped by bytes so that a freed 2^20 x 135 batch (10.7 GB) goes back
+    // to the driver instead of starving torch or a second ctx on the same GPU; b200zkp_ctx_trim empties it on request
+    if (ctx->pool.size() < 256 && ctx->pool_bytes + bytes <= ctx->pool_max_bytes) {
+        ctx->pool.emplace(bytes, p);
+        ctx->pool_bytes += bytes;
+    } else {
+        cudaFree(p);    // (cudaFree synchronises the device: pending work on the buffer has finished when it returns)
+    }
 }
 
 static int upload(b200zkp_ctx* ctx, const std::vector<u64>& h, u64** d) {
@@ -353,6 +366,9 @@ extern "C" int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out) {
         }
         ctx->own_stream = true;
     }
+    size_t mem_free = 0, mem_total = 0;
+    if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total) ctx->pool_max_bytes = mem_total / 8;
+    else (void)cudaGetLastError();
     int rc = ctx_init_tables(ctx);
     if (rc != 0) { b200zkp_ctx_destroy(ctx); return rc; }
     *out = ctx;
@@ -363,7 +379,7 @@ extern "C" void b200zkp_ctx_destroy(b200zkp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->pool) cudaFree(kv.second);
+    pool_drop(ctx);
     for (void* p : ctx->table_allocs) cudaFree(p);
     for (auto& sp : ctx->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
@@ -378,7 +394,27 @@ extern "C" uint64_t b200zkp_ctx_launch_count(const b200zkp_ctx* ctx) { return ct
 
 extern "C" int b200zkp_ctx_synchronize(b200zkp_ctx* ctx) {
     if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);      // ctx->stream is swapped temporarily by the two-stream pipelines: read it under the lock
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int b200zkp_ctx_set_pool_limit(b200zkp_ctx* ctx, uint64_t bytes) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    ctx->pool_max_bytes = (size_t)bytes;
+    if (ctx->pool_bytes > ctx->pool_max_bytes) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        pool_drop(ctx);
+    }
+    return 0;
+}
+
+extern "C" int b200zkp_ctx_trim(b200zkp_ctx* ctx) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    pool_drop(ctx);
     return 0;
 }
 
@@ -921,14 +957,14 @@ static int gather_locked(b200zkp_ctx* ctx, const u64* lde, u64 N, u32 row, const
     if ((rc = h2d(ctx, d_idx, idx, idx_b))) return done(rc);
     if (rows_b) {
         u64 cnt = n_idx * row;
-        merkle::gather_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(lde, N, row, (const u64*)d_idx, n_idx, (u64*)d_rows);
+        merkle::gather_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(lde, N, row, (const u64*)d_idx, n_idx, (u64*)d_rows, N - 1);
         ctx->launches++;
         if ((rc = d2h(ctx, rows, d_rows, rows_b))) return done(rc);
     }
     if (sib_b) {
         merkle::TreeShape shape; shape.sub_log = sub_log; shape.sub_digests = 2 * (((u64)1 << sub_log) - 1);
         u64 cnt = n_idx * sub_log;
-        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(digests, shape, (const u64*)d_idx, n_idx, (u64*)d_sib);
+        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(digests, shape, (const u64*)d_idx, n_idx, (u64*)d_sib, N - 1);
         ctx->launches++;
         if ((rc = d2h(ctx, siblings, d_sib, sib_b))) return done(rc);
     }
@@ -985,7 +1021,7 @@ extern "C" int b200zkp_dev_gather(b200zkp_ctx* ctx, const uint64_t* lde, uint64_
         if (!lde) BAD(ctx, "null leaf buffer");
         u64 cnt = n_idx * row_len;
         if (cnt) {
-            merkle::gather_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const u64*)lde, col_stride, row_len, (const u64*)idx_dev, n_idx, (u64*)rows_dev);
+            merkle::gather_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const u64*)lde, col_stride, row_len, (const u64*)idx_dev, n_idx, (u64*)rows_dev, n_leaves - 1);
             LAUNCH_CHECK(ctx);
         }
     }
@@ -994,7 +1030,7 @@ extern "C" int b200zkp_dev_gather(b200zkp_ctx* ctx, const uint64_t* lde, uint64_
         if (!digests) BAD(ctx, "null digests buffer");
         merkle::TreeShape shape; shape.sub_log = depth; shape.sub_digests = 2 * (((u64)1 << depth) - 1);
         u64 cnt = n_idx * depth;
-        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const u64*)digests, shape, (const u64*)idx_dev, n_idx, (u64*)siblings_dev);
+        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>((const u64*)digests, shape, (const u64*)idx_dev, n_idx, (u64*)siblings_dev, n_leaves - 1);
         LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -1367,7 +1403,7 @@ extern "C" int b200zkp_fri_query(b200zkp_fri* f, uint32_t layer, const uint64_t*
     if (sib_b) {
         merkle::TreeShape shape; shape.sub_log = depth; shape.sub_digests = 2 * (((u64)1 << depth) - 1);
         u64 cnt = n_idx * depth;
-        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(L.digests, shape, (const u64*)d_idx, n_idx, (u64*)d_sib);
+        merkle::gather_siblings_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(L.digests, shape, (const u64*)d_idx, n_idx, (u64*)d_sib, ~0ull);
         ctx->launches++;
         if ((rc = d2h(ctx, siblings, d_sib, sib_b))) return done(rc);
     }

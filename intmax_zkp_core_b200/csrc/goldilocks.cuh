@@ -150,19 +150,6 @@ GL_FN u64 mul_nc(u64 a, u64 b) {
 // any u64 operands -> canonical
 GL_FN u64 mul(u64 a, u64 b) { return canon(mul_nc(a, b)); }
 
-// a^2: B200ZKP_SQR3 (tuning builds) takes three 32x32 products and doubles the cross term with shifts instead of four
-GL_FN u64 sqr_nc(u64 a) {
-#ifdef B200ZKP_SQR3
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
-    const u64 ll = (u64)a0 * a0, lh = (u64)a0 * a1, hh = (u64)a1 * a1;
-    unsigned __int128 p = ((unsigned __int128)hh << 64) | ll;
-    p += (unsigned __int128)lh << 33;
-    return reduce128((u64)p, (u64)(p >> 64));
-#else
-    return mul_nc(a, a);
-#endif
-}
-
 #ifdef B200ZKP_HOST_EMU
 GL_FN u32 brev32(u32 x) { u32 r = 0; for (int i = 0; i < 32; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }
 GL_FN u64 brev64(u64 x) { u64 r = 0; for (int i = 0; i < 64; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r; }

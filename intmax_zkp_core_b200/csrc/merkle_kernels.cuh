@@ -22,9 +22,6 @@
 #ifndef B200ZKP_HASH_THREADS
 #define B200ZKP_HASH_THREADS 256
 #endif
-#ifndef B200ZKP_HASH_PREFETCH
-#define B200ZKP_HASH_PREFETCH 0
-#endif
 
 namespace merkle {
 
@@ -53,38 +50,13 @@ GL_FN void sponge_leaf(const u64* __restrict__ p, u64 col_stride, u32 leaf_len, 
         }
         return;
     }
-#if !B200ZKP_HASH_PREFETCH
     for (u32 c = 0; c < leaf_len; c += poseidon::RATE) {
+        // overwrite mode: a short last chunk leaves the remaining rate words untouched
 #pragma unroll
         for (int i = 0; i < poseidon::RATE; i++)
             if (c + i < leaf_len) s[i] = p[(u64)(c + i) * col_stride];
-#ifdef B200ZKP_LEAN
-        poseidon::permute_nc(s);        // the state stays inside the sponge: only the digest is canonicalised, below
-#else
-        poseidon::permute(s);
-#endif
-    }
-#ifdef B200ZKP_LEAN
-#pragma unroll
-    for (int i = 0; i < 4; i++) s[i] = gl::canon(s[i]);
-#endif
-#else
-    u64 nx[poseidon::RATE];
-#pragma unroll
-    for (int i = 0; i < poseidon::RATE; i++) nx[i] = (u32)i < leaf_len ? p[(u64)i * col_stride] : 0;
-    for (u32 c = 0; c < leaf_len; c += poseidon::RATE) {
-        u32 rem = leaf_len - c;
-        // overwrite mode: a short last chunk leaves the remaining rate words untouched
-#pragma unroll
-        for (int i = 0; i < poseidon::RATE; i++) if ((u32)i < rem) s[i] = nx[i];
-        // prefetch the next chunk before the ~20k-instruction permutation
-        u32 c2 = c + poseidon::RATE;
-#pragma unroll
-        for (int i = 0; i < poseidon::RATE; i++)
-            if (c2 + i < leaf_len) nx[i] = p[(u64)(c2 + i) * col_stride];
         poseidon::permute(s);
     }
-#endif
 }
 
 #ifndef B200ZKP_HOST_EMU
@@ -274,23 +246,24 @@ two_to_one_kernel(const u64* __restrict__ l, const u64* __restrict__ r, u64* __r
 
 // ---------------------------------------------------------------- accessors (A11)
 // rows[q][c] = lde[c*col_stride + idx[q]]  (leaf rows of a column-major LDE)
+// idx_mask = number of leaves - 1: device-side indices cannot be validated by the host, so they are reduced instead
 __global__ void gather_rows_kernel(const u64* __restrict__ lde, u64 col_stride, u32 row_len,
-                                   const u64* __restrict__ idx, u64 n_idx, u64* __restrict__ rows) {
+                                   const u64* __restrict__ idx, u64 n_idx, u64* __restrict__ rows, u64 idx_mask) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_idx * row_len) return;
     u64 q = g / row_len;
     u32 c = (u32)(g % row_len);
-    rows[g] = lde[(u64)c * col_stride + idx[q]];
+    rows[g] = lde[(u64)c * col_stride + (idx[q] & idx_mask)];
 }
 
 // MerkleTree::prove for a batch of leaf indices: siblings[q][i] = sibling digest at layer i
 __global__ void gather_siblings_kernel(const u64* __restrict__ digests, TreeShape shape,
-                                       const u64* __restrict__ idx, u64 n_idx, u64* __restrict__ sib) {
+                                       const u64* __restrict__ idx, u64 n_idx, u64* __restrict__ sib, u64 idx_mask) {
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_idx * shape.sub_log) return;
     u64 q = g / shape.sub_log;
     u32 layer = (u32)(g % shape.sub_log);
-    u64 leaf = idx[q];
+    u64 leaf = idx[q] & idx_mask;
     u64 subtree = leaf >> shape.sub_log;
     u64 m = (leaf & (((u64)1 << shape.sub_log) - 1)) >> layer;   // node on the path at this layer
     const u64* src = digests + 4 * node_slot(shape, subtree, layer, m ^ 1);

@@ -21,11 +21,6 @@
 #include "goldilocks.cuh"
 #include "poseidon_tables.cuh"
 
-// which groups of integer operations are pinned to the ALU pipe (see "Pipe steering" below); tuning builds override it
-#ifndef B200ZKP_MDS_ALU_MASK
-#define B200ZKP_MDS_ALU_MASK 61   // tuning builds only (tools/bench_variants.sh)
-#endif
-
 namespace poseidon {
 
 using gl::u32;
@@ -34,44 +29,11 @@ using gl::u64;
 static constexpr int WIDTH = 12;
 static constexpr int RATE = 8;
 
-// 64 x 64 -> 128 product of the S-box.  B200ZKP_SBOX_ALU: the carries of the middle column are consumed by IADD3.X on the ALU
-// pipe (the compiler's own 128-bit product spends an IMAD.X, an IMAD.MOV and an accumulating IMAD.WIDE.X on them): same seven
-// instructions, three fewer slots on the multiplier pipe, which is the busier one in the hash kernels (not in the transforms,
-// which keep gl::mul_nc).
-GL_FN u64 mul_s(u64 a, u64 b) {
-#if defined(B200ZKP_SBOX_ALU) && !defined(B200ZKP_HOST_EMU)
-    u64 lo, hi;
-    asm("{\n\t"
-        ".reg .u32 a0, a1, b0, b1, p0, p1, m0, m1, h0, h1;\n\t"
-        ".reg .u64 p, m, t, h;\n\t"
-        "mov.b64 {a0, a1}, %2;\n\t"
-        "mov.b64 {b0, b1}, %3;\n\t"
-        "mul.wide.u32 p, a0, b0;\n\t"
-        "mul.wide.u32 h, a1, b1;\n\t"
-        "mov.b64 {h0, h1}, h;\n\t"
-        "mul.wide.u32 m, a0, b1;\n\t"
-        "mul.wide.u32 t, a1, b0;\n\t"
-        "add.cc.u64 m, m, t;\n\t"             // middle column a0 b1 + a1 b0: 65 bits
-        "addc.u32 h1, h1, 0;\n\t"             // its carry has weight 2^96
-        "mov.b64 {p0, p1}, p;\n\t"
-        "mov.b64 {m0, m1}, m;\n\t"
-        "add.cc.u32 p1, p1, m0;\n\t"
-        "addc.cc.u32 h0, h0, m1;\n\t"
-        "addc.u32 h1, h1, 0;\n\t"
-        "mov.b64 %0, {p0, p1};\n\t"
-        "mov.b64 %1, {h0, h1};\n\t"
-        "}" : "=l"(lo), "=l"(hi) : "l"(a), "l"(b));
-    return gl::reduce128(lo, hi);
-#else
-    return gl::mul_nc(a, b);
-#endif
-}
-
 GL_FN u64 sbox(u64 x) {
-    u64 x2 = mul_s(x, x);
-    u64 x4 = mul_s(x2, x2);
-    u64 x3 = mul_s(x2, x);
-    return mul_s(x3, x4);
+    u64 x2 = gl::mul_nc(x, x);
+    u64 x4 = gl::mul_nc(x2, x2);
+    u64 x3 = gl::mul_nc(x2, x);
+    return gl::mul_nc(x3, x4);
 }
 
 // a arbitrary u64, c canonical constant -> arbitrary u64 congruent to a + c
@@ -92,17 +54,9 @@ GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc, u32 zero = 0u) {
         ".reg .u32 a, b, c, d, w0, w1, top, rc0, rc1, m;\n\t"
         ".reg .u64 t, u;\n\t"
         "mov.b64 {rc0, rc1}, %4;\n\t"
-#if B200ZKP_MDS_ALU_MASK & 128
-        "shf.l.wrap.b32 a, %5, %2, 22;\n\t"    // a funnel shift with an opaque-zero low word stays on the ALU pipe (SHF)
-#else
         "shl.b32 a, %2, 22;\n\t"
-#endif
         "shr.u32 b, %2, 10;\n\t"
-#if B200ZKP_MDS_ALU_MASK & 128
-        "shf.l.wrap.b32 c, %5, %3, 11;\n\t"
-#else
         "shl.b32 c, %3, 11;\n\t"
-#endif
         "shr.u32 d, %3, 21;\n\t"
         "add.cc.u32 w0, %1, a;\n\t"
         "addc.cc.u32 w1, b, c;\n\t"
@@ -138,7 +92,7 @@ GL_FN u64 combine3(u32 O0, u32 O1, u32 O2, u64 rc, u32 zero = 0u) {
 // instruction per two cycles each, and an IMAD.WIDE holds the multiplier pipe twice as long.  ptxas turns every two-input
 // add into IMAD.IADD, which left the multiplier pipe 92 % busy with the ALU half idle (profiles/README.md).  A third
 // operand that ptxas cannot prove to be zero (OPAQUE_ZERO, a __constant__ word) makes the add a three-input IADD3,
-// which only the ALU pipe has.  kAluSp/kAluUv/kAluC/kAluOut choose which groups of adds are pinned that way; the
+// which only the ALU pipe has.  kAluSp/kAluUv/kAluC/kAluNorm/kAluInj choose which groups of adds are pinned that way; the
 // setting below balances the two pipes for the whole permutation (tools/sass_mix.py: 12.1 k slots on either pipe,
 // down from 15.9 k on the multiplier pipe).
 #ifdef B200ZKP_HOST_EMU
@@ -146,17 +100,14 @@ static const u32 OPAQUE_ZERO = 0;
 #else
 static __device__ __constant__ u32 OPAQUE_ZERO = 0;
 #endif
-static constexpr bool kAluSp = B200ZKP_MDS_ALU_MASK & 1, kAluUv = B200ZKP_MDS_ALU_MASK & 2, kAluC = B200ZKP_MDS_ALU_MASK & 4,
-                      kAluOut = B200ZKP_MDS_ALU_MASK & 8, kAluNorm = B200ZKP_MDS_ALU_MASK & 16, kAluInj = B200ZKP_MDS_ALU_MASK & 32,
-                      kAluRing = B200ZKP_MDS_ALU_MASK & 64, kAluShift = B200ZKP_MDS_ALU_MASK & 128;
+// chosen on the GPU (profiles/r1c_poseidon_variants.log): pinned are the first butterfly level, the (1, 2, 1) product, the limb
+// re-normalisation and the S-box injection; the second butterfly level and the two larger ring products stay with ptxas
+static constexpr bool kAluSp = true, kAluUv = false, kAluC = true, kAluNorm = true, kAluInj = true;
 
 // The state between two linear layers, in the split basis of Z[t] / (t^12 - 1) = (t^3 - 1)(t^3 + 1)(t^6 + 1): three limb
 // planes of U[3], V[3], W[6] (signed 32-bit; tools/poseidon_crt_model.py bounds every intermediate by interval arithmetic).
 struct SplitState {
     int U[3][3], V[3][3], W[3][6];
-#ifdef B200ZKP_LEAN
-    int X0[3];          // word 0 of the layer's output, limbs + 2^30 (see partial_head)
-#endif
 };
 
 GL_FN u32 limb_of(u64 x, int L) {
@@ -207,14 +158,13 @@ GL_FN void ring_products(const int (&U)[3], const int (&V)[3], const int (&W)[6]
     Cq[0] = T + U[2] + (int)(kAluC ? Z : 0u);
     Cq[1] = T + U[0] + (int)(kAluC ? Z : 0u);
     Cq[2] = T + U[1] + (int)(kAluC ? Z : 0u);
-    const int zr = (int)(kAluRing ? Z : 0u);
-    D[0] = 8 * V[2] - V[0] - 2 * V[1] + zr;
-    D[1] = -8 * V[0] - V[1] - 2 * V[2] + zr;
-    D[2] = 2 * V[0] - 8 * V[1] - V[2] + zr;
+    D[0] = 8 * V[2] - V[0] - 2 * V[1];
+    D[1] = -8 * V[0] - V[1] - 2 * V[2];
+    D[2] = 2 * V[0] - 8 * V[1] - V[2];
     constexpr int Qc[6] = {2, -4, 16, 1, -1, -1};
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        int acc = zr;
+        int acc = 0;
 #pragma unroll
         for (int i = 0; i < 6; i++) {
             const int q = (k >= i) ? Qc[k - i] : -Qc[k - i + 6];
@@ -230,9 +180,6 @@ GL_FN void layer_stay(SplitState& c, const int (&z8)[3], u32 Z) {
     for (int L = 0; L < 3; L++) {
         int Cq[3], D[3], B[6];
         ring_products(c.U[L], c.V[L], c.W[L], Cq, D, B, Z);
-#ifdef B200ZKP_LEAN
-        c.X0[L] = 16 * Cq[0] + D[0] + B[0] + z8[L] + (1 << 30);      // = out[0] of layer_leave: no division by 4 next round
-#endif
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             c.U[L][k] = 64 * Cq[k] + (k == 0 ? z8[L] : 0);
@@ -283,18 +230,11 @@ GL_FN u64 div4(u64 v) {
 // difference is put back into the three components; cst = round constant - 2^21 (1 + 2^22 + 2^43) (SPLIT_ADD)
 GL_FN void partial_head(SplitState& c, u64 cst, int (&z8)[3], u32 Z) {
     const int zi = (int)(kAluInj ? Z : 0u);
-#ifdef B200ZKP_LEAN
-    // tuning build: word 0 comes packed from the previous layer's ring products (layer_stay: X0), cst = plain round constant
-    constexpr u64 X0_UNBIAS = 0xffeffdfec0000201ull;      // -(2^30 (1 + 2^22 + 2^43)) mod p
-    const u64 e = combine3((u32)c.X0[0], (u32)c.X0[1], (u32)c.X0[2], X0_UNBIAS, Z);
-    constexpr int kDBias = 0;
-#else
     u32 E[3];
 #pragma unroll
     for (int L = 0; L < 3; L++) E[L] = (u32)(c.U[L][0] + c.V[L][0] + 2 * c.W[L][0] + (1 << 23));
     const u64 e = div4(combine3(E[0], E[1], E[2], 0ull, Z));
     constexpr int kDBias = 1 << 21;
-#endif
     const u64 z = sbox(add_const(e, cst));
 #pragma unroll
     for (int L = 0; L < 3; L++) {
@@ -318,75 +258,6 @@ GL_FN u64 mul_add_nc(u64 w, u64 x, u64 s) {
 // whole permutation stays resident in the instruction cache (a two-loop form of 59 KB ran at a 67 % hit rate with "no
 // instruction" as the top stall).  The round kind is warp-uniform.  Rounds 3..24 leave the state in the split basis
 // (the next round is partial), every other round packs it back into words for the twelve S-boxes that follow.
-#if defined(B200ZKP_ALIAS_STATE) && !defined(B200ZKP_LEAN)
-// B200ZKP_ALIAS_STATE (tuning build): the loop carries one image of 36 registers that holds either the twelve words or the
-// split-basis limbs, instead of both forms (60 registers live across the back edge): 204 -> 48 bytes of spills at a
-// 64-register cap (256 x 4 CTAs), so the CTA shapes with more warps and the other tuning builds get room.
-GL_FN void st_load(const u32 (&st)[36], SplitState& c) {
-#pragma unroll
-    for (int L = 0; L < 3; L++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { c.U[L][k] = (int)st[L * 12 + k]; c.V[L][k] = (int)st[L * 12 + 3 + k]; }
-#pragma unroll
-        for (int k = 0; k < 6; k++) c.W[L][k] = (int)st[L * 12 + 6 + k];
-    }
-}
-GL_FN void st_store(u32 (&st)[36], const SplitState& c) {
-#pragma unroll
-    for (int L = 0; L < 3; L++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) { st[L * 12 + k] = (u32)c.U[L][k]; st[L * 12 + 3 + k] = (u32)c.V[L][k]; }
-#pragma unroll
-        for (int k = 0; k < 6; k++) st[L * 12 + 6 + k] = (u32)c.W[L][k];
-    }
-}
-
-GL_FN void permute_nc(u64 (&s)[WIDTH]) {
-    using namespace poseidon_tables;
-    // one register file image for both forms of the state: words (24 registers) or split-basis limbs (36)
-    u32 st[36];
-#pragma unroll
-    for (int i = 0; i < WIDTH; i++) {
-        const u64 v = add_const(s[i], SPLIT_ADD[i]);
-        st[2 * i] = (u32)v; st[2 * i + 1] = (u32)(v >> 32);
-    }
-#pragma unroll
-    for (int i = 24; i < 36; i++) st[i] = 0;
-#pragma unroll 1
-    for (int r = 0; r < 30; r++) {
-        const bool full = (r < 4) || (r >= 26);
-        const bool stay = (r >= 3) && (r < 25);
-        const u32 Z = OPAQUE_ZERO;
-        int z8[3];
-        SplitState c;
-        if (full) {
-            u64 w[WIDTH];
-#pragma unroll
-            for (int i = 0; i < WIDTH; i++) w[i] = sbox(((u64)st[2 * i + 1] << 32) | st[2 * i]);
-            split_forward(w, c, z8, Z);
-            if (stay) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) normalise(c.U[0][k], c.U[1][k], c.U[2][k], Z);
-            }
-        } else {
-            st_load(st, c);
-            partial_head(c, SPLIT_ADD[r * WIDTH], z8, Z);
-        }
-        if (stay) {
-            layer_stay(c, z8, Z);
-            st_store(st, c);
-        } else {
-            u64 w[WIDTH];
-            layer_leave(c, z8, w, (full ? 0u : (1u << 30)) + Z, Z, &SPLIT_ADD[(r + 1) * WIDTH]);
-#pragma unroll
-            for (int i = 0; i < WIDTH; i++) { st[2 * i] = (u32)w[i]; st[2 * i + 1] = (u32)(w[i] >> 32); }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < WIDTH; i++) s[i] = ((u64)st[2 * i + 1] << 32) | st[2 * i];
-}
-
-#else
 GL_FN void permute_nc(u64 (&s)[WIDTH]) {
     using namespace poseidon_tables;
 #pragma unroll
@@ -398,9 +269,6 @@ GL_FN void permute_nc(u64 (&s)[WIDTH]) {
         for (int k = 0; k < 3; k++) { c.U[L][k] = 0; c.V[L][k] = 0; }
 #pragma unroll
         for (int k = 0; k < 6; k++) c.W[L][k] = 0;
-#ifdef B200ZKP_LEAN
-        c.X0[L] = 0;
-#endif
     }
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
@@ -417,11 +285,7 @@ GL_FN void permute_nc(u64 (&s)[WIDTH]) {
                 for (int k = 0; k < 3; k++) normalise(c.U[0][k], c.U[1][k], c.U[2][k], Z);
             }
         } else {
-#ifdef B200ZKP_LEAN
-            partial_head(c, ROUND_ADD[r * WIDTH], z8, Z);
-#else
             partial_head(c, SPLIT_ADD[r * WIDTH], z8, Z);
-#endif
         }
         if (stay) {
             layer_stay(c, z8, Z);
@@ -432,8 +296,6 @@ GL_FN void permute_nc(u64 (&s)[WIDTH]) {
     }
 }
 
-#endif
-
 // In-place permutation; input words arbitrary u64, output canonical.
 GL_FN void permute(u64 (&s)[WIDTH]) {
     permute_nc(s);
@@ -442,14 +304,6 @@ GL_FN void permute(u64 (&s)[WIDTH]) {
 }
 
 // permutation whose caller keeps only the digest words 0..3 (compressions, the last permutation of a sponge)
-GL_FN void permute_digest(u64 (&s)[WIDTH]) {
-#ifdef B200ZKP_LEAN
-    permute_nc(s);
-#pragma unroll
-    for (int i = 0; i < 4; i++) s[i] = gl::canon(s[i]);
-#else
-    permute(s);
-#endif
-}
+GL_FN void permute_digest(u64 (&s)[WIDTH]) { permute(s); }
 
 }  // namespace poseidon

@@ -195,7 +195,7 @@ class FriCommitPhase:
         self._ctx, self._h = ctx, handle
 
     @classmethod
-    def from_oracles(cls, instance: FriInstanceInfo, oracles: Sequence[PolynomialBatch], alpha: Ext, mul_by_x: bool = True,
+    def from_oracles(cls, instance: FriInstanceInfo, oracles: Sequence[PolynomialBatch], alpha: Ext, mul_by_x: bool,
                      ctx: Optional[Context] = None) -> "FriCommitPhase":
         """prove_openings up to (and including) `lde_final_values`."""
         ctx = ctx or oracles[0]._ctx
@@ -311,8 +311,12 @@ def fri_proof(initial_merkle_trees: Sequence[PolynomialBatch], commit: FriCommit
 
 
 def prove_openings(instance: FriInstanceInfo, oracles: Sequence[PolynomialBatch], challenger: Challenger,
-                   fri_params: FriParams, mul_by_x: bool = True) -> FriProof:
-    """fri/oracle.rs PolynomialBatch::prove_openings."""
+                   fri_params: FriParams, mul_by_x: bool) -> FriProof:
+    """fri/oracle.rs PolynomialBatch::prove_openings.
+
+    mul_by_x has no default on purpose: whether final_poly carries the factor X depends on the plonky2 revision (the 2022
+    code inserts it, later code pads the quotient) and no proof fixture in the reference pins it — the
+    caller states which verifier the proof is for."""
     assert all(o.degree_log == fri_params.degree_bits and o.rate_bits == fri_params.config.rate_bits for o in oracles)
     alpha = challenger.get_extension_challenge()
     commit = FriCommitPhase.from_oracles(instance, oracles, alpha, mul_by_x)

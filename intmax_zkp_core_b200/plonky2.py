@@ -80,8 +80,17 @@ class Context:
     STAGES = ("intt", "lde", "leaf_hash", "tree")
 
     def set_overlap(self, enabled: bool):
-        """LDE / leaf-hash overlap on two streams (default on)."""
+        """LDE / leaf-hash overlap on two streams.  Off by default: measured on B200, co-resident transform and hash
+        kernels time-slice the issue slots instead of overlapping."""
         self.check(self._lib.b200zkp_ctx_set_overlap(self._h, int(enabled)))
+
+    def trim(self):
+        """Synchronise and hand every cached device buffer back to the driver (b200zkp_ctx_trim)."""
+        self.check(self._lib.b200zkp_ctx_trim(self._h))
+
+    def set_pool_limit(self, nbytes: int):
+        """Upper bound of the per-context cache of freed device buffers (default: 1/8 of the device memory)."""
+        self.check(self._lib.b200zkp_ctx_set_pool_limit(self._h, int(nbytes)))
 
     def set_timing(self, enabled: bool):
         self.check(self._lib.b200zkp_ctx_set_timing(self._h, int(enabled)))

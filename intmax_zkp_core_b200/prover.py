@@ -96,14 +96,22 @@ def zs_partial_products_device(ctx: Context, wires, sigmas, k_is, betas, gammas,
     return out
 
 
-def quotient_poly_chunks(quotient_values, degree_bits: int, ctx: Optional[Context] = None) -> np.ndarray:
+class QuotientError(ValueError):
+    """plonky2's `trim_to_len` panic: the vanishing polynomial is not divisible by Z_H (unsatisfied witness)."""
+
+
+def quotient_poly_chunks(quotient_values, degree_bits: int, quotient_degree_factor: Optional[int] = None,
+                         ctx: Optional[Context] = None) -> np.ndarray:
     """Tail of plonky2's compute_quotient_polys + the chunking in prove() (row N1c):
 
         quotient_values.map(|v| v.coset_ifft(F::coset_shift()))            // one polynomial per challenge
         quotient_poly.trim_to_len(quotient_degree); quotient_poly.chunks(degree)
 
     quotient_values: (num_challenges, n * 2^quotient_degree_bits) values on the coset 7 <w>, natural order.
-    Returns (num_challenges * 2^quotient_degree_bits, n) coefficient chunks, the input of PolynomialBatch.from_coeffs."""
+    quotient_degree_factor (CommonCircuitData; chosen in min..=max, not necessarily a power of two; default: every chunk):
+    coefficients from quotient_degree_factor * n on must vanish — plonky2 panics there, this raises QuotientError — and only
+    quotient_degree_factor chunks per challenge are committed.
+    Returns (num_challenges * quotient_degree_factor, n) coefficient chunks, the input of PolynomialBatch.from_coeffs."""
     q = _u64(quotient_values)
     if q.ndim != 2:
         raise ValueError("expected (num_challenges, n << quotient_degree_bits)")
@@ -111,19 +119,26 @@ def quotient_poly_chunks(quotient_values, degree_bits: int, ctx: Optional[Contex
     if q.shape[1] % n or q.shape[1] < n:
         raise ValueError("quotient length must be a multiple of the degree")
     coeffs = coset_ifft_batch(q, MULTIPLICATIVE_GROUP_GENERATOR, ctx)
-    return coeffs.reshape(q.shape[0] * (q.shape[1] // n), n)
+    total = q.shape[1] // n
+    qdf = total if quotient_degree_factor is None else int(quotient_degree_factor)
+    if not 0 < qdf <= total:
+        raise ValueError("quotient_degree_factor out of range")
+    if coeffs[:, qdf * n:].any():
+        raise QuotientError("Quotient has failed: coefficients beyond quotient_degree_factor * n are not zero")
+    return np.ascontiguousarray(coeffs[:, :qdf * n]).reshape(q.shape[0] * qdf, n)
 
 
 def commit_quotient(quotient_values, degree_bits: int, rate_bits: int, blinding: bool, cap_height: int, salt=None,
-                    ctx: Optional[Context] = None) -> PolynomialBatch:
+                    ctx: Optional[Context] = None, quotient_degree_factor: Optional[int] = None) -> PolynomialBatch:
     """quotient_polys_commitment of prove(): PolynomialBatch::from_coeffs(all_quotient_poly_chunks, ...)"""
-    return PolynomialBatch.from_coeffs(quotient_poly_chunks(quotient_values, degree_bits, ctx), rate_bits, blinding, cap_height,
-                                       salt=salt, ctx=ctx)
+    return PolynomialBatch.from_coeffs(quotient_poly_chunks(quotient_values, degree_bits, quotient_degree_factor, ctx), rate_bits,
+                                       blinding, cap_height, salt=salt, ctx=ctx)
 
 
-def commit_quotient_device(ctx: Context, quotient_values, degree_bits: int, rate_bits: int, cap_height: int):
-    """device-resident form: (C, n << q) CUDA tensor of quotient values -> DeviceCommitment of the C * 2^q chunks; the
-    coefficients never leave HBM"""
+def commit_quotient_device(ctx: Context, quotient_values, degree_bits: int, rate_bits: int, cap_height: int,
+                           quotient_degree_factor: Optional[int] = None):
+    """device-resident form: (C, n << q) CUDA tensor of quotient values -> DeviceCommitment of the C * quotient_degree_factor
+    chunks (default 2^q); the coefficients never leave HBM (the divisibility check reads one flag back)"""
     import torch
     from .device import commit_device
     Cn, total = quotient_values.shape
@@ -133,4 +148,12 @@ def commit_quotient_device(ctx: Context, quotient_values, degree_bits: int, rate
     scratch = torch.empty_like(quotient_values)
     ctx.check(ctx._lib.b200zkp_dev_coset_intt(ctx._h, C.c_void_p(quotient_values.data_ptr()), total, C.c_void_p(coeffs.data_ptr()), total,
                                               C.c_void_p(scratch.data_ptr()), log2_strict(total), Cn, MULTIPLICATIVE_GROUP_GENERATOR))
-    return commit_device(ctx, coeffs.view(Cn * (total // n), n), rate_bits, cap_height, is_coeffs=True)
+    qdf = total // n if quotient_degree_factor is None else int(quotient_degree_factor)
+    if not 0 < qdf <= total // n:
+        raise ValueError("quotient_degree_factor out of range")
+    if qdf < total // n:
+        ctx.synchronize()       # (the ctx stream may not be torch's current stream)
+        if bool(coeffs[:, qdf * n:].any()):
+            raise QuotientError("Quotient has failed: coefficients beyond quotient_degree_factor * n are not zero")
+        coeffs = coeffs[:, :qdf * n].contiguous()
+    return commit_device(ctx, coeffs.view(Cn * qdf, n), rate_bits, cap_height, is_coeffs=True)

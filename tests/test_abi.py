@@ -11,8 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    with open(os.path.join(ROOT, "include", "b200zkp.h")) as f:
-        text = f.read()
+    """every entry point declared by include/*.h (the drop-in surface b200zkp.h and the test probes b200zkp_test.h)"""
+    text = ""
+    for name in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if name.endswith(".h"):
+            with open(os.path.join(ROOT, "include", name)) as f:
+                text += f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(b200zkp_[a-z0-9_]+)\s*\(", text)))
 
@@ -27,6 +31,9 @@ def test_library_builds_and_exports_declared_abi():
         assert hasattr(lib, name), f"{name} declared in include/b200zkp.h but not exported"
     assert sorted(_lib.EXPORTED_SYMBOLS) == decl            # the ctypes table binds every declared entry point
     assert b"sm_100a" in lib.b200zkp_version()
+    # probes and micro-benchmarks are not part of the drop-in surface
+    with open(os.path.join(ROOT, "include", "b200zkp.h")) as f:
+        assert "b200zkp_field_op" not in f.read()
 
 
 def test_library_is_sm_100a_only():

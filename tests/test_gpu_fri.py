@@ -156,7 +156,7 @@ def test_standard_config_proof_passes_the_oracle_verifier(zf, ctx, oracle, n_log
     evals = [b.eval_ext2(np.array(batches[0][0], dtype=np.uint64)) for b in gpu]
     evals_g = gpu[-1].eval_ext2(np.array(batches[1][0], dtype=np.uint64))
     openings = [[tuple(int(v) for v in evals[o][i]) for o, i in batches[0][1]], [tuple(int(v) for v in evals_g[i]) for _, i in batches[1][1]]]
-    proof = zf.prove_openings(instance, gpu, ch, params)
+    proof = zf.prove_openings(instance, gpu, ch, params, True)
     assert 64 - int(oracle.hash_no_pad(list(_pow_hash(F, gpu, proof)) + [proof.pow_witness])[0]).bit_length() >= 16
 
     def fresh():
@@ -239,10 +239,10 @@ def test_fri_argument_checks(zf, ctx):
     b = z.PolynomialBatch.from_coeffs(np.ones((1, 16), np.uint64), 1, False, 0, ctx=ctx)
     inst = zf.FriInstanceInfo([zf.FriBatchInfo((1, 2), [zf.FriPolynomialInfo(0, 0), zf.FriPolynomialInfo(1, 0)])])
     with pytest.raises(z.B200ZkpError):
-        zf.FriCommitPhase.from_oracles(inst, [a, b], (5, 6), ctx=ctx)      # degrees differ
+        zf.FriCommitPhase.from_oracles(inst, [a, b], (5, 6), True, ctx=ctx)      # degrees differ
     inst = zf.FriInstanceInfo([zf.FriBatchInfo((1, 2), [zf.FriPolynomialInfo(0, 1)])])
     with pytest.raises(z.B200ZkpError):
-        zf.FriCommitPhase.from_oracles(inst, [a], (5, 6), ctx=ctx)         # polynomial index out of range
+        zf.FriCommitPhase.from_oracles(inst, [a], (5, 6), True, ctx=ctx)         # polynomial index out of range
 
 
 def test_hypothesis_opening_proofs(zf, ctx, oracle):

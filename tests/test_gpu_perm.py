@@ -146,7 +146,7 @@ def test_quotient_chunks_commitment(ctx):
     n = 1 << degree_bits
     qpoly = O.synthetic_values(Cn, n << q_bits, seed=9)       # the quotient polynomials' coefficients
     qvals = np.stack([O.coset_lde(row, 0) for row in qpoly])  # their values on 7 <w_8n>
-    chunks = Z.quotient_poly_chunks(qvals, degree_bits, ctx)
+    chunks = Z.quotient_poly_chunks(qvals, degree_bits, ctx=ctx)
     assert chunks.shape == (Cn << q_bits, n)
     assert (chunks == qpoly.reshape(Cn << q_bits, n)).all()
     batch = Z.commit_quotient(qvals, degree_bits, 3, False, 4, ctx=ctx)
@@ -158,3 +158,19 @@ def test_quotient_chunks_commitment(ctx):
     torch.cuda.synchronize()
     assert (com.cap.cpu().numpy().view(np.uint64) == ref["cap"]).all()
     assert (com.coeffs.cpu().numpy().view(np.uint64) == qpoly.reshape(Cn << q_bits, n)).all()
+    # quotient_degree_factor that is not a power of two (plonky2 picks it in min..=max): 6 chunks per challenge are committed and
+    # a quotient with non-zero coefficients beyond 6n is refused like plonky2's trim_to_len panic
+    with pytest.raises(Z.QuotientError):
+        Z.quotient_poly_chunks(qvals, degree_bits, 6, ctx)
+    with pytest.raises(Z.QuotientError):
+        Z.commit_quotient_device(tctx, dv, degree_bits, 3, 4, quotient_degree_factor=6)
+    qpoly6 = qpoly.copy()
+    qpoly6[:, 6 * n:] = 0
+    qvals6 = np.stack([O.coset_lde(row, 0) for row in qpoly6])
+    chunks6 = Z.quotient_poly_chunks(qvals6, degree_bits, 6, ctx)
+    assert chunks6.shape == (Cn * 6, n) and (chunks6 == qpoly6[:, :6 * n].reshape(Cn * 6, n)).all()
+    ref6 = O.commit(chunks6, 3, 4, is_coeffs=True)
+    assert (Z.commit_quotient(qvals6, degree_bits, 3, False, 4, ctx=ctx, quotient_degree_factor=6).merkle_tree.cap.elements == ref6["cap"]).all()
+    com6 = Z.commit_quotient_device(tctx, torch.from_numpy(qvals6.view(np.int64)).cuda(), degree_bits, 3, 4, quotient_degree_factor=6)
+    torch.cuda.synchronize()
+    assert (com6.cap.cpu().numpy().view(np.uint64) == ref6["cap"]).all()

@@ -44,7 +44,7 @@ def test_host_cpp_api_runs_on_gpu():
     inst = zf.FriInstanceInfo([
         zf.FriBatchInfo((123456789, 987654321), [zf.FriPolynomialInfo(0, i) for i in range(3)] + [zf.FriPolynomialInfo(1, i) for i in range(2)]),
         zf.FriBatchInfo((555, 777), [zf.FriPolynomialInfo(1, 0), zf.FriPolynomialInfo(1, 1)])])
-    proof = zf.prove_openings(inst, [o0, o1], ch, params)
+    proof = zf.prove_openings(inst, [o0, o1], ch, params, True)
     d = 0xcbf29ce484222325
     words = []
     for cap in proof.commit_phase_merkle_caps:
