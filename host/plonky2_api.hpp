@@ -216,4 +216,54 @@ class PolynomialBatch {
     std::shared_ptr<b200zkp_batch> h_;
 };
 
+// The same commitment partitioned over every GPU of the box, driven by ONE process (b200zkp_comm_init_all): what a
+// single-process rayon prove() (/root/reference/Cargo.toml:19-21) binds when more than one device is visible.  The cap
+// equals PolynomialBatch::from_values' bit for bit; leaves live where they are hashed (rank g owns leaves
+// [g*N/G, (g+1)*N/G)) and are opened through open(), which asks the owning rank.
+class ShardedPolynomialBatch {
+  public:
+    // contexts: one per device, contexts[i] = rank i; their number must be a power of two <= 2^rate_bits, 2^cap_height
+    static ShardedPolynomialBatch from_values(const std::vector<const Context*>& contexts, const std::vector<std::vector<F>>& values,
+                                              size_t rate_bits, size_t cap_height) {
+        if (values.empty() || contexts.empty()) throw std::invalid_argument("empty polynomial batch");
+        size_t n = values[0].size(), k = values.size(), n_log = log2_strict(n);
+        std::vector<F> flat(k * n);
+        for (size_t i = 0; i < k; i++) {
+            if (values[i].size() != n) throw std::invalid_argument("polynomials must have equal length");
+            std::copy(values[i].begin(), values[i].end(), flat.begin() + i * n);
+        }
+        std::vector<b200zkp_ctx*> raw;
+        for (auto* c : contexts) raw.push_back(c->raw());
+        ShardedPolynomialBatch b;
+        b200zkp_comm* comm = nullptr;
+        contexts[0]->check(b200zkp_comm_init_all(raw.data(), (int)raw.size(), &comm));
+        b.comm_.reset(comm, b200zkp_comm_destroy);
+        b.degree_log = n_log; b.rate_bits = rate_bits; b.cap_height = cap_height; b.num_polys = k;
+        b.cap.resize(size_t(1) << cap_height);
+        b200zkp_sharded* sh = nullptr;
+        b.check(b200zkp_sharded_commit_from_values(comm, flat.data(), (uint32_t)n_log, (uint32_t)k, (uint32_t)rate_bits,
+                                                   (uint32_t)cap_height, b.cap[0].elements.data(), &sh));
+        b.h_.reset(sh, b200zkp_sharded_free);
+        return b;
+    }
+    // leaf row + Merkle proof for a GLOBAL leaf index (MerkleTree::get + MerkleTree::prove on the owning rank)
+    std::pair<std::vector<F>, MerkleProof> open(uint64_t leaf_index) const {
+        std::vector<F> row(num_polys);
+        MerkleProof p;
+        p.siblings.resize(degree_log + rate_bits - cap_height);
+        check(b200zkp_sharded_rows(h_.get(), &leaf_index, 1, row.data(), p.siblings.empty() ? nullptr : p.siblings[0].elements.data()));
+        return {row, p};
+    }
+    MerkleCap cap;
+    size_t degree_log = 0, rate_bits = 0, cap_height = 0, num_polys = 0;
+
+  private:
+    void check(int rc) const {
+        if (rc == B200ZKP_ERR_BAD_ARG) throw std::invalid_argument(b200zkp_comm_last_error(comm_.get()));
+        if (rc != 0) throw std::runtime_error(b200zkp_comm_last_error(comm_.get()));
+    }
+    std::shared_ptr<b200zkp_comm> comm_;      // (declared before h_: the buffers are released first)
+    std::shared_ptr<b200zkp_sharded> h_;
+};
+
 }  // namespace plonky2

@@ -2,6 +2,7 @@
 // Merkle proofs.  Built and run by tests/test_host_cpp.py (gpu); exit code 0 = all checks passed.
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 #include "fri_api.hpp"
 #include "prover_api.hpp"
 
@@ -112,6 +113,29 @@ int main() {
         CHECK(cols[0][0] == 1 && cols[0][8] != 1 && cols[0][21] == 1 && cols[1][31] == 1);
         auto per = all_wires_permutation_partial_products(ctx, wires, sigmas, k_is, {11, 22}, {33, 44}, deg);
         CHECK(per.size() == 2 && per[1].size() == 2 && per[1][1] == cols[1] && per[0][0] == cols[2]);
+    }
+    if (b200zkp_device_count() >= 2) {
+        // one process, every GPU of the box (b200zkp_comm_init_all): same cap, same openings as the single-GPU commitment
+        int G = 2;
+        while (G * 2 <= b200zkp_device_count() && G * 2 <= 8) G *= 2;
+        std::vector<std::unique_ptr<Context>> owned;
+        std::vector<const Context*> cs;
+        for (int g = 0; g < G; g++) { owned.emplace_back(new Context(g)); cs.push_back(owned.back().get()); }
+        const size_t sn = 1 << 9, sk = 21;
+        std::vector<std::vector<F>> sv(sk, std::vector<F>(sn));
+        for (size_t c = 0; c < sk; c++)
+            for (size_t i = 0; i < sn; i++) { uint64_t v = splitmix64((7ull << 48) + c * sn + i); sv[c][i] = v >= GOLDILOCKS_ORDER ? v - GOLDILOCKS_ORDER : v; }
+        PolynomialBatch one = PolynomialBatch::from_values(ctx, sv, 3, false, 4);
+        ShardedPolynomialBatch many = ShardedPolynomialBatch::from_values(cs, sv, 3, 4);
+        CHECK(many.cap == one.cap);
+        for (uint64_t j : {0ull, 1ull, 2047ull, 2048ull, 4095ull}) {
+            auto a = one.open(j), b2 = many.open(j);
+            CHECK(a.first == b2.first && a.second.siblings == b2.second.siblings);
+        }
+        bool bad = false;
+        try { ShardedPolynomialBatch::from_values(cs, sv, 0, 4); } catch (const std::invalid_argument&) { bad = true; }
+        CHECK(bad);
+        std::printf("multi-GPU C++ API ok on %d devices\n", G);
     }
     std::printf("host C++ API ok\n");
     return 0;

@@ -42,7 +42,8 @@ typedef enum {
     B200ZKP_ERR_BAD_ARG = -1, /* plonky2's asserts: power-of-two sizes, cap_height <= log2(N), ... */
     B200ZKP_ERR_OOM = -2,
     B200ZKP_ERR_CUDA = -3,
-    B200ZKP_ERR_UNSUPPORTED = -4
+    B200ZKP_ERR_UNSUPPORTED = -4,
+    B200ZKP_ERR_NCCL = -5
 } b200zkp_status;
 
 typedef struct b200zkp_ctx b200zkp_ctx;
@@ -258,6 +259,63 @@ int b200zkp_dev_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires_
                                         uint32_t num_routed, uint32_t degree, const uint64_t* k_is, const uint64_t* betas,
                                         const uint64_t* gammas, uint32_t num_challenges, uint64_t* out_dev,
                                         uint64_t out_col_stride);
+
+/* ---- one commitment partitioned over several GPUs (NCCL over NVLink / NVSwitch) ----------------------
+ * north_star's partition: rank g of G (a power of two, G <= 2^rate_bits and G <= 2^cap_height) inverse-transforms columns
+ * [g*kp, (g+1)*kp), kp = ceil(k/G); the coefficient shards are exchanged with NCCL point-to-point groups (a few peers per
+ * group, so the coset transforms of the shards already received overlap the rest of the exchange); every rank then extends
+ * ALL k columns on its 2^rate_bits/G coset blocks = leaves [g*N/G, (g+1)*N/G), hashes them and builds its 2^cap_height/G
+ * cap subtrees without further communication; one ncclAllGather of 32 * 2^cap_height bytes hands every rank the cap.
+ *
+ * Two ways to form the communicator, matching how the caller is deployed:
+ *   b200zkp_comm_init_all   ONE process drives n GPUs (what a single rayon `prove()` process needs; plonky2 is one process,
+ *                           /root/reference/Cargo.toml:19-21): ctxs[i] is rank i (distinct devices).  Each entry point below
+ *                           then serves all n ranks, internally on one host thread per rank.
+ *   b200zkp_comm_init_rank  one process per GPU (torchrun / MPI style): rank 0 makes an id with b200zkp_comm_unique_id,
+ *                           hands it to the others out of band, every process calls init_rank with its ctx.
+ * libnccl.so.2 is loaded on first use (dlopen; a copy already loaded by the host process, e.g. torch's, is reused): the
+ * single-GPU entry points do not need NCCL.  Errors: B200ZKP_ERR_NCCL, text in b200zkp_comm_last_error. */
+typedef struct b200zkp_comm b200zkp_comm;
+typedef struct b200zkp_sharded b200zkp_sharded; /* a PolynomialBatch whose leaves are partitioned over the ranks */
+#define B200ZKP_COMM_ID_BYTES 128
+int b200zkp_comm_unique_id(uint8_t id[B200ZKP_COMM_ID_BYTES]);
+int b200zkp_comm_init_rank(b200zkp_ctx* ctx, const uint8_t id[B200ZKP_COMM_ID_BYTES], int rank, int world,
+                           b200zkp_comm** out);
+int b200zkp_comm_init_all(b200zkp_ctx* const* ctxs, int n, b200zkp_comm** out);
+void b200zkp_comm_destroy(b200zkp_comm* comm);
+const char* b200zkp_comm_last_error(const b200zkp_comm* comm);
+/* shape: world size, ranks driven by this process (1 after init_rank, world after init_all), global rank of local rank 0 */
+int b200zkp_comm_shape(const b200zkp_comm* comm, int32_t shape[3]);
+/* peers per exchange group (default 2; 0 = the whole exchange in one group, i.e. no overlap with the transforms) */
+int b200zkp_comm_set_exchange_group(b200zkp_comm* comm, uint32_t peers_per_group);
+
+/* buffers of one partitioned commitment on every local rank (coefficients of all k columns, the rank's leaf range of the
+ * LDE, its digests, the full cap); reusable for any number of commits of that shape */
+int b200zkp_sharded_create(b200zkp_comm* comm, uint32_t n_log, uint32_t k, uint32_t rate_bits, uint32_t cap_height,
+                           b200zkp_sharded** out);
+void b200zkp_sharded_free(b200zkp_sharded* sh);
+/* partition of local rank `local`: lay = { kp, col_begin, col_end, block_begin, block_end, N_local, cap_begin, cap_end } */
+int b200zkp_sharded_layout(const b200zkp_sharded* sh, int local, uint64_t lay[8]);
+/* PolynomialBatch::from_values / from_coeffs, partitioned.  inputs[i]: columns [col_begin, col_end) of local rank i,
+ * column-major (col_end - col_begin) * n words, host memory (pinned for full PCIe speed; the upload is chunked and
+ * overlaps the inverse transforms) or, with inputs_on_device, memory of that rank's device (read on the ctx stream).
+ * cap_out: NULL -> the call only enqueues (results are complete after b200zkp_sharded_synchronize); else 4 * 2^cap_height
+ * words of host memory, written before the call returns.  Collective: every process of the communicator calls it. */
+int b200zkp_sharded_commit(b200zkp_sharded* sh, const uint64_t* const* inputs, int inputs_on_device, int is_coeffs,
+                           uint64_t* cap_out);
+/* convenience for the one-process deployment and for tests: `values` is the FULL k*n column-major host matrix (every
+ * process passes the same one); creates the buffers, commits, returns the cap */
+int b200zkp_sharded_commit_from_values(b200zkp_comm* comm, const uint64_t* values, uint32_t n_log, uint32_t k,
+                                       uint32_t rate_bits, uint32_t cap_height, uint64_t* cap_out, b200zkp_sharded** out);
+int b200zkp_sharded_synchronize(b200zkp_sharded* sh);
+/* device views on local rank `local`: coefficients [G*kp][n] (all columns, natural column order, zero columns past k),
+ * LDE [k][N_local] (the rank's leaves, column-major), digests of its cap subtrees (plonky2 layout), the full cap */
+int b200zkp_sharded_device_ptrs(b200zkp_sharded* sh, int local, const uint64_t** coeffs, const uint64_t** lde,
+                                const uint64_t** digests, const uint64_t** cap);
+/* MerkleTree::get + MerkleTree::prove for GLOBAL leaf indices (what the FRI query rounds open): the owning rank gathers row
+ * and sibling path; rows n_idx * k, siblings n_idx * (log2 N - cap_height) * 4 (host; either may be NULL).  Collective. */
+int b200zkp_sharded_rows(b200zkp_sharded* sh, const uint64_t* idx, uint64_t n_idx, uint64_t* rows, uint64_t* siblings);
+
 #ifdef __cplusplus
 }
 #endif

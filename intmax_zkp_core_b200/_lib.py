@@ -20,7 +20,7 @@ TEST_HEADER = os.path.join(os.path.dirname(_HERE), "include", "b200zkp_test.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-ldl",
 ]
 
 u64p = C.POINTER(C.c_uint64)
@@ -143,6 +143,23 @@ _SIGS = {
                                                 C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200zkp_dev_partial_products_and_zs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "b200zkp_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "b200zkp_comm_init_rank": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "b200zkp_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "b200zkp_comm_destroy": (None, [C.c_void_p]),
+    "b200zkp_comm_last_error": (C.c_char_p, [C.c_void_p]),
+    "b200zkp_comm_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "b200zkp_comm_set_exchange_group": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "b200zkp_sharded_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "b200zkp_sharded_free": (None, [C.c_void_p]),
+    "b200zkp_sharded_layout": (C.c_int, [C.c_void_p, C.c_int, u64p]),
+    "b200zkp_sharded_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
+    "b200zkp_sharded_commit_from_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                   C.POINTER(C.c_void_p)]),
+    "b200zkp_sharded_synchronize": (C.c_int, [C.c_void_p]),
+    "b200zkp_sharded_device_ptrs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_void_p)]),
+    "b200zkp_sharded_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "b200zkp_field_op": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "b200zkp_int_pipe_bench": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_double)]),
 }

@@ -569,7 +569,18 @@ static int launch_leaf_hash(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride,
 
 static int launch_tree_levels(b200zkp_ctx* ctx, u64 n_leaves, const merkle::TreeShape& shape, u64* digests, u64* cap) {
     StageTimer tm(ctx, B200ZKP_STAGE_TREE);
+    // layers with at most 2^TOP_PARENTS_LOG parents per cap subtree: one launch for all of them (merkle_top_kernel)
+    const u32 top_layer0 = shape.sub_log > merkle::TOP_PARENTS_LOG ? shape.sub_log - merkle::TOP_PARENTS_LOG : 0;
+    const u64 n_subtrees = n_leaves >> shape.sub_log;
+    const bool fused_top = shape.sub_log > 0 && n_subtrees <= 65535;
     for (u32 layer = 0; layer < shape.sub_log; layer++) {
+        if (fused_top && layer == top_layer0) {
+            const u32 par0 = 1u << (shape.sub_log - layer - 1);          // parents per subtree at the first fused layer
+            const unsigned threads = std::max(32u, std::min(1024u, par0 * 16));
+            merkle::merkle_top_kernel<<<(unsigned)n_subtrees, threads, 0, ctx->stream>>>(digests, cap, shape, layer, ctx->round_add);
+            LAUNCH_CHECK(ctx);
+            break;
+        }
         u64 n_parents = n_leaves >> (layer + 1);
         if (n_parents <= COOP_MAX_NODES) {
             // too few nodes to fill the GPU: one node per 16 lanes, ~4x less latency per level
@@ -1958,3 +1969,6 @@ extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters
     *out_gips = instr / (ms * 1e-3) / 1e9;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ multi-GPU (NCCL)
+#include "sharded.inl"

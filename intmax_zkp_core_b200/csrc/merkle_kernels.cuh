@@ -165,6 +165,40 @@ merkle_level_coop_kernel(u64* __restrict__ digests, u64* __restrict__ cap, TreeS
     }
 }
 
+// The top of every cap subtree in ONE launch: CTA s reduces subtree s from layer `layer0` (at most TOP_PARENTS parents per
+// subtree) up to its cap entry, one node per 16-lane group, __syncthreads() between layers (a subtree never reads another
+// subtree's digests, so no grid-wide step is needed).  Replaces the chain of up to 8 dependent latency-form launches that
+// ended every tree (profiles/r1c_bench_launch_list.csv); warps without a live node skip the round so that the few live
+// warps of the last layers own the issue slots.  `digests` is read and written by different threads of the CTA: no
+// __restrict__ / read-only path on it.
+static constexpr u32 TOP_PARENTS_LOG = 7;      // 128 parents per subtree = 2 rounds of the 64 groups of a 1024-thread CTA
+__global__ void __launch_bounds__(1024)
+merkle_top_kernel(u64* digests, u64* __restrict__ cap, TreeShape shape, u32 layer0, const u64* __restrict__ ra) {
+    const u32 lane = threadIdx.x & 31, l = lane & 15, grp_base = lane & 16;
+    const u32 li = l < 12 ? l : 0;
+    const u32 grp = threadIdx.x >> 4, n_grp = blockDim.x >> 4;
+    const u32 warp_grp0 = (threadIdx.x >> 5) << 1;
+    const u64 subtree = blockIdx.x;
+    for (u32 layer = layer0; layer < shape.sub_log; layer++) {
+        const u32 par_log = shape.sub_log - layer - 1;
+        const u32 n_par = 1u << par_log;
+        for (u32 m0 = 0; m0 < n_par; m0 += n_grp) {
+            if (m0 + warp_grp0 >= n_par) continue;                   // warp-uniform: neither group of this warp has a node
+            u32 m = m0 + grp;
+            const bool live = m < n_par;
+            if (!live) m = 0;
+            const u64* src = digests + 4 * node_slot(shape, subtree, layer, 2 * (u64)m);
+            u64 s = (l < 8) ? src[l] : 0;
+            s = coop_permute(s, li, grp_base, ra);
+            if (live && l < 4) {
+                u64* dst = (par_log == 0) ? cap + 4 * subtree : digests + 4 * node_slot(shape, subtree, layer + 1, m);
+                dst[l] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // hash_or_noop / hash_no_pad of one leaf per 16-lane group (small trees: FRI layers, tiny circuits); same arguments as
 // leaf_hash_kernel
 __global__ void __launch_bounds__(128)

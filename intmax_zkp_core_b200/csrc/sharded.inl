@@ -1,0 +1,544 @@
+// One commitment partitioned over several GPUs behind the C ABI (include/b200zkp.h, "partitioned over several GPUs").
+// Included at the end of b200zkp.cu (uses its static stage functions).  Product code: NCCL is the only library on this
+// path and it only moves the coefficient shards and the 512-byte cap; every transform and hash is this repo's kernels.
+//
+// Replaces nothing in plonky2 (the CPU prover is one process on one memory): it is north_star's multi-GPU form of
+// PolynomialBatch::from_values, reached from the same prove() call sites
+// (/root/reference/src/rollup/circuits/mod.rs:1247, src/transaction/circuits/mod.rs:453).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <thread>
+
+namespace {
+
+// ---- libnccl.so.2, loaded on first use (the single-GPU ABI must load and run without NCCL)
+struct NcclApi {
+    void* handle = nullptr;
+    std::string err;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    bool ok() const { return handle != nullptr && err.empty(); }
+};
+
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // RTLD_NOLOAD first: a host process that already mapped libnccl.so.2 (torch ships its own) must not get a second copy
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { const char* e = dlerror(); api.err = std::string("cannot load libnccl.so.2: ") + (e ? e : "?"); return; }
+        api.handle = h;
+        auto sym = [&](const char* name) -> void* {
+            void* p = dlsym(h, name);
+            if (!p && api.err.empty()) api.err = std::string("libnccl lacks ") + name;
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.Send = (decltype(api.Send))sym("ncclSend");
+        api.Recv = (decltype(api.Recv))sym("ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    });
+    return api;
+}
+
+}  // namespace
+
+struct b200zkp_comm {
+    int world = 0;
+    std::vector<int> rank;             // global rank of local rank i
+    std::vector<b200zkp_ctx*> ctx;     // (not owned)
+    std::vector<ncclComm_t> nc;
+    std::vector<cudaStream_t> xstream; // exchange stream per local rank (NCCL point-to-point groups)
+    std::vector<cudaEvent_t> ev;       // per local rank: [2 + world] events (coefficients ready, buffers free, one per group)
+    uint32_t peers_per_group = 2;
+    std::mutex mu;                     // serialises the collective entry points of this process
+    std::string err;
+    int n_local() const { return (int)rank.size(); }
+};
+
+struct ShardRank {
+    u64 *coeffs_all = nullptr, *lde = nullptr, *digests = nullptr, *cap_local = nullptr, *cap = nullptr, *stage = nullptr;
+    size_t coeffs_b = 0, lde_b = 0, digests_b = 0, cap_local_b = 0, cap_b = 0, stage_b = 0;
+};
+
+struct b200zkp_sharded {
+    b200zkp_comm* comm = nullptr;
+    u32 n_log = 0, k = 0, rate_bits = 0, cap_height = 0;
+    u32 kp = 0, bpr = 0, cpr = 0, cap_height_local = 0;
+    u64 N_local = 0;
+    std::vector<ShardRank> r;
+};
+
+#define COMM_BAD(c, msg) do { (c)->err = (msg); return B200ZKP_ERR_BAD_ARG; } while (0)
+
+static int nccl_fail(std::string* err, const char* what, ncclResult_t r) {
+    NcclApi& a = nccl_api();
+    *err = std::string(what) + ": " + (a.GetErrorString ? a.GetErrorString(r) : "nccl error");
+    return B200ZKP_ERR_NCCL;
+}
+#define NCCL_TRY(errp, expr) do { ncclResult_t r__ = (expr); if (r__ != ncclSuccess) return nccl_fail((errp), #expr, r__); } while (0)
+
+static int nccl_ready(std::string* err) {
+    NcclApi& a = nccl_api();
+    if (!a.ok()) { *err = a.err.empty() ? "NCCL unavailable" : a.err; return B200ZKP_ERR_NCCL; }
+    return 0;
+}
+
+extern "C" int b200zkp_comm_unique_id(uint8_t id[B200ZKP_COMM_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) == B200ZKP_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!id) return B200ZKP_ERR_BAD_ARG;
+    std::string err;
+    if (nccl_ready(&err)) return B200ZKP_ERR_NCCL;
+    ncclUniqueId u;
+    if (nccl_api().GetUniqueId(&u) != ncclSuccess) return B200ZKP_ERR_NCCL;
+    memcpy(id, &u, sizeof(u));
+    return 0;
+}
+
+static int comm_finish_init(b200zkp_comm* c) {
+    // side stream + events of every local rank
+    for (int i = 0; i < c->n_local(); i++) {
+        b200zkp_ctx* ctx = c->ctx[i];
+        if (cudaSetDevice(ctx->device) != cudaSuccess) { (void)cudaGetLastError(); c->err = "cudaSetDevice failed"; return B200ZKP_ERR_CUDA; }
+        cudaStream_t s = nullptr;
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) {
+            (void)cudaGetLastError(); c->err = "cannot create the exchange stream"; return B200ZKP_ERR_CUDA;
+        }
+        c->xstream.push_back(s);
+        for (int e = 0; e < 2 + c->world; e++) {
+            cudaEvent_t ev = nullptr;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); c->err = "cannot create an event"; return B200ZKP_ERR_CUDA; }
+            c->ev.push_back(ev);
+        }
+    }
+    return 0;
+}
+
+static bool valid_world(int w) { return w >= 1 && w <= 256 && (w & (w - 1)) == 0; }
+
+extern "C" int b200zkp_comm_init_rank(b200zkp_ctx* ctx, const uint8_t id[B200ZKP_COMM_ID_BYTES], int rank, int world,
+                                      b200zkp_comm** out) {
+    if (!out) return B200ZKP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!id || !valid_world(world) || rank < 0 || rank >= world) BAD(ctx, "bad communicator shape (world must be a power of two)");
+    if (int rc = nccl_ready(&ctx->err)) return rc;
+    b200zkp_comm* c = new (std::nothrow) b200zkp_comm();
+    if (!c) return B200ZKP_ERR_OOM;
+    c->world = world;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    ncclComm_t nc = nullptr;
+    ncclResult_t r = nccl_api().CommInitRank(&nc, world, u, rank);
+    if (r != ncclSuccess) { int rc = nccl_fail(&ctx->err, "ncclCommInitRank", r); delete c; return rc; }
+    c->rank.push_back(rank); c->ctx.push_back(ctx); c->nc.push_back(nc);
+    if (int rc = comm_finish_init(c)) { ctx->err = c->err; b200zkp_comm_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" int b200zkp_comm_init_all(b200zkp_ctx* const* ctxs, int n, b200zkp_comm** out) {
+    if (!out) return B200ZKP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!ctxs || !valid_world(n)) return B200ZKP_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i]) return B200ZKP_ERR_BAD_ARG;
+        for (int j = 0; j < i; j++)
+            if (ctxs[j] == ctxs[i] || ctxs[j]->device == ctxs[i]->device) { ctxs[0]->err = "init_all needs one ctx per distinct device"; return B200ZKP_ERR_BAD_ARG; }
+    }
+    if (int rc = nccl_ready(&ctxs[0]->err)) return rc;
+    b200zkp_comm* c = new (std::nothrow) b200zkp_comm();
+    if (!c) return B200ZKP_ERR_OOM;
+    c->world = n;
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) { devs[i] = ctxs[i]->device; c->rank.push_back(i); c->ctx.push_back(ctxs[i]); }
+    c->nc.assign(n, nullptr);
+    ncclResult_t r = nccl_api().CommInitAll(c->nc.data(), n, devs.data());
+    if (r != ncclSuccess) { int rc = nccl_fail(&ctxs[0]->err, "ncclCommInitAll", r); c->nc.clear(); delete c; return rc; }
+    if (int rc = comm_finish_init(c)) { ctxs[0]->err = c->err; b200zkp_comm_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+extern "C" void b200zkp_comm_destroy(b200zkp_comm* c) {
+    if (!c) return;
+    for (int i = 0; i < c->n_local(); i++) {
+        cudaSetDevice(c->ctx[i]->device);
+        if (i < (int)c->xstream.size()) { cudaStreamSynchronize(c->xstream[i]); }
+        cudaStreamSynchronize(c->ctx[i]->stream);
+    }
+    for (size_t i = 0; i < c->nc.size(); i++) if (c->nc[i]) nccl_api().CommDestroy(c->nc[i]);
+    for (int i = 0; i < (int)c->xstream.size(); i++) { cudaSetDevice(c->ctx[i]->device); cudaStreamDestroy(c->xstream[i]); }
+    for (size_t e = 0; e < c->ev.size(); e++) {
+        cudaSetDevice(c->ctx[e / (2 + c->world)]->device);
+        cudaEventDestroy(c->ev[e]);
+    }
+    (void)cudaGetLastError();
+    delete c;
+}
+
+extern "C" const char* b200zkp_comm_last_error(const b200zkp_comm* c) { return c ? c->err.c_str() : "null comm"; }
+
+extern "C" int b200zkp_comm_shape(const b200zkp_comm* c, int32_t shape[3]) {
+    if (!c || !shape) return B200ZKP_ERR_BAD_ARG;
+    shape[0] = c->world; shape[1] = c->n_local(); shape[2] = c->rank[0];
+    return 0;
+}
+
+extern "C" int b200zkp_comm_set_exchange_group(b200zkp_comm* c, uint32_t peers_per_group) {
+    if (!c) return B200ZKP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->peers_per_group = peers_per_group;
+    return 0;
+}
+
+// runs f(local rank index) for every local rank: inline for one rank, one host thread per rank otherwise (each rank has its
+// own device, ctx, NCCL communicator and streams; NCCL point-to-point groups of different ranks must be issued concurrently)
+template <typename F>
+static int for_each_rank(b200zkp_comm* c, F f) {
+    const int n = c->n_local();
+    if (n == 1) {
+        int rc1 = f(0);
+        if (rc1) c->err = c->ctx[0]->err;
+        return rc1;
+    }
+    std::vector<int> rc(n, 0);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (int i = 0; i < n; i++) th.emplace_back([&, i] { rc[i] = f(i); });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rc[i]) { c->err = "rank " + std::to_string(c->rank[i]) + ": " + c->ctx[i]->err; return rc[i]; }
+    return 0;
+}
+
+static void sharded_release(b200zkp_sharded* sh) {
+    for (size_t i = 0; i < sh->r.size(); i++) {
+        b200zkp_ctx* ctx = sh->comm->ctx[i];
+        Guard g(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(sh->comm->xstream[i]);
+        ShardRank& s = sh->r[i];
+        dev_release(ctx, s.coeffs_all, s.coeffs_b); dev_release(ctx, s.lde, s.lde_b); dev_release(ctx, s.digests, s.digests_b);
+        dev_release(ctx, s.cap_local, s.cap_local_b); dev_release(ctx, s.cap, s.cap_b); dev_release(ctx, s.stage, s.stage_b);
+    }
+    delete sh;
+}
+
+extern "C" int b200zkp_sharded_create(b200zkp_comm* c, uint32_t n_log, uint32_t k, uint32_t rate_bits, uint32_t cap_height,
+                                      b200zkp_sharded** out) {
+    if (!out) return B200ZKP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!c) return B200ZKP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const u32 G = (u32)c->world;
+    if (k == 0) COMM_BAD(c, "empty polynomial batch");
+    if (rate_bits > 8 || n_log + rate_bits > 32) COMM_BAD(c, "n_log + rate_bits exceeds two-adicity");
+    if (cap_height > n_log + rate_bits) COMM_BAD(c, "cap_height exceeds log2(LDE size)");
+    if (G > (1u << rate_bits) || G > (1u << cap_height)) COMM_BAD(c, "world size must be <= 2^rate_bits and <= 2^cap_height");
+    b200zkp_sharded* sh = new (std::nothrow) b200zkp_sharded();
+    if (!sh) return B200ZKP_ERR_OOM;
+    sh->comm = c; sh->n_log = n_log; sh->k = k; sh->rate_bits = rate_bits; sh->cap_height = cap_height;
+    sh->kp = (k + G - 1) / G;
+    sh->bpr = (1u << rate_bits) / G;
+    sh->cpr = (1u << cap_height) / G;
+    u32 g_log = 0;
+    while ((1u << g_log) < G) g_log++;
+    sh->cap_height_local = cap_height - g_log;
+    const u64 n = (u64)1 << n_log;
+    sh->N_local = (n << rate_bits) / G;
+    sh->r.resize(c->n_local());
+    int rc = for_each_rank(c, [&](int i) -> int {
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        ShardRank& s = sh->r[i];
+        s.coeffs_b = (size_t)sh->kp * G * n * 8;
+        s.lde_b = (size_t)k * sh->N_local * 8;
+        s.digests_b = (size_t)2 * (sh->N_local - ((u64)1 << sh->cap_height_local)) * 32;
+        s.cap_local_b = (size_t)32 << sh->cap_height_local;
+        s.cap_b = (size_t)32 << cap_height;
+        TRY(dev_alloc(ctx, s.coeffs_b, (void**)&s.coeffs_all));
+        TRY(dev_alloc(ctx, s.lde_b, (void**)&s.lde));
+        TRY(dev_alloc(ctx, s.digests_b, (void**)&s.digests));
+        TRY(dev_alloc(ctx, s.cap_local_b, (void**)&s.cap_local));
+        TRY(dev_alloc(ctx, s.cap_b, (void**)&s.cap));
+        // columns past k of the last shard are never written by a transform: they travel as zeros
+        CUDA_TRY(ctx, cudaMemsetAsync(s.coeffs_all, 0, s.coeffs_b, ctx->stream));
+        return 0;
+    });
+    if (rc) { sharded_release(sh); return rc; }
+    *out = sh;
+    return 0;
+}
+
+extern "C" void b200zkp_sharded_free(b200zkp_sharded* sh) {
+    if (!sh) return;
+    std::lock_guard<std::mutex> lk(sh->comm->mu);
+    sharded_release(sh);
+}
+
+extern "C" int b200zkp_sharded_layout(const b200zkp_sharded* sh, int local, uint64_t lay[8]) {
+    if (!sh || !lay || local < 0 || local >= sh->comm->n_local()) return B200ZKP_ERR_BAD_ARG;
+    const u64 g = (u64)sh->comm->rank[local];
+    lay[0] = sh->kp;
+    lay[1] = std::min<u64>(sh->k, g * sh->kp);
+    lay[2] = std::min<u64>(sh->k, (g + 1) * sh->kp);
+    lay[3] = g * sh->bpr; lay[4] = (g + 1) * sh->bpr;
+    lay[5] = sh->N_local;
+    lay[6] = g * sh->cpr; lay[7] = (g + 1) * sh->cpr;
+    return 0;
+}
+
+// everything one rank does for one commit; asynchronous (returns after enqueueing)
+static int sharded_commit_rank(b200zkp_sharded* sh, int i, const u64* input, int on_device, int is_coeffs) {
+    b200zkp_comm* c = sh->comm;
+    b200zkp_ctx* ctx = c->ctx[i];
+    NcclApi& nc = nccl_api();
+    Guard guard(ctx);
+    ShardRank& s = sh->r[i];
+    const u32 G = (u32)c->world, g = (u32)c->rank[i];
+    const u64 n = (u64)1 << sh->n_log;
+    const u32 c0 = std::min(sh->k, g * sh->kp), c1 = std::min(sh->k, (g + 1) * sh->kp), kl = c1 - c0;
+    u64* mine = s.coeffs_all + (u64)g * sh->kp * n;
+    cudaStream_t main_s = ctx->stream, xs = c->xstream[i];
+    cudaEvent_t* ev = &c->ev[(size_t)i * (2 + G)];
+    if (kl && !input) BAD(ctx, "null input shard");
+
+    // ---- 1. this rank's columns -> coefficients (host input: chunked upload on the copy stream, overlapped)
+    if (kl) {
+        // scratch of the inverse transform: this rank's own columns of the (still unused) LDE shard; N_local >= n
+        u64* scratch = s.lde + (u64)c0 * sh->N_local;
+        if (on_device) {
+            if (is_coeffs) TRY(launch_canon_copy(ctx, input, mine, (u64)kl * n));
+            else TRY(dev_intt_locked(ctx, input, n, mine, n, scratch, sh->n_log, kl));
+        } else {
+            if (s.stage_b < (size_t)sh->kp * n * 8) {
+                dev_release(ctx, s.stage, s.stage_b);
+                s.stage = nullptr; s.stage_b = 0;
+                TRY(dev_alloc(ctx, (size_t)sh->kp * n * 8, (void**)&s.stage));
+                s.stage_b = (size_t)sh->kp * n * 8;
+            }
+            if (!ctx->stream2) {
+                int lo = 0, hi = 0;
+                CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+            }
+            const u32 n_chunks = (kl >= 4 && (size_t)kl * n * 8 >= ((size_t)16 << 20)) ? 4 : 1;
+            const u32 per = (kl + n_chunks - 1) / n_chunks;
+            cudaEvent_t e_free;
+            TRY(get_sync_event(ctx, 0, &e_free));
+            CUDA_TRY(ctx, cudaEventRecord(e_free, main_s));                  // the staging buffer may still feed the previous step
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, e_free, 0));
+            std::vector<cudaEvent_t> up(n_chunks);
+            for (u32 q = 0; q < n_chunks; q++) {
+                u32 a = std::min(kl, q * per), b = std::min(kl, (q + 1) * per);
+                TRY(get_sync_event(ctx, 1 + q, &up[q]));
+                if (b > a) CUDA_TRY(ctx, cudaMemcpyAsync(s.stage + (u64)a * n, input + (u64)a * n, (size_t)(b - a) * n * 8, cudaMemcpyHostToDevice, ctx->stream2));
+                CUDA_TRY(ctx, cudaEventRecord(up[q], ctx->stream2));
+            }
+            for (u32 q = 0; q < n_chunks; q++) {
+                u32 a = std::min(kl, q * per), b = std::min(kl, (q + 1) * per);
+                CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, up[q], 0));
+                if (b == a) continue;
+                if (is_coeffs) TRY(launch_canon_copy(ctx, s.stage + (u64)a * n, mine + (u64)a * n, (u64)(b - a) * n));
+                else TRY(dev_intt_locked(ctx, s.stage + (u64)a * n, n, mine + (u64)a * n, n, scratch + (u64)a * sh->N_local, sh->n_log, b - a));
+            }
+        }
+    }
+
+    // ---- 2. exchange of the coefficient shards in point-to-point groups on the exchange stream, and the coset transforms
+    //         of every shard as soon as it is here (own shard first)
+    auto lde_shard = [&](u32 src) -> int {
+        u32 a = std::min(sh->k, src * sh->kp), b = std::min(sh->k, (src + 1) * sh->kp);
+        if (b == a) return 0;
+        return dev_lde_locked(ctx, s.coeffs_all + (u64)a * n, n, s.lde + (u64)a * sh->N_local, sh->N_local, sh->n_log, b - a,
+                              sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr);
+    };
+    if (G > 1) {
+        CUDA_TRY(ctx, cudaEventRecord(ev[0], main_s));            // own coefficients ready; earlier readers of coeffs_all done
+        CUDA_TRY(ctx, cudaStreamWaitEvent(xs, ev[0], 0));
+    }
+    TRY(lde_shard(g));
+    if (G > 1) {
+        const u32 per_group = c->peers_per_group ? c->peers_per_group : (G - 1);
+        const size_t count = (size_t)sh->kp * n;
+        u32 gi = 0;
+        for (u32 d0 = 1; d0 < G; d0 += per_group, gi++) {
+            const u32 d1 = std::min(G, d0 + per_group);
+            NCCL_TRY(&ctx->err, nc.GroupStart());
+            for (u32 d = d0; d < d1; d++) {
+                const u32 to = (g + d) % G, from = (g + G - d) % G;
+                NCCL_TRY(&ctx->err, nc.Send(mine, count, ncclUint64, (int)to, c->nc[i], xs));
+                NCCL_TRY(&ctx->err, nc.Recv(s.coeffs_all + (u64)from * sh->kp * n, count, ncclUint64, (int)from, c->nc[i], xs));
+            }
+            NCCL_TRY(&ctx->err, nc.GroupEnd());
+            ctx->launches++;
+            CUDA_TRY(ctx, cudaEventRecord(ev[2 + gi], xs));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, ev[2 + gi], 0));
+            for (u32 d = d0; d < d1; d++) TRY(lde_shard((g + G - d) % G));
+        }
+    }
+
+    // ---- 3. this rank's leaves -> digests of its cap subtrees; 4. the cap
+    TRY(dev_merkle_locked(ctx, s.lde, /*row_stride=*/1, /*col_stride=*/sh->N_local, sh->k, sh->N_local, sh->cap_height_local,
+                          s.digests, s.cap_local));
+    if (G > 1) {
+        NCCL_TRY(&ctx->err, nc.AllGather(s.cap_local, s.cap, s.cap_local_b / 8, ncclUint64, c->nc[i], main_s));
+        ctx->launches++;
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.cap, s.cap_local, s.cap_b, cudaMemcpyDeviceToDevice, main_s));
+    }
+    return 0;
+}
+
+static int sharded_commit_locked(b200zkp_sharded* sh, const u64* const* inputs, int on_device, int is_coeffs, u64* cap_out) {
+    b200zkp_comm* c = sh->comm;
+    if (!inputs) COMM_BAD(c, "null inputs");
+    TRY(for_each_rank(c, [&](int i) -> int { return sharded_commit_rank(sh, i, inputs[i], on_device, is_coeffs); }));
+    if (cap_out) {
+        TRY(for_each_rank(c, [&](int i) -> int {
+            b200zkp_ctx* ctx = c->ctx[i];
+            Guard g(ctx);
+            if (i == 0) return d2h(ctx, cap_out, sh->r[0].cap, sh->r[0].cap_b);
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            return 0;
+        }));
+    }
+    return 0;
+}
+
+extern "C" int b200zkp_sharded_commit(b200zkp_sharded* sh, const uint64_t* const* inputs, int inputs_on_device, int is_coeffs,
+                                      uint64_t* cap_out) {
+    if (!sh) return B200ZKP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(sh->comm->mu);
+    return sharded_commit_locked(sh, (const u64* const*)inputs, inputs_on_device, is_coeffs, (u64*)cap_out);
+}
+
+extern "C" int b200zkp_sharded_commit_from_values(b200zkp_comm* c, const uint64_t* values, uint32_t n_log, uint32_t k,
+                                                  uint32_t rate_bits, uint32_t cap_height, uint64_t* cap_out,
+                                                  b200zkp_sharded** out) {
+    if (!c || !out) return B200ZKP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!values) { std::lock_guard<std::mutex> lk(c->mu); COMM_BAD(c, "null values"); }
+    b200zkp_sharded* sh = nullptr;
+    TRY(b200zkp_sharded_create(c, n_log, k, rate_bits, cap_height, &sh));
+    std::lock_guard<std::mutex> lk(c->mu);
+    const u64 n = (u64)1 << n_log;
+    std::vector<const u64*> in(c->n_local());
+    for (int i = 0; i < c->n_local(); i++) in[i] = (const u64*)values + std::min<u64>(k, (u64)c->rank[i] * sh->kp) * n;
+    int rc = sharded_commit_locked(sh, in.data(), /*on_device=*/0, /*is_coeffs=*/0, (u64*)cap_out);
+    if (!rc && !cap_out)   // the caller's host matrix must stay valid only for the duration of this call
+        rc = for_each_rank(c, [&](int i) -> int { Guard g(c->ctx[i]); CUDA_TRY(c->ctx[i], cudaStreamSynchronize(c->ctx[i]->stream)); return 0; });
+    if (rc) { sharded_release(sh); return rc; }
+    *out = sh;
+    return 0;
+}
+
+extern "C" int b200zkp_sharded_synchronize(b200zkp_sharded* sh) {
+    if (!sh) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_comm* c = sh->comm;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return for_each_rank(c, [&](int i) -> int {
+        Guard g(c->ctx[i]);
+        CUDA_TRY(c->ctx[i], cudaStreamSynchronize(c->ctx[i]->stream));
+        return 0;
+    });
+}
+
+extern "C" int b200zkp_sharded_device_ptrs(b200zkp_sharded* sh, int local, const uint64_t** coeffs, const uint64_t** lde,
+                                           const uint64_t** digests, const uint64_t** cap) {
+    if (!sh || local < 0 || local >= sh->comm->n_local()) return B200ZKP_ERR_BAD_ARG;
+    const ShardRank& s = sh->r[local];
+    if (coeffs) *coeffs = (const uint64_t*)s.coeffs_all;
+    if (lde) *lde = (const uint64_t*)s.lde;
+    if (digests) *digests = (const uint64_t*)s.digests;
+    if (cap) *cap = (const uint64_t*)s.cap;
+    return 0;
+}
+
+extern "C" int b200zkp_sharded_rows(b200zkp_sharded* sh, const uint64_t* idx, uint64_t n_idx, uint64_t* rows,
+                                    uint64_t* siblings) {
+    if (!sh) return B200ZKP_ERR_BAD_ARG;
+    b200zkp_comm* c = sh->comm;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!n_idx) return 0;
+    if (!idx) COMM_BAD(c, "null index list");
+    const u64 N = sh->N_local * (u64)c->world;
+    for (u64 q = 0; q < n_idx; q++) if (idx[q] >= N) COMM_BAD(c, "leaf index out of range");
+    u32 lg = 0;
+    while (((u64)1 << lg) < sh->N_local) lg++;
+    const u32 depth = lg - sh->cap_height_local;
+    const u32 k = sh->k;
+    const bool multi_process = c->n_local() < c->world;
+    // every local rank answers the indices it owns (compacted list -> gather -> scatter on the host); with one process
+    // per GPU the answers of the other ranks arrive through one all-reduce (sum with zeros) of the small result buffers
+    std::vector<std::vector<u64>> lrows(c->n_local()), lsib(c->n_local());
+    std::vector<std::vector<u64>> lq(c->n_local());
+    TRY(for_each_rank(c, [&](int i) -> int {
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        const u64 rk = (u64)c->rank[i];
+        std::vector<u64> local_idx;
+        for (u64 q = 0; q < n_idx; q++)
+            if (idx[q] / sh->N_local == rk) { lq[i].push_back(q); local_idx.push_back(idx[q] % sh->N_local); }
+        if (local_idx.empty()) return 0;
+        if (rows) lrows[i].resize(local_idx.size() * k);
+        if (siblings && depth) lsib[i].resize(local_idx.size() * depth * 4);
+        return gather_locked(ctx, sh->r[i].lde, sh->N_local, k, sh->r[i].digests, depth, local_idx.data(), local_idx.size(),
+                             rows ? lrows[i].data() : nullptr, (siblings && depth) ? lsib[i].data() : nullptr);
+    }));
+    if (rows) memset(rows, 0, (size_t)n_idx * k * 8);
+    if (siblings && depth) memset(siblings, 0, (size_t)n_idx * depth * 32);
+    for (int i = 0; i < c->n_local(); i++)
+        for (size_t j = 0; j < lq[i].size(); j++) {
+            if (rows) memcpy(rows + lq[i][j] * k, lrows[i].data() + j * k, (size_t)k * 8);
+            if (siblings && depth) memcpy(siblings + lq[i][j] * depth * 4, lsib[i].data() + j * depth * 4, (size_t)depth * 32);
+        }
+    if (multi_process) {
+        b200zkp_ctx* ctx = c->ctx[0];
+        Guard g(ctx);
+        NcclApi& nc = nccl_api();
+        const size_t rows_w = rows ? (size_t)n_idx * k : 0, sib_w = (siblings && depth) ? (size_t)n_idx * depth * 4 : 0;
+        const size_t total = rows_w + sib_w;
+        if (total) {
+            void* d = nullptr;
+            TRY(dev_alloc(ctx, total * 8, &d));
+            int rc = 0;
+            if (rows_w) rc = h2d(ctx, d, rows, rows_w * 8);
+            if (!rc && sib_w) rc = h2d(ctx, (u64*)d + rows_w, siblings, sib_w * 8);
+            if (!rc) {
+                ncclResult_t r = nc.AllReduce(d, d, total, ncclUint64, ncclSum, c->nc[0], ctx->stream);
+                if (r != ncclSuccess) rc = nccl_fail(&ctx->err, "ncclAllReduce", r);
+                ctx->launches++;
+            }
+            if (!rc && rows_w) rc = d2h(ctx, rows, d, rows_w * 8);
+            if (!rc && sib_w) rc = d2h(ctx, siblings, (u64*)d + rows_w, sib_w * 8);
+            if (rc) cudaStreamSynchronize(ctx->stream);
+            dev_release(ctx, d, total * 8);
+            if (rc) { c->err = ctx->err; return rc; }
+        }
+    }
+    return 0;
+}

@@ -1,11 +1,13 @@
 """Device-resident entry points: torch tensors in HBM in, torch tensors out, no host copies.
 
-torch is used for what the north star allows it for — device memory, streams and torch.distributed (NCCL);
-every transform and hash is one of this repo's CUDA kernels behind the C ABI (`b200zkp_dev_*`).
+torch is used for what the north star allows it for — device memory and streams; every transform and hash is one of this
+repo's CUDA kernels behind the C ABI (`b200zkp_dev_*`), and the multi-GPU exchange is NCCL called from the C library
+(`b200zkp_comm_*`, `b200zkp_sharded_*`; csrc/sharded.inl), not torch.distributed.
 
 Multi-GPU partitioning (one process per GPU):
   1. values are sharded by COLUMN: rank g inverse-transforms columns [g*kp, (g+1)*kp), kp = ceil(k/G)
-  2. one all-gather of the coefficients (NCCL over NVLink; k padded to G*kp with zero columns)
+  2. the coefficient shards are exchanged in NCCL point-to-point groups (k padded to G*kp with zero columns); the coset
+     transforms of the shards already received overlap the rest of the exchange
   3. the LDE is sharded by LEAF RANGE: rank g owns leaves [g*N/G, (g+1)*N/G) = 2^r/G whole cosets of the
      same coefficients, so the coset NTTs, the leaf hashing and the 2^h/G cap subtrees are all local
   4. one all-gather of the 2^h x 32 B cap digests.
@@ -88,135 +90,164 @@ def commit_device(ctx: Context, inp, rate_bits: int, cap_height: int, out: Optio
     return out
 
 
+def _dev_view(ptr: int, shape, device_index: int):
+    """torch int64 view of `shape` words of device memory owned by the C library (valid while its handle lives)"""
+    import torch
+
+    class _View:
+        pass
+    v = _View()
+    v.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(v, device=torch.device("cuda", device_index))
+
+
+class Comm:
+    """b200zkp_comm: the ranks of one partitioned commitment.  NCCL is driven from the C library (csrc/sharded.inl);
+    torch.distributed is at most the out-of-band channel that hands rank 0's NCCL id to the other processes."""
+
+    def __init__(self, ctxs, handle):
+        self.ctxs, self._h = list(ctxs), handle
+        self._lib = self.ctxs[0]._lib
+        shape = (C.c_int32 * 3)()
+        self._lib.b200zkp_comm_shape(self._h, shape)
+        self.world, self.n_local, self.rank0 = int(shape[0]), int(shape[1]), int(shape[2])
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.lib().b200zkp_comm_unique_id(buf)
+        if rc != 0:
+            raise _lib.B200ZkpError(rc, "b200zkp_comm_unique_id failed (is libnccl.so.2 available?)")
+        return bytes(buf)
+
+    @classmethod
+    def init_rank(cls, ctx: Context, unique_id: bytes, rank: int, world: int) -> "Comm":
+        """one process per GPU: every process calls this with the same id (b200zkp_comm_init_rank)"""
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        ctx.check(ctx._lib.b200zkp_comm_init_rank(ctx._h, buf, rank, world, C.byref(h)))
+        return cls([ctx], h)
+
+    @classmethod
+    def from_torch_distributed(cls, ctx: Context, group=None) -> "Comm":
+        """one process per GPU under torchrun: rank 0's id travels through the (gloo or nccl) process group"""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls.init_rank(ctx, box[0], rank, world)
+
+    @classmethod
+    def init_all(cls, ctxs) -> "Comm":
+        """ONE process drives len(ctxs) GPUs (b200zkp_comm_init_all): ctxs[i] is rank i"""
+        ctxs = list(ctxs)
+        arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        h = C.c_void_p()
+        ctxs[0].check(ctxs[0]._lib.b200zkp_comm_init_all(arr, len(ctxs), C.byref(h)))
+        return cls(ctxs, h)
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.b200zkp_comm_last_error(self._h).decode() or self._lib.b200zkp_last_error(self.ctxs[0]._h).decode()
+            raise _lib.B200ZkpError(rc, msg)
+
+    def set_exchange_group(self, peers_per_group: int):
+        self.check(self._lib.b200zkp_comm_set_exchange_group(self._h, peers_per_group))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200zkp_comm_destroy(self._h)
+            self._h = None
+
+
 class ShardedCommitment:
-    """One rank's share of a commitment partitioned over `world` GPUs (see module docstring)."""
+    """One commitment partitioned over the ranks of a Comm (b200zkp_sharded; see the module docstring).  With one process
+    per GPU this object holds that process's rank; with Comm.init_all it holds every rank (index them with `local`)."""
 
-    def __init__(self, ctx: Context, n_log: int, k: int, rate_bits: int, cap_height: int, rank: int, world: int,
-                 device, group=None):
-        import torch
-        lay = shard_layout(n_log, k, rate_bits, cap_height, rank, world)
-        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+    def __init__(self, comm: Comm, n_log: int, k: int, rate_bits: int, cap_height: int):
+        self.comm, self._lib = comm, comm._lib
         self.n_log, self.k, self.rate_bits, self.cap_height = n_log, k, rate_bits, cap_height
+        shard_layout(n_log, k, rate_bits, cap_height, 0, comm.world)          # plonky2-style argument errors as ValueError
+        h = C.c_void_p()
+        comm.check(self._lib.b200zkp_sharded_create(comm._h, n_log, k, rate_bits, cap_height, C.byref(h)))
+        self._h = h
+        self.layouts = [shard_layout(n_log, k, rate_bits, cap_height, comm.rank0 + i, comm.world) for i in range(comm.n_local)]
+        lay = self.layouts[0]
+        self.kp, self.N_local, self.cap_height_local = lay["kp"], lay["N_local"], lay["cap_height_local"]
+        self.world = comm.world
         n = 1 << n_log
-        self.kp = lay["kp"]                                     # columns per rank (padded)
-        self.blocks_per_rank = lay["block_end"] - lay["block_begin"]
-        self.N_local = lay["N_local"]
-        self.cap_height_local = lay["cap_height_local"]
-        self.col_begin, self.col_end = lay["col_begin"], lay["col_end"]
-        self.coeffs_all = torch.zeros((self.kp * world, n), dtype=torch.int64, device=device)
-        self.lde = torch.empty((k, self.N_local), dtype=torch.int64, device=device)
-        self.digests = torch.empty((max(2 * (self.N_local - (1 << self.cap_height_local)), 1), 4),
-                                   dtype=torch.int64, device=device)
-        self.cap_local = torch.empty((1 << self.cap_height_local, 4), dtype=torch.int64, device=device)
-        self.cap = torch.empty((1 << cap_height, 4), dtype=torch.int64, device=device)
+        self._views = []
+        for i in range(comm.n_local):
+            p = [C.c_void_p() for _ in range(4)]
+            comm.check(self._lib.b200zkp_sharded_device_ptrs(self._h, i, *[C.byref(x) for x in p]))
+            dev = comm.ctxs[i].device
+            nd = max(2 * (self.N_local - (1 << self.cap_height_local)), 1)
+            self._views.append(dict(
+                coeffs_all=_dev_view(p[0].value, (self.kp * comm.world, n), dev),
+                lde=_dev_view(p[1].value, (k, self.N_local), dev),
+                digests=_dev_view(p[2].value, (nd, 4), dev) if p[2].value else None,
+                cap=_dev_view(p[3].value, (1 << cap_height, 4), dev)))
 
-    @property
-    def local_columns(self) -> int:
-        return max(self.col_end - self.col_begin, 0)
+    def local(self, i: int = 0) -> dict:
+        """device views of local rank i: coeffs_all (G*kp, n), lde (k, N_local), digests, cap"""
+        return self._views[i]
 
-    def run_from_host(self, host_values, staging, n_chunks: int = 4):
-        """End-to-end variant: `host_values` is this rank's pinned (kp, n) column shard, `staging` a (kp, n) device
-        tensor.  Column chunks cross PCIe on a side stream while the previous chunk is inverse-transformed."""
-        import torch
-        ctx, lib = self.ctx, self.ctx._lib
+    coeffs_all = property(lambda self: self._views[0]["coeffs_all"])
+    lde = property(lambda self: self._views[0]["lde"])
+    digests = property(lambda self: self._views[0]["digests"])
+    cap = property(lambda self: self._views[0]["cap"])
+
+    def _ptrs(self, tensors):
+        if not isinstance(tensors, (list, tuple)):
+            tensors = [tensors]
+        if len(tensors) != self.comm.n_local:
+            raise ValueError("one input per local rank")
         n = 1 << self.n_log
-        kl = self.local_columns
-        mine = self.coeffs_all[self.rank * self.kp:(self.rank + 1) * self.kp]
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(device=staging.device)
-        main = torch.cuda.current_stream()
-        self._copy_stream.wait_stream(main)          # staging may still be read by the previous step
-        per = max(1, (kl + n_chunks - 1) // n_chunks)
-        events = []
-        for c0 in range(0, kl, per):
-            c1 = min(kl, c0 + per)
-            with torch.cuda.stream(self._copy_stream):
-                staging[c0:c1].copy_(host_values[c0:c1], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-            events.append((c0, c1, ev))
-        for c0, c1, ev in events:
-            main.wait_event(ev)
-            # scratch: this chunk's share of the (still unused) LDE buffer
-            ctx.check(lib.b200zkp_dev_intt(ctx._h, C.c_void_p(staging.data_ptr() + 8 * n * c0), n,
-                                           C.c_void_p(mine.data_ptr() + 8 * n * c0), n,
-                                           C.c_void_p(self.lde.data_ptr() + 8 * n * c0), self.n_log, c1 - c0))
-        return self._finish()
+        for t, lay in zip(tensors, self.layouts):
+            kl = lay["col_end"] - lay["col_begin"]
+            if t is None:
+                if kl:
+                    raise ValueError("missing input shard")
+                continue
+            if t.element_size() != 8 or not t.is_contiguous() or t.shape[-1] != n or t.shape[0] < kl:
+                raise ValueError("input shard must be a contiguous (>= local columns, n) 64-bit tensor")
+        return (C.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors]), tensors
 
     def run(self, values_local, is_coeffs: bool = False):
-        """values_local: (kp, n) device tensor, this rank's columns (rows past local_columns ignored)."""
-        ctx, lib = self.ctx, self.ctx._lib
-        n = 1 << self.n_log
-        mine = self.coeffs_all[self.rank * self.kp:(self.rank + 1) * self.kp]
-        kl = self.local_columns
-        if kl:
-            if is_coeffs:
-                mine[:kl].copy_(values_local[:kl])
-            else:
-                # the LDE buffer is free until step 3: use it as the transform scratch
-                ctx.check(lib.b200zkp_dev_intt(ctx._h, _ptr(values_local), n, _ptr(mine), n, _ptr(self.lde),
-                                               self.n_log, kl))
-        return self._finish()
-
-    def _finish(self):
-        """all-gather of the coefficients, this rank's coset blocks, its cap subtrees, all-gather of the cap."""
-        import torch
-        import torch.distributed as dist
-        ctx, lib = self.ctx, self.ctx._lib
-        n = 1 << self.n_log
-        mine = self.coeffs_all[self.rank * self.kp:(self.rank + 1) * self.kp]
-        b0 = self.rank * self.blocks_per_rank
-        b1 = b0 + self.blocks_per_rank
-        N_loc = self.N_local
-
-        def lde_cols(c0, c1):
-            if c1 > c0:
-                ctx.check(lib.b200zkp_dev_lde(ctx._h, C.c_void_p(self.coeffs_all.data_ptr() + 8 * n * c0), n,
-                                              C.c_void_p(self.lde.data_ptr() + 8 * N_loc * c0), N_loc, self.n_log,
-                                              c1 - c0, self.rate_bits, b0, b1))
-
-        if self.world > 1:
-            # the all-gather of the other ranks' coefficients (NCCL, its own stream) overlaps the coset transforms of
-            # the columns this rank already holds
-            work = dist.all_gather_into_tensor(self.coeffs_all, mine, group=self.group, async_op=True)
-            lde_cols(self.col_begin, self.col_end)
-            work.wait()
-            lde_cols(0, self.col_begin)
-            lde_cols(self.col_end, self.k)
-        else:
-            lde_cols(0, self.k)
-        ctx.check(lib.b200zkp_dev_merkle(ctx._h, _ptr(self.lde), 1, N_loc, self.k, N_loc, self.cap_height_local,
-                                         _ptr(self.digests), _ptr(self.cap_local)))
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.cap, self.cap_local, group=self.group)
-        else:
-            self.cap.copy_(self.cap_local)
+        """values_local: this rank's (>= local columns, n) DEVICE tensor (a list, one per local rank, after init_all).
+        Asynchronous on the ctx streams; returns the device view of the cap."""
+        arr, keep = self._ptrs(values_local)
+        self.comm.check(self._lib.b200zkp_sharded_commit(self._h, arr, 1, int(is_coeffs), None))
         return self.cap
 
+    def run_from_host(self, host_values, is_coeffs: bool = False, cap_out=None):
+        """host_values: pinned (>= local columns, n) HOST tensor(s); the upload is chunked and overlaps the inverse
+        transforms.  cap_out: optional pinned (2^h, 4) host tensor — then the call returns when the cap is in it."""
+        arr, keep = self._ptrs(host_values)
+        self.comm.check(self._lib.b200zkp_sharded_commit(self._h, arr, 0, int(is_coeffs),
+                                                         C.c_void_p(cap_out.data_ptr()) if cap_out is not None else None))
+        return self.cap
+
+    def synchronize(self):
+        self.comm.check(self._lib.b200zkp_sharded_synchronize(self._h))
+
     def rows(self, indices):
-        """MerkleTree::get + MerkleTree::prove for GLOBAL leaf indices of the sharded commitment (what the FRI query rounds
-        open): the rank that owns a leaf gathers its row and sibling path from its shard, one all-reduce (sum with zeros from
-        the other ranks) hands every rank the full answer.  Returns (rows (q, k), siblings (q, log2 N - cap_height, 4))."""
-        import torch
-        import torch.distributed as dist
-        ctx, lib = self.ctx, self.ctx._lib
-        dev = self.lde.device
-        idx = torch.as_tensor(list(indices), dtype=torch.int64, device=dev)
-        q = idx.numel()
+        """MerkleTree::get + MerkleTree::prove for GLOBAL leaf indices (b200zkp_sharded_rows; collective).
+        Returns numpy (rows (q, k), siblings (q, log2 N - cap_height, 4))."""
+        import numpy as np
+        idx = np.ascontiguousarray(np.asarray(list(indices), dtype=np.uint64))
         depth = log2_strict(self.N_local) - self.cap_height_local
-        rows = torch.zeros((q, self.k), dtype=torch.int64, device=dev)
-        sib = torch.zeros((q, depth, 4), dtype=torch.int64, device=dev)
-        if q == 0:
-            return rows, sib
-        if int(idx.min()) < 0 or int(idx.max()) >= self.N_local * self.world:
+        rows = np.zeros((idx.size, self.k), np.uint64)
+        sib = np.zeros((idx.size, depth, 4), np.uint64)
+        if idx.size and int(idx.max()) >= self.N_local * self.world:
             raise ValueError("leaf index out of range")
-        mine = (idx // self.N_local) == self.rank
-        local = torch.where(mine, idx % self.N_local, torch.zeros_like(idx)).contiguous()
-        ctx.check(lib.b200zkp_dev_gather(ctx._h, _ptr(self.lde), self.N_local, self.k, _ptr(self.digests), self.N_local,
-                                         self.cap_height_local, _ptr(local), q, _ptr(rows), _ptr(sib) if depth else None))
-        rows *= mine[:, None]
-        sib *= mine[:, None, None]
-        if self.world > 1:
-            dist.all_reduce(rows, group=self.group)
-            dist.all_reduce(sib, group=self.group)
+        self.comm.check(self._lib.b200zkp_sharded_rows(self._h, idx.ctypes.data_as(C.c_void_p), idx.size,
+                                                       rows.ctypes.data_as(C.c_void_p),
+                                                       sib.ctypes.data_as(C.c_void_p) if depth else None))
         return rows, sib
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._views = []
+            self._lib.b200zkp_sharded_free(self._h)
+            self._h = None

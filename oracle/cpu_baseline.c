@@ -189,6 +189,8 @@ static void fill_subtree(gl_t* digests, size_t digests_len, const uint64_t* leav
 }
 
 int cpub_threads(void) { return omp_get_max_threads(); }
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the bench sets the team size explicitly */
+void cpub_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* times[5] = { ifft, lde, transpose+bitrev, merkle, total } seconds */
 int cpub_commit(const uint64_t* in, int is_coeffs, uint32_t n_log, uint32_t k, uint32_t rate_bits,

@@ -229,6 +229,7 @@ def baseline_lib():
                                       _u64p, _u64p, _u64p, _u64p, C.POINTER(C.c_double)]
         _blib.cpub_commit.restype = C.c_int
         _blib.cpub_threads.restype = C.c_int
+        _blib.cpub_set_threads.argtypes = [C.c_int]
         _blib.cpub_permute.argtypes = [_u64p]
         _blib.cpub_leaf_hash_rows.argtypes = [_u64p, C.c_uint64, C.c_uint32, _u64p]
         _blib.cpub_leaf_hash_rows.restype = C.c_double
@@ -256,3 +257,9 @@ def baseline_commit(inp, rate_bits: int, cap_height: int, is_coeffs: bool = Fals
 
 def baseline_threads() -> int:
     return int(baseline_lib().cpub_threads())
+
+
+def baseline_set_threads(n: int) -> int:
+    """OpenMP team size of the CPU baseline (torchrun exports OMP_NUM_THREADS=1 to its workers); returns the new size"""
+    baseline_lib().cpub_set_threads(int(n))
+    return baseline_threads()
