@@ -280,10 +280,17 @@ def test_device_api_and_single_rank_shard(z, ctx, oracle):
     assert (out.coeffs.cpu().numpy().view(np.uint64) == ref["coeffs"]).all()
     assert (out.lde.cpu().numpy().view(np.uint64).T == ref["leaves"]).all()
     assert (out.digests.cpu().numpy().view(np.uint64) == ref["digests"]).all()
-    sh = D.ShardedCommitment(tctx, n_log, k, r, h, 0, 1, vt.device)
+    # the partitioned path with a communicator of one rank (b200zkp_comm_init_all over one ctx)
+    comm = D.Comm.init_all([tctx])
+    sh = D.ShardedCommitment(comm, n_log, k, r, h)
     cap = sh.run(vt)
     tctx.synchronize()
     assert (cap.cpu().numpy().view(np.uint64) == ref["cap"]).all()
+    assert (sh.lde.cpu().numpy().view(np.uint64).T == ref["leaves"]).all()
+    rows, sib = sh.rows([0, 77, (1 << (n_log + r)) - 1])
+    assert (rows[1] == ref["leaves"][77]).all() and oracle.merkle_verify(rows[1], 77, sib[1], ref["cap"])
+    sh.close()
+    comm.close()
     # leaf-range shards computed one at a time on one GPU must tile the full commitment (world = 4 layout)
     for rank in range(4):
         lay = D.shard_layout(n_log, k, r, h, rank, 4)
