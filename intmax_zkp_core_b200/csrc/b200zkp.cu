@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -49,6 +50,12 @@ struct b200zkp_ctx {
     std::map<u64, u64*> coset_scale;                    // (n_log<<8 | rate_bits) -> [2^rate_bits][n] shift powers
     std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
     std::map<std::pair<u64, u32>, u64*> power_scale;    // (shift, bits) -> shift^i, i < 2^bits (FRI layer cosets)
+    // second-generation passes (ntt_ct_kernels.cuh): block-twiddle tables Z, [n_blk][n] each
+    std::map<u64, u64*> ztab_lde;                       // (n_log<<8 | rate_bits) -> forward transform on every leaf block's coset
+    std::map<u32, u64*> ztab_inv;                       // n_log -> inverse transform (s = 1), last level carries n^-1
+    bool ntt_ct = true;                                 // B200ZKP_NTT_CT=0: every transform through ntt_kernels.cuh (A/B testing)
+    bool ntt_tma = true;                                // B200ZKP_NTT_TMA=0: the new passes stage their tiles with plain loads
+    u32 ct_smem_set = 0;                                // kernels whose dynamic shared memory limit has been raised on this device
     u64* round_add = nullptr;                           // poseidon_tables::ROUND_ADD in global memory (latency-form kernels)
     std::multimap<size_t, void*> pool;                  // cached device allocations (dev_release), at most pool_max_bytes
     size_t pool_bytes = 0;
@@ -298,6 +305,132 @@ static int get_coset_scale(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const u64
     return 0;
 }
 
+// ---- second-generation passes: Z tables, tensor maps, launches
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            p = nullptr;
+        }
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+
+// 5-D view (c, row, a, coset block, column) of one side of a strided pass; box = one tile [2^B rows][T]
+static bool encode_tile_map(CUtensorMap* map, const u64* base, u32 B, u32 S, u32 C_log, u32 n_blk, u64 blk_stride, u32 ncols,
+                            u64 col_stride) {
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const u64 C = (u64)1 << C_log, rows = (u64)1 << B, A = (u64)1 << S;
+    cuuint64_t dims[5] = {C, rows, A, n_blk ? n_blk : 1, ncols};
+    cuuint64_t strides[4] = {C * 8, C * rows * 8, (blk_stride ? blk_stride : C * rows * A) * 8, col_stride * 8};
+    cuuint32_t box[5] = {(cuuint32_t)(ntc::TILE >> B), (cuuint32_t)rows, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <int B>
+static int launch_ct_b(b200zkp_ctx* ctx, int kind, const ntc::PassParams& p, u64 grid, const CUtensorMap& tm_in, const CUtensorMap& tm_out) {
+    const void* fn = nullptr;
+    u32 smem = 0;
+    switch (kind) {
+        case ntc::KIND_STRIDED: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_STRIDED>; smem = ntc::StridedSmem<B, false>::bytes; break;
+        case ntc::KIND_STRIDED_LOOP: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_STRIDED_LOOP>; smem = ntc::StridedSmem<B, true>::bytes; break;
+        case ntc::KIND_FINAL_INPLACE: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_FINAL_INPLACE>; smem = ntc::FinalSmem<B>::bytes; break;
+        default: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_FINAL_NATURAL>; smem = ntc::FinalSmem<B>::bytes; break;
+    }
+    const u32 bit = 1u << ((B - ntc::MIN_BITS) * 4 + kind);
+    if (smem > 48 * 1024 && !(ctx->ct_smem_set & bit)) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->ct_smem_set |= bit;
+    }
+    void* args[3] = {(void*)&p, (void*)&tm_in, (void*)&tm_out};
+    CUDA_TRY(ctx, cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(ntc::THREADS), args, smem, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan) {
+    for (u32 pi = 0; pi < plan.n_passes; pi++) {
+        ntc::PassParams& p = plan.pass[pi];
+        const u32 B = plan.bits[pi];
+        const int kind = plan.kind[pi];
+        if (plan.grid[pi] > 0x7fffffffull) BAD(ctx, "transform too large for one launch");
+        alignas(64) CUtensorMap tm_in, tm_out;
+        memset(&tm_in, 0, sizeof tm_in); memset(&tm_out, 0, sizeof tm_out);
+        if (p.use_tma) {
+            // the staged side of a coset loop has a single block; every other side walks the blocks of its buffer
+            const bool loop = kind == ntc::KIND_STRIDED_LOOP;
+            if (!ctx->ntt_tma ||
+                !encode_tile_map(&tm_in, p.in, B, p.S, p.C_log, loop ? 1 : p.n_blk, loop ? 0 : p.in_blk_stride, p.ncols, p.in_col_stride) ||
+                !encode_tile_map(&tm_out, p.out, B, p.S, p.C_log, p.n_blk, p.out_blk_stride, p.ncols, p.out_col_stride))
+                p.use_tma = 0;
+        }
+        switch (B) {
+            case 5: TRY(launch_ct_b<5>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
+            case 6: TRY(launch_ct_b<6>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
+            case 7: TRY(launch_ct_b<7>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
+            case 8: TRY(launch_ct_b<8>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
+            default: BAD(ctx, "internal: bad pass width");
+        }
+    }
+    return 0;
+}
+
+// Z tables of `n_blk` cosets s_b <w_n>: shifts[b] on the host; built on the device and kept for the life of the ctx
+static int build_ztab(b200zkp_ctx* ctx, u32 n_log, int dir, const std::vector<u64>& shifts, u64 last_scale, u64** out) {
+    TwoLevel tw{};
+    TRY(get_tw(ctx, dir, n_log, &tw));
+    std::vector<u64> spow((size_t)shifts.size() * n_log);
+    for (size_t b = 0; b < shifts.size(); b++) {
+        u64 x = shifts[b] % hostgl::P;
+        for (u32 e = 0; e < n_log; e++) { spow[b * n_log + e] = x; x = hostgl::mul(x, x); }
+    }
+    u64* d_spow = nullptr;
+    TRY(upload(ctx, spow, &d_spow));
+    u64* d = nullptr;
+    TRY(table_alloc(ctx, (u64)shifts.size() << n_log, &d));
+    const u64 n = (u64)1 << n_log;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)shifts.size());
+    ntc::build_ztab_kernel<<<grid, 256, 0, ctx->stream>>>(d, n_log, d_spow, tw.lo, tw.hi, tw.lo_bits, last_scale);
+    LAUNCH_CHECK(ctx);
+    *out = d;
+    return 0;
+}
+
+static int get_ztab_lde(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const u64** out) {
+    const u64 key = ((u64)n_log << 8) | rate_bits;
+    auto it = ctx->ztab_lde.find(key);
+    if (it == ctx->ztab_lde.end()) {
+        std::vector<u64> shifts;
+        for (u32 b = 0; b < (1u << rate_bits); b++) shifts.push_back(hostgl::coset_shift_of_block(n_log, rate_bits, b));
+        u64* d = nullptr;
+        TRY(build_ztab(ctx, n_log, 0, shifts, 0, &d));
+        it = ctx->ztab_lde.emplace(key, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
+static int get_ztab_inv(b200zkp_ctx* ctx, u32 n_log, const u64** out) {
+    auto it = ctx->ztab_inv.find(n_log);
+    if (it == ctx->ztab_inv.end()) {
+        u64* d = nullptr;
+        TRY(build_ztab(ctx, n_log, 1, std::vector<u64>{1}, hostgl::inv(((u64)1 << n_log) % hostgl::P), &d));
+        it = ctx->ztab_inv.emplace(n_log, d).first;
+    }
+    *out = it->second;
+    return 0;
+}
+
 // One multi-pass transform over `ncols` columns, for `n_blk` blocks at once (blockIdx.y: the coset blocks of an
 // LDE share the input and differ in scale table and output offset).
 //   bitrev_out: in-place DIF order (LDE leaf order); else natural order (needs scratch when P > 1)
@@ -366,6 +499,8 @@ extern "C" int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out) {
         }
         ctx->own_stream = true;
     }
+    if (const char* e = getenv("B200ZKP_NTT_CT")) ctx->ntt_ct = atoi(e) != 0;
+    if (const char* e = getenv("B200ZKP_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
     size_t mem_free = 0, mem_total = 0;
     if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total) ctx->pool_max_bytes = mem_total / 8;
     else (void)cudaGetLastError();
@@ -464,6 +599,19 @@ extern "C" void b200zkp_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 static int dev_intt_locked(b200zkp_ctx* ctx, const u64* values, u64 in_stride, u64* coeffs, u64 out_stride,
                            u64* scratch, u32 n_log, u32 k) {
+    if (ctx->ntt_ct && scratch && k) {
+        // 2^11 points and more: block-twiddle passes (ntt_ct_kernels.cuh), natural order out through the scratch buffer
+        const u64* z = nullptr;
+        ntc::Plan plan;
+        if (ntc::covers(n_log)) {
+            TRY(get_ztab_inv(ctx, n_log, &z));
+            if (ntc::make_plan(&plan, values, in_stride, coeffs, out_stride, scratch, n_log, k, 1, 0, /*natural_out=*/true, z, 0,
+                               hostgl::inv(((u64)1 << n_log) % hostgl::P), ctx->ntt_tma)) {
+                StageTimer tm(ctx, B200ZKP_STAGE_INTT);
+                return run_ct_plan(ctx, plan);
+            }
+        }
+    }
     StageTimer tm(ctx, B200ZKP_STAGE_INTT);
     return run_transform(ctx, values, in_stride, coeffs, out_stride, scratch, n_log, k, /*dir=*/1,
                          /*bitrev_out=*/false, nullptr, 0, /*inverse_scale=*/true, /*canon_in=*/true);
@@ -481,12 +629,23 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
                           u32 n_log, u32 k, u32 rate_bits, u32 b0, u32 b1) {
     if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "rate_bits / n_log out of range");
     if (b0 > b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
+    u64 n = (u64)1 << n_log;
+    if (ctx->ntt_ct && k && b1 > b0 && ntc::covers(n_log)) {
+        // block-twiddle passes: the coset shift lives in the twiddles, the first pass stages a coefficient tile once for all blocks
+        const u64* z = nullptr;
+        TRY(get_ztab_lde(ctx, n_log, rate_bits, &z));
+        ntc::Plan plan;
+        if (ntc::make_plan(&plan, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, k, b1 - b0, n, /*natural_out=*/false,
+                           z + (u64)b0 * n, n, 0, ctx->ntt_tma)) {
+            StageTimer tm(ctx, B200ZKP_STAGE_LDE);
+            return run_ct_plan(ctx, plan);
+        }
+    }
     const u64* cs = nullptr;
     TRY(get_coset_scale(ctx, n_log, rate_bits, &cs));
     StageTimer tm(ctx, B200ZKP_STAGE_LDE);
     // all coset blocks in one launch per pass (blockIdx.y): block b reads the same coefficients, scales them
     // by the powers of its shift and writes leaves [(b - b0) * n, (b - b0 + 1) * n) of every column
-    u64 n = (u64)1 << n_log;
     return run_transform(ctx, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, k, /*dir=*/0, /*bitrev_out=*/true,
                          cs + (u64)b0 * n, n, /*inverse_scale=*/false, /*canon_in=*/true, b1 - b0, n);
 }

@@ -65,6 +65,13 @@ GL_FN u64 add_nc(u64 a, u64 c) {
     u64 s = a + c;
     return (s < a) ? s + EPS : s;         // single wrap: cannot wrap twice because c < p
 }
+// a arbitrary u64, c canonical -> arbitrary u64 congruent to a - c
+GL_FN u64 sub_nc(u64 a, u64 c) {
+    u64 d = a - c;
+    return (a < c) ? d - EPS : d;         // a - c + 2^64 >= 2^64 - p + 1 = EPS: cannot borrow twice
+}
+// any u64 -> canonical (same as canon; the device version is a carry chain)
+GL_FN u64 canon_cc(u64 a) { return a >= P ? a - P : a; }
 #else
 // ---- sm_100a versions: IADD3 carry chains written in PTX.  ptxas fuses `mul.wide.u32 + add.cc.u64` into
 // one IMAD.WIDE.U32 with a carry-out predicate, and `subc 0,0` turns a carry/borrow into a 0 / 0xFFFFFFFF
@@ -109,6 +116,40 @@ GL_FN u64 add_nc(u64 a, u64 c) {
         "add.u32 l1, l1, m;\n\t"
         "mov.b64 %0, {l0, l1};\n\t"
         "}" : "=l"(r) : "l"(a), "l"(c));
+    return r;
+}
+// a arbitrary u64, c canonical -> arbitrary u64 congruent to a - c  (a - c + 2^64 >= EPS: one fold, cannot borrow twice).
+// Same instructions as `sub`; the name states the weaker contract the lazy butterflies rely on.
+GL_FN u64 sub_nc(u64 a, u64 c) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 l0, l1, m;\n\t"
+        ".reg .u64 t;\n\t"
+        "sub.cc.u64 t, %1, %2;\n\t"
+        "subc.u32 m, 0, 0;\n\t"               // 0xFFFFFFFF on borrow: -2^64 == -EPS
+        "mov.b64 {l0, l1}, t;\n\t"
+        "sub.cc.u32 l0, l0, m;\n\t"
+        "subc.u32 l1, l1, 0;\n\t"
+        "mov.b64 %0, {l0, l1};\n\t"
+        "}" : "=l"(r) : "l"(a), "l"(c));
+    return r;
+}
+// any u64 -> canonical: a + EPS carries out of 64 bits iff a >= p, and then the low 64 bits are a - p
+// (4 SASS instructions: IADD3 + IADD3.X with a carry-out predicate + 2 SEL, against 6 for the compare form `canon`)
+GL_FN u64 canon_cc(u64 a) {
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 l0, l1, s0, s1, m;\n\t"
+        ".reg .pred q;\n\t"
+        "mov.b64 {l0, l1}, %1;\n\t"
+        "add.cc.u32 s0, l0, 0xFFFFFFFF;\n\t"
+        "addc.cc.u32 s1, l1, 0;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "setp.ne.u32 q, m, 0;\n\t"
+        "selp.u32 l0, s0, l0, q;\n\t"
+        "selp.u32 l1, s1, l1, q;\n\t"
+        "mov.b64 %0, {l0, l1};\n\t"
+        "}" : "=l"(r) : "l"(a));
     return r;
 }
 // a canonical, b canonical -> canonical

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "ntt_kernels.cuh"
+#include "ntt_ct_kernels.cuh"
 
 namespace hostgl {
 typedef unsigned long long u64;
@@ -136,3 +137,99 @@ static inline void make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
 }
 
 }  // namespace ntt
+
+// ---- second-generation passes (ntt_ct_kernels.cuh): schedule of one multi-pass transform
+namespace ntc {
+
+struct Plan {
+    u32 n_passes;
+    u32 bits[ntt::MAX_PASSES];
+    int kind[ntt::MAX_PASSES];
+    PassParams pass[ntt::MAX_PASSES];
+    u64 grid[ntt::MAX_PASSES];      // CTAs of the launch
+};
+
+// does this generation cover a transform of 2^n_log points?  (two or more passes of 5..8 bits, strided tiles at least T wide)
+static inline bool covers(u32 n_log) {
+    if (n_log <= (u32)ntt::MAX_PASS_BITS || n_log > 32) return false;
+    u32 bits[ntt::MAX_PASSES], P, S = 0;
+    ntt::split_passes(n_log, bits, &P);
+    if (P < 2 || P > (u32)ntt::MAX_PASSES) return false;
+    for (u32 pi = 0; pi < P; pi++) {
+        if (bits[pi] < (u32)MIN_BITS || bits[pi] > (u32)MAX_BITS) return false;
+        S += bits[pi];
+        if (pi + 1 < P && n_log - S < 11 - bits[pi]) return false;      // C >= T
+    }
+    return true;
+}
+
+// Z[i] of the transform on the coset s <w>, i in [1, n): host replica of build_ztab_kernel (emulation harness, tests)
+static inline std::vector<u64> ztab_host(u32 n_log, u64 s, int dir, u64 last_scale) {
+    u64 n = (u64)1 << n_log;
+    u64 w = hostgl::root(n_log);
+    if (dir) w = hostgl::inv(w);
+    std::vector<u64> spow(n_log), z(n, 0);
+    u64 x = s % hostgl::P;
+    for (u32 e = 0; e < n_log; e++) { spow[e] = x; x = hostgl::mul(x, x); }
+    for (u64 i = 1; i < n; i++) {
+        u32 l = 63 - (u32)__builtin_clzll(i);
+        u32 j = (u32)(i - ((u64)1 << l));
+        u64 e = (u64)hostgl::bitrev(j, l) << (n_log - 1 - l);
+        u64 r = hostgl::mul(hostgl::pw(w, e), spow[n_log - 1 - l]);
+        if (last_scale && l == n_log - 1) r = hostgl::mul(r, last_scale);
+        z[i] = r;
+    }
+    return z;
+}
+
+//   natural_out: first pass in -> scratch, middle passes in place in scratch, last pass scatters scratch -> out (inverse
+//   transform; a_scale = n^-1 and the Z table's last level carries the same factor); otherwise in -> out, then in place in
+//   out, bit-reversed (leaf) order.  n_blk > 1: every block reads the same input (in_blk_stride = 0 in the first pass) and
+//   writes at out + blk * out_blk_stride.
+static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch, u32 n_log,
+                             u32 ncols, u32 n_blk, u64 out_blk_stride, bool natural_out, const u64* ztab, u64 ztab_blk_stride,
+                             u64 a_scale, bool use_tma) {
+    if (!covers(n_log) || ncols == 0 || n_blk == 0) return false;
+    if (natural_out && (!scratch || n_blk != 1)) return false;
+    u32 P;
+    ntt::split_passes(n_log, plan->bits, &P);
+    plan->n_passes = P;
+    const u64 n = (u64)1 << n_log;
+    u64* work = natural_out ? scratch : out;
+    const u64 work_stride = natural_out ? n : out_stride;
+    u32 S = 0;
+    for (u32 pi = 0; pi < P; pi++) {
+        const u32 B = plan->bits[pi];
+        const bool last = pi + 1 == P;
+        PassParams p{};
+        p.ncols = ncols; p.n_blk = n_blk; p.n_log = n_log; p.S = S; p.C_log = n_log - S - B;
+        p.ztab = ztab; p.ztab_blk_stride = ztab_blk_stride;
+        p.use_tma = use_tma ? 1u : 0u;
+        if (pi == 0) { p.in = in; p.in_col_stride = in_stride; p.in_blk_stride = 0; }
+        else { p.in = work; p.in_col_stride = work_stride; p.in_blk_stride = out_blk_stride; }
+        if (last && natural_out) { p.out = out; p.out_col_stride = out_stride; p.out_blk_stride = 0; p.a_scale = a_scale; }
+        else { p.out = work; p.out_col_stride = work_stride; p.out_blk_stride = out_blk_stride; }
+        int kind;
+        if (last) kind = natural_out ? KIND_FINAL_NATURAL : KIND_FINAL_INPLACE;
+        else kind = (pi == 0 && n_blk > 1 && n_blk <= (u32)MAX_LOOP_BLOCKS) ? KIND_STRIDED_LOOP : KIND_STRIDED;
+        // TMA needs 16-byte aligned bases and strides, and a real (non-zero) block stride wherever a block coordinate moves
+        if (kind == KIND_STRIDED || kind == KIND_STRIDED_LOOP) {
+            const bool in_blk_moves = kind == KIND_STRIDED && n_blk > 1;
+            if (((uintptr_t)p.in | (uintptr_t)p.out) & 15) p.use_tma = 0;
+            if ((p.in_col_stride | p.out_col_stride | p.out_blk_stride) & 1) p.use_tma = 0;
+            if (in_blk_moves && (p.in_blk_stride == 0 || (p.in_blk_stride & 1))) p.use_tma = 0;
+            if (n_blk > 1 && p.out_blk_stride == 0) p.use_tma = 0;
+        } else {
+            p.use_tma = 0;
+            if ((((uintptr_t)p.in | (uintptr_t)p.out) & 15) || ((p.in_col_stride | p.out_col_stride | p.in_blk_stride | p.out_blk_stride) & 1))
+                return false;       // the last pass moves pairs of elements (128-bit accesses)
+        }
+        plan->kind[pi] = kind;
+        plan->pass[pi] = p;
+        plan->grid[pi] = (n >> 11) * (u64)ncols * (kind == KIND_STRIDED_LOOP ? 1 : n_blk);
+        S += B;
+    }
+    return true;
+}
+
+}  // namespace ntc

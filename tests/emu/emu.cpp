@@ -94,7 +94,47 @@ static void transform(const u64* in, u64 in_stride, u64* out, u64 out_stride, u6
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_pass(plan.pass[pi], plan.bits[pi], n_blk);
 }
 
+// ---- second-generation passes (ntt_ct_kernels.cuh): the thread bodies stepped on the host (generic staging path; the TMA
+// staging of the device build moves the same [row][T] image)
+static void run_ct_pass(const ntc::PassParams& p, u32 B, int kind, u64 grid) {
+    static std::vector<u64> smem(16 * 1024);
+    for (u64 bid = 0; bid < grid; bid++) {
+#define EMU_CT(BB)                                                                                                       \
+    case BB:                                                                                                             \
+        if (kind == ntc::KIND_STRIDED) ntc::strided_body<BB, false, int>(p, nullptr, nullptr, smem.data(), (u32)bid);     \
+        else if (kind == ntc::KIND_STRIDED_LOOP) ntc::strided_body<BB, true, int>(p, nullptr, nullptr, smem.data(), (u32)bid); \
+        else if (kind == ntc::KIND_FINAL_INPLACE) ntc::final_body<BB, false>(p, smem.data(), (u32)bid);                  \
+        else ntc::final_body<BB, true>(p, smem.data(), (u32)bid);                                                        \
+        break;
+        switch (B) { EMU_CT(5) EMU_CT(6) EMU_CT(7) EMU_CT(8) }
+#undef EMU_CT
+    }
+}
+
 extern "C" {
+// values [k][n] -> coeffs [k][n] through the block-twiddle passes; returns 0 when this generation does not cover n_log
+int emu_ct_intt(const u64* in, u64* out, u32 n_log, u32 k) {
+    u64 n = (u64)1 << n_log;
+    u64 n_inv = hostgl::inv(n % hostgl::P);
+    std::vector<u64> z = ntc::ztab_host(n_log, 1, 1, n_inv), scratch((size_t)k * n);
+    ntc::Plan plan;
+    if (!ntc::make_plan(&plan, in, n, out, n, scratch.data(), n_log, k, 1, 0, true, z.data(), 0, n_inv, false)) return 0;
+    for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
+    return 1;
+}
+// coeffs [k][n] -> leaves of coset blocks [b0, b1) of every column, [k][(b1 - b0) * n] in leaf order
+int emu_ct_lde(const u64* coeffs, u64* lde, u32 n_log, u32 k, u32 rate_bits, u32 b0, u32 b1) {
+    u64 n = (u64)1 << n_log;
+    std::vector<u64> z;
+    for (u32 b = b0; b < b1; b++) {
+        std::vector<u64> zb = ntc::ztab_host(n_log, hostgl::coset_shift_of_block(n_log, rate_bits, b), 0, 0);
+        z.insert(z.end(), zb.begin(), zb.end());
+    }
+    ntc::Plan plan;
+    if (!ntc::make_plan(&plan, coeffs, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, k, b1 - b0, n, false, z.data(), n, 0, false)) return 0;
+    for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
+    return 1;
+}
 u64 emu_inverse(u64 x) { return perm::inverse(x); }
 // rows of the permutation argument (perm::row_chunk_products): running[(c * chunks + l) * n + i]
 void emu_perm_rows(const u64* wires, const u64* sigmas, const u64* k_is, const u64* betas, const u64* gammas, u32 n_log, u32 R,

@@ -103,6 +103,27 @@ def test_ntt_pass_bodies(emu, oracle, n_log):
             assert (lde[c] == oracle.coset_lde(v[c], r)[perm]).all()
 
 
+@pytest.mark.parametrize("n_log", [11, 12, 13, 14, 15, 16, 17, 18])
+def test_ct_pass_bodies(emu, oracle, n_log):
+    """second-generation passes (ntt_ct_kernels.cuh): inverse transform in natural order, coset LDE blocks in leaf order"""
+    rng = np.random.default_rng(200 + n_log)
+    k = 2 if n_log < 15 else 1
+    n = 1 << n_log
+    v = rng.integers(0, 2**64, size=(k, n), dtype=np.uint64)       # includes non-canonical inputs
+    v[0, :4] = [2**64 - 1, P, P - 1, 0]
+    out = np.zeros_like(v)
+    assert emu.emu_ct_intt(ptr(v), ptr(out), n_log, k) == 1
+    assert (out == np.stack([oracle.ifft(c) for c in v])).all()
+    cases = [(3, 0, 8)] if n_log > 13 else [(3, 0, 8), (3, 2, 4), (1, 0, 2), (0, 0, 1), (3, 5, 6), (4, 0, 16)]
+    for r, b0, b1 in cases:
+        N = n << r
+        lde = np.zeros((k, (b1 - b0) * n), np.uint64)
+        assert emu.emu_ct_lde(ptr(v), ptr(lde), n_log, k, r, b0, b1) == 1
+        perm = bitrev_perm(n_log + r)
+        for c in range(k):
+            assert (lde[c] == oracle.coset_lde(v[c], r)[perm][b0 * n:b1 * n]).all(), (r, b0, b1)
+
+
 def test_ntt_hostile_columns(emu, oracle):
     v = hostile_columns(64)
     out = np.zeros_like(v)

@@ -131,6 +131,53 @@ def test_transforms_three_and_four_passes(z, ctx, oracle, n_log):
         assert (lde == oracle.coset_lde(v[0], 1)).all()
 
 
+@pytest.mark.parametrize("n_log,k", [(11, 5), (12, 3), (13, 4), (14, 2), (15, 2), (16, 3), (17, 2), (19, 1), (20, 2)])
+def test_second_generation_passes(z, oracle, n_log, k, monkeypatch):
+    """ntt_ct_kernels.cuh (block-twiddle passes, TMA-staged tiles) against the oracle and against the first-generation
+    passes: inverse transform in natural order; coset LDE blocks in leaf order with the coset loop (2^r <= 8 blocks), without
+    it (16 blocks), with plain-load staging instead of TMA, and for a sub-range of the blocks (a multi-GPU rank's share)."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(500 + n_log)
+    n = 1 << n_log
+    v = rng.integers(0, 2**64, size=(k, n), dtype=np.uint64)
+    v[0, :4] = [2**64 - 1, P, P - 1, 0]
+    ctxs = {}
+    for name, env in (("tma", {}), ("plain", {"B200ZKP_NTT_TMA": "0"}), ("gen1", {"B200ZKP_NTT_CT": "0"})):
+        for key in ("B200ZKP_NTT_TMA", "B200ZKP_NTT_CT"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        ctxs[name] = z.Context(0)
+    want_c = np.stack([oracle.ifft(c) for c in v]) if n_log <= 17 else None
+    got = {name: z.ifft_batch(v, c) for name, c in ctxs.items()}
+    assert (got["tma"] == got["gen1"]).all() and (got["plain"] == got["gen1"]).all()
+    if want_c is not None:
+        assert (got["tma"] == want_c).all()
+    vt = torch.from_numpy(v.view(np.int64)).cuda()
+    perm = None
+    for r, b0, b1 in ((3, 0, 8), (3, 2, 4), (1, 0, 2), (4, 0, 16), (0, 0, 1)):
+        if n_log >= 19 and r == 4:
+            continue
+        outs = {}
+        for name, c in ctxs.items():
+            lde = torch.zeros((k, (b1 - b0) * n), dtype=torch.int64, device="cuda")
+            c.check(c._lib.b200zkp_dev_lde(c._h, C.c_void_p(vt.data_ptr()), n, C.c_void_p(lde.data_ptr()), (b1 - b0) * n, n_log, k, r, b0, b1))
+            c.synchronize()
+            outs[name] = lde.cpu().numpy().view(np.uint64)
+        assert (outs["tma"] == outs["gen1"]).all(), (r, b0, b1)
+        assert (outs["plain"] == outs["gen1"]).all(), (r, b0, b1)
+        if n_log <= 14:
+            perm = bitrev_perm(n_log + r)
+            for c in range(k):
+                assert (outs["tma"][c] == oracle.coset_lde(v[c], r)[perm][b0 * n:b1 * n]).all(), (r, b0, b1)
+    # a whole commitment through each generation
+    caps = {name: z.PolynomialBatch.from_values(v, 3, False, min(4, n_log), ctx=c).merkle_tree.cap.elements for name, c in ctxs.items()}
+    assert (caps["tma"] == caps["gen1"]).all() and (caps["plain"] == caps["gen1"]).all()
+    for c in ctxs.values():
+        c.close()
+
+
 def test_transform_roundtrip_large(z, ctx):
     rng = np.random.default_rng(31)
     v = rand_field(rng, (3, 1 << 20))
