@@ -51,8 +51,9 @@ struct b200zkp_ctx {
     std::map<u32, u64*> shift7_scale;                   // N_log -> 7^i, i < N
     std::map<std::pair<u64, u32>, u64*> power_scale;    // (shift, bits) -> shift^i, i < 2^bits (FRI layer cosets)
     // second-generation passes (ntt_ct_kernels.cuh): block-twiddle tables Z, [n_blk][n] each
-    std::map<u64, u64*> ztab_lde;                       // (n_log<<8 | rate_bits) -> forward transform on every leaf block's coset
-    std::map<u32, u64*> ztab_inv;                       // n_log -> inverse transform (s = 1), last level carries n^-1
+    struct ZTables { const u64* strided = nullptr; const u64* final_ = nullptr; };   // see ntc::ztab_entries / zfinal_words
+    std::map<u64, ZTables> ztab_lde;                    // (n_log<<8 | rate_bits) -> forward transform on every leaf block's coset
+    std::map<u32, ZTables> ztab_inv;                    // n_log -> inverse transform (s = 1), last level carries n^-1
     bool ntt_ct = true;                                 // B200ZKP_NTT_CT=0: every transform through ntt_kernels.cuh (A/B testing)
     bool ntt_tma = true;                                // B200ZKP_NTT_TMA=0: the new passes stage their tiles with plain loads
     u32 ct_smem_set = 0;                                // kernels whose dynamic shared memory limit has been raised on this device
@@ -386,7 +387,8 @@ static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan) {
 }
 
 // Z tables of `n_blk` cosets s_b <w_n>: shifts[b] on the host; built on the device and kept for the life of the ctx
-static int build_ztab(b200zkp_ctx* ctx, u32 n_log, int dir, const std::vector<u64>& shifts, u64 last_scale, u64** out) {
+static int build_ztab(b200zkp_ctx* ctx, u32 n_log, int dir, const std::vector<u64>& shifts, u64 last_scale, bool natural,
+                      b200zkp_ctx::ZTables* out) {
     TwoLevel tw{};
     TRY(get_tw(ctx, dir, n_log, &tw));
     std::vector<u64> spow((size_t)shifts.size() * n_log);
@@ -396,36 +398,41 @@ static int build_ztab(b200zkp_ctx* ctx, u32 n_log, int dir, const std::vector<u6
     }
     u64* d_spow = nullptr;
     TRY(upload(ctx, spow, &d_spow));
-    u64* d = nullptr;
-    TRY(table_alloc(ctx, (u64)shifts.size() << n_log, &d));
-    const u64 n = (u64)1 << n_log;
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)shifts.size());
-    ntc::build_ztab_kernel<<<grid, 256, 0, ctx->stream>>>(d, n_log, d_spow, tw.lo, tw.hi, tw.lo_bits, last_scale);
+    const u64 count = ntc::ztab_entries(n_log), words = ntc::zfinal_words(n_log);
+    u64 *d = nullptr, *f = nullptr;
+    TRY(table_alloc(ctx, count * shifts.size(), &d));
+    TRY(table_alloc(ctx, words * shifts.size(), &f));
+    ntc::build_ztab_kernel<<<dim3((unsigned)((count + 255) / 256), (unsigned)shifts.size()), 256, 0, ctx->stream>>>(
+        d, count, n_log, d_spow, tw.lo, tw.hi, tw.lo_bits, last_scale);
     LAUNCH_CHECK(ctx);
-    *out = d;
+    ntc::build_zfinal_kernel<<<dim3((unsigned)((words + 255) / 256), (unsigned)shifts.size()), 256, 0, ctx->stream>>>(
+        f, words, n_log, ntc::last_pass_bits(n_log), natural ? 1u : 0u, d_spow, tw.lo, tw.hi, tw.lo_bits, last_scale);
+    LAUNCH_CHECK(ctx);
+    out->strided = d;
+    out->final_ = f;
     return 0;
 }
 
-static int get_ztab_lde(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, const u64** out) {
+static int get_ztab_lde(b200zkp_ctx* ctx, u32 n_log, u32 rate_bits, b200zkp_ctx::ZTables* out) {
     const u64 key = ((u64)n_log << 8) | rate_bits;
     auto it = ctx->ztab_lde.find(key);
     if (it == ctx->ztab_lde.end()) {
         std::vector<u64> shifts;
         for (u32 b = 0; b < (1u << rate_bits); b++) shifts.push_back(hostgl::coset_shift_of_block(n_log, rate_bits, b));
-        u64* d = nullptr;
-        TRY(build_ztab(ctx, n_log, 0, shifts, 0, &d));
-        it = ctx->ztab_lde.emplace(key, d).first;
+        b200zkp_ctx::ZTables t;
+        TRY(build_ztab(ctx, n_log, 0, shifts, 0, /*natural=*/false, &t));
+        it = ctx->ztab_lde.emplace(key, t).first;
     }
     *out = it->second;
     return 0;
 }
 
-static int get_ztab_inv(b200zkp_ctx* ctx, u32 n_log, const u64** out) {
+static int get_ztab_inv(b200zkp_ctx* ctx, u32 n_log, b200zkp_ctx::ZTables* out) {
     auto it = ctx->ztab_inv.find(n_log);
     if (it == ctx->ztab_inv.end()) {
-        u64* d = nullptr;
-        TRY(build_ztab(ctx, n_log, 1, std::vector<u64>{1}, hostgl::inv(((u64)1 << n_log) % hostgl::P), &d));
-        it = ctx->ztab_inv.emplace(n_log, d).first;
+        b200zkp_ctx::ZTables t;
+        TRY(build_ztab(ctx, n_log, 1, std::vector<u64>{1}, hostgl::inv(((u64)1 << n_log) % hostgl::P), /*natural=*/true, &t));
+        it = ctx->ztab_inv.emplace(n_log, t).first;
     }
     *out = it->second;
     return 0;
@@ -601,12 +608,12 @@ static int dev_intt_locked(b200zkp_ctx* ctx, const u64* values, u64 in_stride, u
                            u64* scratch, u32 n_log, u32 k) {
     if (ctx->ntt_ct && scratch && k) {
         // 2^11 points and more: block-twiddle passes (ntt_ct_kernels.cuh), natural order out through the scratch buffer
-        const u64* z = nullptr;
+        b200zkp_ctx::ZTables z;
         ntc::Plan plan;
         if (ntc::covers(n_log)) {
             TRY(get_ztab_inv(ctx, n_log, &z));
-            if (ntc::make_plan(&plan, values, in_stride, coeffs, out_stride, scratch, n_log, k, 1, 0, /*natural_out=*/true, z, 0,
-                               hostgl::inv(((u64)1 << n_log) % hostgl::P), ctx->ntt_tma)) {
+            if (ntc::make_plan(&plan, values, in_stride, coeffs, out_stride, scratch, n_log, k, 1, 0, /*natural_out=*/true, z.strided,
+                               z.final_, hostgl::inv(((u64)1 << n_log) % hostgl::P), ctx->ntt_tma)) {
                 StageTimer tm(ctx, B200ZKP_STAGE_INTT);
                 return run_ct_plan(ctx, plan);
             }
@@ -632,11 +639,11 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
     u64 n = (u64)1 << n_log;
     if (ctx->ntt_ct && k && b1 > b0 && ntc::covers(n_log)) {
         // block-twiddle passes: the coset shift lives in the twiddles, the first pass stages a coefficient tile once for all blocks
-        const u64* z = nullptr;
+        b200zkp_ctx::ZTables z;
         TRY(get_ztab_lde(ctx, n_log, rate_bits, &z));
         ntc::Plan plan;
         if (ntc::make_plan(&plan, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, k, b1 - b0, n, /*natural_out=*/false,
-                           z + (u64)b0 * n, n, 0, ctx->ntt_tma)) {
+                           z.strided + (u64)b0 * ntc::ztab_entries(n_log), z.final_ + (u64)b0 * ntc::zfinal_words(n_log), 0, ctx->ntt_tma)) {
             StageTimer tm(ctx, B200ZKP_STAGE_LDE);
             return run_ct_plan(ctx, plan);
         }

@@ -186,8 +186,37 @@ static inline std::vector<u64> ztab_host(u32 n_log, u64 s, int dir, u64 last_sca
 //   transform; a_scale = n^-1 and the Z table's last level carries the same factor); otherwise in -> out, then in place in
 //   out, bit-reversed (leaf) order.  n_blk > 1: every block reads the same input (in_blk_stride = 0 in the first pass) and
 //   writes at out + blk * out_blk_stride.
+// width of the last pass / entries per block of the strided table / words per block of the tile-ordered last-pass table
+static inline u32 last_pass_bits(u32 n_log) {
+    u32 bits[ntt::MAX_PASSES], P;
+    ntt::split_passes(n_log, bits, &P);
+    return bits[P - 1];
+}
+static inline u64 ztab_entries(u32 n_log) { return (u64)1 << (n_log - last_pass_bits(n_log)); }
+static inline u64 zfinal_words(u32 n_log) {
+    const u32 B = last_pass_bits(n_log);
+    return (((u64)1 << n_log) >> 11) * ((u64)(TILE >> B) * (((u64)1 << B) + 1));
+}
+// host replica of build_zfinal_kernel from the full table of ztab_host
+static inline std::vector<u64> zfinal_host(u32 n_log, const std::vector<u64>& z, bool natural) {
+    const u32 B = last_pass_bits(n_log), T_log = 11 - B, TWP = (1u << B) + 1, S = n_log - B;
+    std::vector<u64> f(zfinal_words(n_log), 0);
+    for (u64 x = 0; x < f.size(); x++) {
+        const u64 tile_i = x / ((u64)TWP << T_log);
+        const u32 rem = (u32)(x - tile_i * ((u64)TWP << T_log));
+        const u32 b = rem / TWP, e = rem - b * TWP;
+        if (e < 1 || e >= (1u << B)) continue;
+        const u32 batch = (u32)(tile_i << T_log) + b;
+        const u32 a_b = natural ? hostgl::bitrev(batch, S) : batch;
+        const u32 u = 31 - (u32)__builtin_clz(e);
+        f[x] = z[(((((u64)1 << S) + a_b)) << u) + (e ^ (1u << u))];      // ntc::z_index
+    }
+    return f;
+}
+
+// ztab / zfinal: the strided table (ztab_entries per block) and the tile-ordered last-pass table (zfinal_words per block)
 static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch, u32 n_log,
-                             u32 ncols, u32 n_blk, u64 out_blk_stride, bool natural_out, const u64* ztab, u64 ztab_blk_stride,
+                             u32 ncols, u32 n_blk, u64 out_blk_stride, bool natural_out, const u64* ztab, const u64* zfinal,
                              u64 a_scale, bool use_tma) {
     if (!covers(n_log) || ncols == 0 || n_blk == 0) return false;
     if (natural_out && (!scratch || n_blk != 1)) return false;
@@ -203,7 +232,8 @@ static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
         const bool last = pi + 1 == P;
         PassParams p{};
         p.ncols = ncols; p.n_blk = n_blk; p.n_log = n_log; p.S = S; p.C_log = n_log - S - B;
-        p.ztab = ztab; p.ztab_blk_stride = ztab_blk_stride;
+        p.ztab = last ? zfinal : ztab;
+        p.ztab_blk_stride = last ? zfinal_words(n_log) : ztab_entries(n_log);
         p.use_tma = use_tma ? 1u : 0u;
         if (pi == 0) { p.in = in; p.in_col_stride = in_stride; p.in_blk_stride = 0; }
         else { p.in = work; p.in_col_stride = work_stride; p.in_blk_stride = out_blk_stride; }

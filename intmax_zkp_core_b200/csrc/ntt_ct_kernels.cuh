@@ -58,8 +58,8 @@ struct PassParams {
     u32 n_log;      // L
     u32 S;          // levels done by earlier passes
     u32 C_log;      // L - S - B
-    const u64* ztab;          // Z table of block b at ztab + b * ztab_blk_stride, entries [1, n)
-    u64 ztab_blk_stride;
+    const u64* ztab;          // strided passes: Z of block b at ztab + b * ztab_blk_stride, entries [1, 2^(L - B_last))
+    u64 ztab_blk_stride;      // final passes: the tile-ordered image of the last levels (see FinalSmem), block stride in words
     u64 a_scale;    // 0, or n^-1: multiplies the sum operand of the LAST level (its twiddles carry the same factor)
     u32 use_tma;
 };
@@ -186,6 +186,11 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* map, u32 c0, u
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
                  ::"l"(map), "r"(c0), "r"(0u), "r"(a), "r"(blk), "r"(col), "r"(smem_u32(src)) : "memory");
 }
+// contiguous run global -> shared (UBLKCP), completion on the mbarrier; 16-byte aligned addresses and size
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -296,12 +301,17 @@ GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_o
 }
 
 // ---------------------------------------------------------------------------------------------------- final passes
-// shared memory: [tile: 2^B rows x (T + 1)][per-batch sub-twiddles: T x (2^B + 1)]
+// shared memory: [tile: 2^B rows x (T + 1)][per-batch sub-twiddles: T x (2^B + 1)][mbarrier]
+// The sub-twiddles of a tile are ONE contiguous run of the tile-ordered table (built once per transform shape by
+// build_zfinal_kernel): tile i of a block at words [i * tw_words, (i + 1) * tw_words), batch b at b * TWP, sub-twiddle e
+// (level u = floor(log2 e), block h = e - 2^u of the batch) at + e; words 0 and 2^B of a batch are padding, so that the
+// batches of the 32 lanes of a warp start in different banks.  One cp.async.bulk (UBLKCP) stages it.
 template <int B>
 struct FinalSmem {
     static constexpr u32 NPTS = 1u << B, T = (u32)TILE >> B;
     static constexpr u32 TP = T + 1, TWP = NPTS + 1;
-    static constexpr u32 bytes = (NPTS * TP + T * TWP) * 8;
+    static constexpr u32 tw_words = T * TWP;
+    static constexpr u32 bytes = (NPTS * TP + tw_words) * 8 + 16;
 };
 
 template <int B, bool NATURAL>
@@ -311,6 +321,8 @@ GL_FN void final_body(const PassParams& p, u64* smem, u32 bid) {
     constexpr u32 IT = TILE / THREADS;
     u64* const tile = smem;
     u64* const swb = smem + NPTS * TP;
+    u64* const bar = swb + FinalSmem<B>::tw_words;
+    (void)bar;
     const u32 batches_log = p.n_log - B;                       // = S
     const u32 V = p.ncols * p.n_blk;
     const u32 vcol = bid % V, tile_i = bid / V;
@@ -318,8 +330,18 @@ GL_FN void final_body(const PassParams& p, u64* smem, u32 bid) {
     const u32 batch0 = tile_i << T_log;
     const u64* __restrict__ in = p.in + (u64)col * p.in_col_stride + (u64)blk * p.in_blk_stride;
     u64* __restrict__ out = p.out + (u64)col * p.out_col_stride + (u64)blk * p.out_blk_stride;
-    const u64* __restrict__ ztab = p.ztab + (u64)blk * p.ztab_blk_stride;
+    const u64* __restrict__ ztile = p.ztab + (u64)blk * p.ztab_blk_stride + (u64)tile_i * FinalSmem<B>::tw_words;
 
+#ifndef B200ZKP_HOST_EMU
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, FinalSmem<B>::tw_words * 8);
+        bulk_load(swb, ztile, FinalSmem<B>::tw_words * 8, bar);
+    }
+#else
+    for (u32 i = 0; i < FinalSmem<B>::tw_words; i++) swb[i] = ztile[i];
+#endif
     NTC_FOR_THREADS(tid) {
         // data: batch b = rows [a_b << B, (a_b + 1) << B) of the column block; pairs of elements per access
         u64 v[IT];
@@ -335,15 +357,6 @@ GL_FN void final_body(const PassParams& p, u64* smem, u32 bid) {
             v[it] = q.x; v[it + 1] = q.y;
 #endif
         }
-        // twiddles: level u of batch b at swb[b * TWP + 2^u + h] = Z[((2^S + a_b) << u) + h]
-        for (u32 i = tid; i < T * (NPTS - 1); i += THREADS) {
-            const u32 j = i + T;
-            const u32 u = ulog2(j >> T_log);
-            const u32 q = j - (T << u);
-            const u32 b = q >> u, h = q & ((1u << u) - 1);
-            const u32 a_b = NATURAL ? bitrev_bits(batch0 + b, batches_log) : batch0 + b;
-            swb[b * TWP + (1u << u) + h] = gl::ldg(ztab + (((((u64)1 << batches_log) + a_b) << u) + h));
-        }
 #pragma unroll
         for (u32 it = 0; it < IT; it += 2) {
             const u32 i = 2 * (tid + (it / 2) * THREADS);
@@ -352,6 +365,9 @@ GL_FN void final_body(const PassParams& p, u64* smem, u32 bid) {
             tile[(g + 1) * TP + b] = v[it + 1];
         }
     }
+#ifndef B200ZKP_HOST_EMU
+    mbar_wait(bar, 0);
+#endif
     NTC_SYNC();
 
     if (p.a_scale) run_rounds<B, true>(tile, tile, swb, TWP, T_log, TP, p.a_scale);
@@ -397,21 +413,41 @@ ct_pass_kernel(const PassParams p, const __grid_constant__ CUtensorMap tm_in, co
 
 // Z[i], i in [1, n):  l = floor(log2 i), j = i - 2^l:  Z[i] = spow[L - 1 - l] * w^(bitrev_l(j) << (L - 1 - l)) * (l == L-1 ? last_scale : 1)
 // spow[e] = s^(2^e) (host computed, L entries per block, in global memory); (lo, hi): two-level powers of w_n (direction specific)
-__global__ void build_ztab_kernel(u64* __restrict__ out, u32 n_log, const u64* __restrict__ spow, const u64* __restrict__ lo,
+__device__ __forceinline__ u64 z_entry(u64 i, u32 n_log, const u64* __restrict__ spow, const u64* __restrict__ lo,
+                                       const u64* __restrict__ hi, u32 lo_bits, u64 last_scale) {
+    if (!i) return 0;
+    const u32 l = 63u - (u32)__clzll((long long)i);
+    const u32 j = (u32)(i - ((u64)1 << l));
+    const u64 e = (u64)bitrev_bits(j, l) << (n_log - 1 - l);
+    const u64 w = gl::mul(gl::ldg(lo + (e & (((u64)1 << lo_bits) - 1))), gl::ldg(hi + (e >> lo_bits)));
+    u64 r = gl::mul(w, gl::ldg(spow + (n_log - 1 - l)));
+    if (last_scale && l == n_log - 1) r = gl::mul(r, last_scale);
+    return r;
+}
+// strided passes: out[blk][i] = Z_blk[i] for i < count (the levels before the last pass); grid (ceil(count / 256), n_blk)
+__global__ void build_ztab_kernel(u64* __restrict__ out, u64 count, u32 n_log, const u64* __restrict__ spow, const u64* __restrict__ lo,
                                   const u64* __restrict__ hi, u32 lo_bits, u64 last_scale) {
     const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 blk = blockIdx.y;
-    if (i >= ((u64)1 << n_log)) return;
+    if (i >= count) return;
+    out[(u64)blockIdx.y * count + i] = z_entry(i, n_log, spow + (u64)blockIdx.y * n_log, lo, hi, lo_bits, last_scale);
+}
+// final pass of B bits: the tile-ordered image described at FinalSmem; natural: batch b of tile i is row block
+// bitrev(i * T + b) (inverse transform).  grid (ceil(words / 256), n_blk), words = (n >> 11) * T * (2^B + 1)
+__global__ void build_zfinal_kernel(u64* __restrict__ out, u64 words, u32 n_log, u32 B, u32 natural, const u64* __restrict__ spow,
+                                    const u64* __restrict__ lo, const u64* __restrict__ hi, u32 lo_bits, u64 last_scale) {
+    const u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= words) return;
+    const u32 T_log = 11 - B, TWP = (1u << B) + 1, S = n_log - B;
+    const u64 tile_i = x / ((u64)TWP << T_log);
+    const u32 rem = (u32)(x - tile_i * ((u64)TWP << T_log));
+    const u32 b = rem / TWP, e = rem - b * TWP;
     u64 r = 0;
-    if (i) {
-        const u32 l = 63u - (u32)__clzll((long long)i);
-        const u32 j = (u32)(i - ((u64)1 << l));
-        const u64 e = (u64)bitrev_bits(j, l) << (n_log - 1 - l);
-        const u64 w = gl::mul(gl::ldg(lo + (e & (((u64)1 << lo_bits) - 1))), gl::ldg(hi + (e >> lo_bits)));
-        r = gl::mul(w, gl::ldg(spow + (u64)blk * n_log + (n_log - 1 - l)));
-        if (last_scale && l == n_log - 1) r = gl::mul(r, last_scale);
+    if (e >= 1 && e < (1u << B)) {
+        const u32 batch = (u32)(tile_i << T_log) + b;
+        const u32 a_b = natural ? bitrev_bits(batch, S) : batch;
+        r = z_entry(z_index(((u64)1 << S) + a_b, e), n_log, spow + (u64)blockIdx.y * n_log, lo, hi, lo_bits, last_scale);
     }
-    out[(u64)blk << n_log | i] = r;
+    out[(u64)blockIdx.y * words + x] = r;
 }
 #endif  // !B200ZKP_HOST_EMU
 

@@ -116,22 +116,28 @@ extern "C" {
 int emu_ct_intt(const u64* in, u64* out, u32 n_log, u32 k) {
     u64 n = (u64)1 << n_log;
     u64 n_inv = hostgl::inv(n % hostgl::P);
+    if (!ntc::covers(n_log)) return 0;
     std::vector<u64> z = ntc::ztab_host(n_log, 1, 1, n_inv), scratch((size_t)k * n);
+    std::vector<u64> zf = ntc::zfinal_host(n_log, z, true);
+    z.resize(ntc::ztab_entries(n_log));
     ntc::Plan plan;
-    if (!ntc::make_plan(&plan, in, n, out, n, scratch.data(), n_log, k, 1, 0, true, z.data(), 0, n_inv, false)) return 0;
+    if (!ntc::make_plan(&plan, in, n, out, n, scratch.data(), n_log, k, 1, 0, true, z.data(), zf.data(), n_inv, false)) return 0;
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
     return 1;
 }
 // coeffs [k][n] -> leaves of coset blocks [b0, b1) of every column, [k][(b1 - b0) * n] in leaf order
 int emu_ct_lde(const u64* coeffs, u64* lde, u32 n_log, u32 k, u32 rate_bits, u32 b0, u32 b1) {
     u64 n = (u64)1 << n_log;
-    std::vector<u64> z;
+    if (!ntc::covers(n_log)) return 0;
+    std::vector<u64> z, zf;
     for (u32 b = b0; b < b1; b++) {
         std::vector<u64> zb = ntc::ztab_host(n_log, hostgl::coset_shift_of_block(n_log, rate_bits, b), 0, 0);
-        z.insert(z.end(), zb.begin(), zb.end());
+        std::vector<u64> fb = ntc::zfinal_host(n_log, zb, false);
+        z.insert(z.end(), zb.begin(), zb.begin() + ntc::ztab_entries(n_log));
+        zf.insert(zf.end(), fb.begin(), fb.end());
     }
     ntc::Plan plan;
-    if (!ntc::make_plan(&plan, coeffs, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, k, b1 - b0, n, false, z.data(), n, 0, false)) return 0;
+    if (!ntc::make_plan(&plan, coeffs, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, k, b1 - b0, n, false, z.data(), zf.data(), 0, false)) return 0;
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
     return 1;
 }
