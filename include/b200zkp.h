@@ -186,6 +186,13 @@ int b200zkp_hash_no_pad(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, ui
 int b200zkp_hash_or_noop(b200zkp_ctx* ctx, const uint64_t* in, uint64_t count, uint32_t len, uint64_t* out);
 int b200zkp_two_to_one(b200zkp_ctx* ctx, const uint64_t* left, const uint64_t* right, uint64_t count,
                        uint64_t* out);
+/* The Fiat-Shamir transcript (plonky2 iop/challenger.rs `Challenger::duplexing`), any number of steps in ONE launch:
+ * every chunk of up to 8 of the n_inputs pending observations overwrites the head of state[12] (overwrite-mode sponge) and is
+ * followed by a permutation; then n_squeeze further permutations run, each appending its 8 rate words to `squeezed`
+ * (8 * n_squeeze words).  state is updated in place.  A transcript that defers its observations until the next challenge is
+ * drawn makes one call where it made one b200zkp_poseidon_permute per 8 elements (host mirror: fri.py Challenger). */
+int b200zkp_duplex_chain(b200zkp_ctx* ctx, uint64_t state[12], const uint64_t* inputs, uint64_t n_inputs,
+                         uint32_t n_squeeze, uint64_t* squeezed);
 /* in-place transforms of k columns of 2^n_log elements (natural order in and out) */
 int b200zkp_ntt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k);
 int b200zkp_intt(b200zkp_ctx* ctx, uint64_t* data, uint32_t n_log, uint32_t k);

@@ -124,6 +124,7 @@ _SIGS = {
     "b200zkp_tree_digests": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200zkp_tree_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "b200zkp_poseidon_permute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "b200zkp_duplex_chain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "b200zkp_hash_no_pad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "b200zkp_hash_or_noop": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]),
     "b200zkp_two_to_one": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),

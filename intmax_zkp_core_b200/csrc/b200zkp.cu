@@ -57,6 +57,10 @@ struct b200zkp_ctx {
     bool ntt_ct = true;                                 // B200ZKP_NTT_CT=0: every transform through ntt_kernels.cuh (A/B testing)
     bool ntt_tma = true;                                // B200ZKP_NTT_TMA=0: the new passes stage their tiles with plain loads
     u32 ct_smem_set = 0;                                // kernels whose dynamic shared memory limit has been raised on this device
+    // mailbox: 64 KB of mapped pinned host memory the small host-buffer calls (single hashes, the Fiat-Shamir transcript)
+    // read and write directly from the kernel: no cudaMemcpy on those paths, one launch + one stream synchronise per call
+    void* mailbox = nullptr;
+    void* mailbox_dev = nullptr;
     u64* round_add = nullptr;                           // poseidon_tables::ROUND_ADD in global memory (latency-form kernels)
     std::multimap<size_t, void*> pool;                  // cached device allocations (dev_release), at most pool_max_bytes
     size_t pool_bytes = 0;
@@ -527,6 +531,7 @@ extern "C" void b200zkp_ctx_destroy(b200zkp_ctx* ctx) {
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     for (auto e : ctx->sync_events) cudaEventDestroy(e);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1774,8 +1779,31 @@ extern "C" int b200zkp_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t*
 }
 
 // ------------------------------------------------------------------------------------------------ Hasher / field helpers
+static constexpr size_t MAILBOX_BYTES = 64 << 10;
+static bool mailbox_ready(b200zkp_ctx* ctx) {
+    if (ctx->mailbox) return true;
+    if (cudaHostAlloc(&ctx->mailbox, MAILBOX_BYTES, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&ctx->mailbox_dev, ctx->mailbox, 0) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+        ctx->mailbox = ctx->mailbox_dev = nullptr;
+        return false;
+    }
+    return true;
+}
+
 template <typename F>
 static int with_io(b200zkp_ctx* ctx, const void* in, size_t in_b, void* out, size_t out_b, F body) {
+    const size_t in_pad = (in_b + 255) & ~(size_t)255;
+    if (in_pad + out_b <= MAILBOX_BYTES && mailbox_ready(ctx)) {
+        // latency path: the kernel reads its input from and writes its result to mapped host memory
+        if (in_b) memcpy(ctx->mailbox, in, in_b);
+        int rc = body((u64*)ctx->mailbox_dev, (u64*)((char*)ctx->mailbox_dev + in_pad));
+        if (rc) return rc;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (out_b) memcpy(out, (char*)ctx->mailbox + in_pad, out_b);
+        return 0;
+    }
     void *d_in = nullptr, *d_out = nullptr;
     int rc = 0;
     if ((rc = dev_alloc(ctx, std::max<size_t>(in_b, 8), &d_in)) || (rc = dev_alloc(ctx, std::max<size_t>(out_b, 8), &d_out))) {
@@ -1802,6 +1830,26 @@ extern "C" int b200zkp_poseidon_permute(b200zkp_ctx* ctx, const uint64_t* in, ui
         LAUNCH_CHECK(ctx);
         return 0;
     });
+}
+
+// iop/challenger.rs `duplexing`, chained: io = state[12] || inputs[n_inputs] in, state[12] || squeezed[8 * n_squeeze] out
+extern "C" int b200zkp_duplex_chain(b200zkp_ctx* ctx, uint64_t state[12], const uint64_t* inputs, uint64_t n_inputs,
+                                    uint32_t n_squeeze, uint64_t* squeezed) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!state || (n_inputs && !inputs) || (n_squeeze && !squeezed)) BAD(ctx, "null buffer");
+    if (n_inputs > 4096 || n_squeeze > 512) BAD(ctx, "transcript step too large");
+    std::vector<u64> in(12 + n_inputs), out(12 + (size_t)8 * n_squeeze);
+    memcpy(in.data(), state, 96);
+    if (n_inputs) memcpy(in.data() + 12, inputs, n_inputs * 8);
+    TRY(with_io(ctx, in.data(), in.size() * 8, out.data(), out.size() * 8, [&](u64* di, u64* dout) -> int {
+        merkle::duplex_chain_kernel<<<1, 32, 0, ctx->stream>>>(di, n_inputs, n_squeeze, dout, ctx->round_add);
+        LAUNCH_CHECK(ctx);
+        return 0;
+    }));
+    memcpy(state, out.data(), 96);
+    if (n_squeeze) memcpy(squeezed, out.data() + 12, (size_t)n_squeeze * 64);
+    return 0;
 }
 
 static int hash_rows(b200zkp_ctx* ctx, const u64* in, u64 count, u32 len, u64* out, bool noop_short) {

@@ -252,6 +252,25 @@ permute_coop_kernel(const u64* __restrict__ in, const u64* __restrict__ in2, u64
     }
 }
 
+// The Fiat-Shamir transcript's sponge (plonky2 iop/challenger.rs `duplexing`), a whole chain of steps in one launch of one warp:
+// in = state[12] || inputs[n_inputs]: every chunk of up to 8 inputs overwrites the head of the state and is followed by a
+// permutation; then n_squeeze further permutations, each publishing the 8 rate words.  out = final state[12] || squeezed.
+__global__ void __launch_bounds__(32)
+duplex_chain_kernel(const u64* __restrict__ in, u64 n_inputs, u32 n_squeeze, u64* __restrict__ out, const u64* __restrict__ ra) {
+    const u32 lane = threadIdx.x & 31, l = lane & 15, grp_base = lane & 16;
+    const u32 li = l < 12 ? l : 0;
+    u64 s = l < 12 ? in[l] : 0;
+    for (u64 c = 0; c < n_inputs; c += poseidon::RATE) {
+        if (l < poseidon::RATE && c + l < n_inputs) s = in[12 + c + l];
+        s = coop_permute(s, li, grp_base, ra);
+    }
+    for (u32 q = 0; q < n_squeeze; q++) {
+        s = coop_permute(s, li, grp_base, ra);
+        if (lane < poseidon::RATE) out[12 + q * poseidon::RATE + lane] = s;
+    }
+    if (lane < 12) out[lane] = s;
+}
+
 // ---------------------------------------------------------------- stateless Hasher helpers (tests, N4)
 // out[i] = permute(in[i]), states row-major 12 words each
 __global__ void __launch_bounds__(128)

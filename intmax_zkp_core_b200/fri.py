@@ -107,30 +107,34 @@ class FriInstanceInfo:
 
 # ------------------------------------------------------------------------------------------------ transcript
 class Challenger:
-    """iop/challenger.rs: sponge_state / input_buffer / output_buffer, inputs overwrite the rate part."""
+    """iop/challenger.rs: sponge_state / input_buffer / output_buffer, inputs overwrite the rate part.
+
+    Same transcript as plonky2's, evaluated lazily: observations are only queued, and the permutations they imply (one per
+    full chunk of 8, as `observe_element` triggers them, plus the one `get_challenge` runs on a partial chunk or an empty
+    output buffer) run on the device in ONE call when the next challenge is drawn (b200zkp_duplex_chain).  A draw of
+    several challenges asks for all the permutations it will need in the same call."""
 
     def __init__(self, ctx: Optional[Context] = None):
         self._ctx = ctx or default_context()
         self.sponge_state = np.zeros(SPONGE_WIDTH, dtype=np.uint64)
-        self.input_buffer: List[int] = []
+        self.input_buffer: List[int] = []        # every observation since the last draw (may exceed the rate: lazy)
         self.output_buffer: List[int] = []
 
     def observe_element(self, e: int):
         self.output_buffer = []
         self.input_buffer.append(int(e) % P)
-        if len(self.input_buffer) == SPONGE_RATE:
-            self.duplexing()
 
     def observe_elements(self, es):
-        for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist():
-            self.observe_element(e)
+        es = [int(e) % P for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist()]
+        if es:
+            self.output_buffer = []
+            self.input_buffer.extend(es)
 
     def observe_extension_element(self, e: Ext):
         self.observe_elements(list(e))
 
     def observe_extension_elements(self, es):
-        for e in es:
-            self.observe_extension_element(e)
+        self.observe_elements([x for e in es for x in e])
 
     def observe_hash(self, h):
         self.observe_elements(h.elements if isinstance(h, HashOut) else h)
@@ -138,13 +142,45 @@ class Challenger:
     def observe_cap(self, cap):
         self.observe_elements(cap.flatten() if isinstance(cap, MerkleCap) else cap)
 
+    def _chain(self, n_squeeze: int) -> np.ndarray:
+        """every queued observation (with all the permutations it implies), then n_squeeze further permutations: one call"""
+        m = len(self.input_buffer)
+        state = np.ascontiguousarray(self.sponge_state, dtype=np.uint64)
+        inputs = _u64(self.input_buffer) if m else None
+        squeezed = np.zeros((max(n_squeeze, 1), SPONGE_RATE), dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.b200zkp_duplex_chain(self._ctx._h, _p(state), _p(inputs) if m else None, m, n_squeeze,
+                                                            _p(squeezed) if n_squeeze else None))
+        self.sponge_state = state
+        self.input_buffer = []
+        return squeezed[:n_squeeze]
+
     def get_challenge(self) -> int:
-        if self.input_buffer or not self.output_buffer:
-            self.duplexing()
-        return self.output_buffer.pop()
+        return self.get_n_challenges(1)[0]
 
     def get_n_challenges(self, n: int) -> List[int]:
-        return [self.get_challenge() for _ in range(n)]
+        out: List[int] = []
+        while len(out) < n:
+            if self.input_buffer:
+                # plonky2 duplexes on every 8th observation and once more for a partial chunk when a challenge is drawn
+                self._chain(0)
+                self.output_buffer = [int(v) for v in self.sponge_state[:SPONGE_RATE]]
+            elif not self.output_buffer:
+                # one permutation per 8 challenges still missing; challenges pop from the END of each block of rate words
+                blocks = self._chain(-(-(n - len(out)) // SPONGE_RATE))
+                for blk in blocks[:-1]:
+                    out.extend(int(v) for v in blk[::-1])
+                self.output_buffer = [int(v) for v in blocks[-1]]
+            else:
+                out.append(self.output_buffer.pop())
+        return out
+
+    def duplexing(self):
+        """plonky2's name for one forced step: the queued observations, or one permutation when nothing is queued"""
+        if self.input_buffer:
+            self._chain(0)
+            self.output_buffer = [int(v) for v in self.sponge_state[:SPONGE_RATE]]
+        else:
+            self.output_buffer = [int(v) for v in self._chain(1)[0]]
 
     def get_hash(self) -> HashOut:
         return HashOut(self.get_n_challenges(4))
@@ -154,12 +190,8 @@ class Challenger:
         return (c[0], c[1])
 
     def duplexing(self):
-        assert len(self.input_buffer) <= SPONGE_RATE
-        for i, v in enumerate(self.input_buffer):
-            self.sponge_state[i] = v
-        self.input_buffer = []
-        self.sponge_state = PoseidonPermutation.permute(self.sponge_state, self._ctx)
-        self.output_buffer = [int(v) for v in self.sponge_state[:SPONGE_RATE]]
+        """plonky2's name for one flush (kept for callers that force it)"""
+        self._duplex_once_or_absorb()
 
 
 # ------------------------------------------------------------------------------------------------ proof
