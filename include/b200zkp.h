@@ -267,6 +267,40 @@ int b200zkp_dev_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires_
                                         const uint64_t* gammas, uint32_t num_challenges, uint64_t* out_dev,
                                         uint64_t out_col_stride);
 
+/* ---- row N1b: compute_quotient_polys — the vanishing polynomial on the quotient coset, divided by Z_H -----------------
+ * Replaces plonky2 @ f99ed9c plonk/prover.rs `compute_quotient_polys` up to its coset_ifft (b200zkp_dev_coset_intt does
+ * that, b200zkp_dev_commit(is_coeffs) commits the chunks), with plonk/vanishing_poly.rs `eval_vanishing_poly_base_batch`
+ * and the eval_unfiltered of the gate types below; reached from every prove() of the reference
+ * (/root/reference/src/rollup/circuits/mod.rs:1247, src/transaction/circuits/mod.rs:453).  It reads the three LDEs where
+ * the commitments left them (device, column-major, leaf order), so no LDE crosses PCIe any more.
+ * The circuit description is what CommonCircuitData holds: the gate list in CircuitBuilder's order (sorted by degree) with
+ * each gate's selector polynomial and selector group (gates/selectors.rs), num_constants = num_selectors + 2 gate constants,
+ * standard_recursion_config's 135 wires / 80 routed wires.  Gate types evaluated: NoopGate, ConstantGate (2 constants),
+ * PublicInputGate, ArithmeticGate (20 ops), PoseidonGate; any other kind is B200ZKP_ERR_UNSUPPORTED (not silently skipped). */
+enum { B200ZKP_GATE_NOOP = 0, B200ZKP_GATE_CONSTANT = 1, B200ZKP_GATE_PUBLIC_INPUT = 2, B200ZKP_GATE_ARITHMETIC = 3,
+       B200ZKP_GATE_POSEIDON = 4 };
+#define B200ZKP_MAX_GATES 16
+typedef struct {
+    uint32_t degree_bits;               /* n = 2^degree_bits rows */
+    uint32_t quotient_degree_bits;      /* the quotient is evaluated on n << quotient_degree_bits points (<= rate_bits of the LDEs) */
+    uint32_t quotient_degree_factor;    /* chunk size of the permutation argument (max_degree of check_partial_products) */
+    uint32_t num_routed_wires;          /* 80 */
+    uint32_t num_challenges;            /* <= 4 */
+    uint32_t num_selectors;
+    uint32_t n_gates;
+    uint32_t gate_kind[B200ZKP_MAX_GATES], gate_selector_index[B200ZKP_MAX_GATES];
+    uint32_t gate_group_begin[B200ZKP_MAX_GATES], gate_group_end[B200ZKP_MAX_GATES];
+    const uint64_t* k_is;               /* num_routed_wires coset shifts (host) */
+    const uint64_t *betas, *gammas, *alphas;   /* num_challenges each (host) */
+    uint64_t public_inputs_hash[4];
+} b200zkp_vanishing_desc;
+/* constants_sigmas [num_selectors + 2 + num_routed_wires][cs_stride], wires [135][wires_stride], zs_partial_products
+ * [num_challenges * ceil(num_routed / factor)][zpp_stride]: device LDEs in leaf order (what b200zkp_dev_commit wrote), every
+ * stride >= n << quotient_degree_bits.  out_dev: [num_challenges][out_stride] quotient values in natural order on 7 <w>. */
+int b200zkp_dev_quotient_values(b200zkp_ctx* ctx, const b200zkp_vanishing_desc* desc, const uint64_t* constants_sigmas,
+                                uint64_t cs_stride, const uint64_t* wires, uint64_t wires_stride,
+                                const uint64_t* zs_partial_products, uint64_t zpp_stride, uint64_t* out_dev, uint64_t out_stride);
+
 /* ---- one commitment partitioned over several GPUs (NCCL over NVLink / NVSwitch) ----------------------
  * north_star's partition: rank g of G (a power of two, G <= 2^rate_bits and G <= 2^cap_height) inverse-transforms columns
  * [g*kp, (g+1)*kp), kp = ceil(k/G); the coefficient shards are exchanged with NCCL point-to-point groups (a few peers per

@@ -144,6 +144,8 @@ _SIGS = {
                                                 C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "b200zkp_dev_partial_products_and_zs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
                                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "b200zkp_dev_quotient_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                            C.c_void_p, C.c_uint64]),
     "b200zkp_comm_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "b200zkp_comm_init_rank": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "b200zkp_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),

@@ -19,6 +19,7 @@
 #include "eval_kernels.cuh"
 #include "fri_kernels.cuh"
 #include "perm_kernels.cuh"
+#include "vanishing_kernels.cuh"
 #include "host_plan.hpp"
 
 using gl::u32;
@@ -2182,6 +2183,83 @@ extern "C" int b200zkp_int_pipe_bench(b200zkp_ctx* ctx, int kind, uint32_t iters
     double instr = (double)blocks * 256.0 * (double)iters * 64.0 * (kind == 7 ? 2.0 : 1.0);   // 8 rounds x 8 instructions (x2 for the carry pair)
     *out_gips = instr / (ms * 1e-3) / 1e9;
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ row N1b
+extern "C" int b200zkp_dev_quotient_values(b200zkp_ctx* ctx, const b200zkp_vanishing_desc* d, const uint64_t* cs, uint64_t cs_stride,
+                                           const uint64_t* wires, uint64_t wires_stride, const uint64_t* zpp, uint64_t zpp_stride,
+                                           uint64_t* out_dev, uint64_t out_stride) {
+    if (!ctx) return B200ZKP_ERR_BAD_ARG;
+    Guard g(ctx);
+    if (!d || !cs || !wires || !zpp || !out_dev) BAD(ctx, "null argument");
+    if (!d->k_is || !d->betas || !d->gammas || !d->alphas) BAD(ctx, "null challenge / shift list");
+    const u32 Cn = d->num_challenges, R = d->num_routed_wires, deg = d->quotient_degree_factor;
+    if (Cn == 0 || Cn > vanish::MAX_CHALLENGES) BAD(ctx, "num_challenges must be 1..4");
+    if (R == 0 || R > 128 || (R & 3) || deg == 0) BAD(ctx, "bad routed wire count / chunk size");
+    if (d->n_gates == 0 || d->n_gates > vanish::MAX_GATES || d->num_selectors == 0) BAD(ctx, "bad gate list");
+    const u32 Q_log = d->degree_bits + d->quotient_degree_bits;
+    if (Q_log > 32 || d->quotient_degree_bits > 8) BAD(ctx, "quotient domain exceeds the field's two-adicity");
+    const u64 Q = (u64)1 << Q_log, n = (u64)1 << d->degree_bits;
+    if (cs_stride < Q || wires_stride < Q || zpp_stride < Q || out_stride < Q) BAD(ctx, "stride shorter than the quotient domain");
+    vanish::Params p{};
+    u32 max_constraints = 0;
+    for (u32 i = 0; i < d->n_gates; i++) {
+        static const u32 n_constraints[vanish::N_GATE_KINDS] = {0, 2, 4, 0, 123};
+        const u32 kind = d->gate_kind[i];
+        if (kind >= vanish::N_GATE_KINDS) { ctx->err = "gate kind not supported by the device evaluator"; return B200ZKP_ERR_UNSUPPORTED; }
+        if (d->gate_selector_index[i] >= d->num_selectors || d->gate_group_begin[i] > i || d->gate_group_end[i] <= i ||
+            d->gate_group_end[i] > d->n_gates)
+            BAD(ctx, "gate outside its selector group");
+        p.gates[i] = vanish::GateDesc{kind, d->gate_selector_index[i], d->gate_group_begin[i], d->gate_group_end[i]};
+        max_constraints = std::max(max_constraints, kind == vanish::GATE_ARITHMETIC ? R / 4 : n_constraints[kind]);
+    }
+    const u32 chunks = (R + deg - 1) / deg;
+    p.n_terms = Cn + Cn * chunks + max_constraints;
+    // small tables, one upload: k_is | alpha powers [C][n_terms] | Z_H on the coset | its inverse
+    const u32 qn = 1u << d->quotient_degree_bits;
+    std::vector<u64> pack(R + (size_t)Cn * p.n_terms + 2 * qn);
+    for (u32 j = 0; j < R; j++) pack[j] = gl_host_canon(d->k_is[j]);
+    for (u32 c = 0; c < Cn; c++) {
+        u64 a = gl_host_canon(d->alphas[c]), x = 1;
+        for (u32 t = 0; t < p.n_terms; t++) { pack[R + (size_t)c * p.n_terms + t] = x; x = hostgl::mul(x, a); }
+        p.betas[c] = gl_host_canon(d->betas[c]);
+        p.gammas[c] = gl_host_canon(d->gammas[c]);
+    }
+    const u64 shift_n = hostgl::pw(7, n), wq = d->quotient_degree_bits ? hostgl::root(d->quotient_degree_bits) : 1;
+    u64 wpow = 1;
+    for (u32 i = 0; i < qn; i++) {
+        const u64 zh = (hostgl::mul(shift_n, wpow) + hostgl::P - 1) % hostgl::P;       // x^n - 1 = 7^n w_(2^q)^i - 1
+        if (zh == 0) BAD(ctx, "Z_H vanishes on the coset");
+        pack[R + (size_t)Cn * p.n_terms + i] = zh;
+        pack[R + (size_t)Cn * p.n_terms + qn + i] = hostgl::inv(zh);
+        wpow = hostgl::mul(wpow, wq);
+    }
+    for (int i = 0; i < 4; i++) p.pi_hash[i] = gl_host_canon(d->public_inputs_hash[i]);
+    TwoLevel tw{};
+    TRY(get_tw(ctx, 0, Q_log, &tw));
+    void* d_pack = nullptr;
+    TRY(dev_alloc(ctx, pack.size() * 8, &d_pack));
+    int rc = h2d(ctx, d_pack, pack.data(), pack.size() * 8);
+    if (!rc) {
+        // (the pageable source is staged by the runtime before cudaMemcpyAsync returns)
+        p.cs = (const u64*)cs; p.wires = (const u64*)wires; p.zpp = (const u64*)zpp;
+        p.cs_stride = cs_stride; p.wires_stride = wires_stride; p.zpp_stride = zpp_stride;
+        p.n_log = d->degree_bits; p.q_bits = d->quotient_degree_bits;
+        p.num_selectors = d->num_selectors; p.num_gate_consts = 2; p.num_routed = R; p.num_challenges = Cn;
+        p.num_prods = chunks - 1; p.degree = deg; p.n_gates = d->n_gates;
+        p.k_is = (const u64*)d_pack;
+        p.alpha_pows = p.k_is + R;
+        p.zh = p.alpha_pows + (size_t)Cn * p.n_terms;
+        p.zh_inv = p.zh + qn;
+        p.tw_lo = tw.lo; p.tw_hi = tw.hi; p.tw_lo_bits = tw.lo_bits;
+        p.n_inv = hostgl::inv(n % hostgl::P);
+        p.out = (u64*)out_dev; p.out_stride = out_stride;
+        vanish::quotient_values_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, ctx->stream>>>(p);
+        ctx->launches++;
+        if (cudaGetLastError() != cudaSuccess) { ctx->err = "quotient_values_kernel launch failed"; rc = B200ZKP_ERR_CUDA; }
+    }
+    dev_release(ctx, d_pack, pack.size() * 8);     // (stream ordered: the next user of this buffer runs after the kernel)
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU (NCCL)

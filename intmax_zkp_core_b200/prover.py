@@ -157,3 +157,72 @@ def commit_quotient_device(ctx: Context, quotient_values, degree_bits: int, rate
             raise QuotientError("Quotient has failed: coefficients beyond quotient_degree_factor * n are not zero")
         coeffs = coeffs[:, :qdf * n].contiguous()
     return commit_device(ctx, coeffs.view(Cn * qdf, n), rate_bits, cap_height, is_coeffs=True)
+
+
+# ------------------------------------------------------------------------------------------------ row N1b: compute_quotient_polys
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = range(5)
+MAX_GATES = 16
+
+
+class _VanishingDesc(C.Structure):
+    _fields_ = [("degree_bits", C.c_uint32), ("quotient_degree_bits", C.c_uint32), ("quotient_degree_factor", C.c_uint32),
+                ("num_routed_wires", C.c_uint32), ("num_challenges", C.c_uint32), ("num_selectors", C.c_uint32),
+                ("n_gates", C.c_uint32),
+                ("gate_kind", C.c_uint32 * MAX_GATES), ("gate_selector_index", C.c_uint32 * MAX_GATES),
+                ("gate_group_begin", C.c_uint32 * MAX_GATES), ("gate_group_end", C.c_uint32 * MAX_GATES),
+                ("k_is", C.c_void_p), ("betas", C.c_void_p), ("gammas", C.c_void_p), ("alphas", C.c_void_p),
+                ("public_inputs_hash", C.c_uint64 * 4)]
+
+
+class CommonCircuitData:
+    """What compute_quotient_polys needs of plonky2's CommonCircuitData: degree_bits, the gate list in CircuitBuilder's order with
+    the selector polynomial and selector group of every gate (SelectorsInfo), quotient_degree_factor, k_is.
+    gates: [(kind, selector_index, (group_begin, group_end)), ...]"""
+
+    def __init__(self, degree_bits: int, gates, num_selectors: int, quotient_degree_factor: int = 8, num_routed_wires: int = 80,
+                 k_is=None):
+        self.degree_bits, self.gates, self.num_selectors = degree_bits, list(gates), num_selectors
+        self.quotient_degree_factor, self.num_routed_wires = quotient_degree_factor, num_routed_wires
+        self.k_is = _u64(k_is) if k_is is not None else get_unique_coset_shifts(num_routed_wires)
+        if len(self.gates) > MAX_GATES:
+            raise ValueError("too many gate types")
+
+    @property
+    def quotient_degree_bits(self) -> int:
+        return max(self.quotient_degree_factor - 1, 0).bit_length()        # log2_ceil
+
+
+def compute_quotient_values_device(ctx: Context, common: CommonCircuitData, constants_sigmas_lde, wires_lde, zs_partial_products_lde,
+                                   betas, gammas, alphas, public_inputs_hash, out=None):
+    """compute_quotient_polys up to its coset_ifft, on the three LDEs where the commitments left them: (columns, N) CUDA tensors
+    in leaf order (DeviceCommitment.lde).  Returns the (num_challenges, n << quotient_degree_bits) quotient values in natural order
+    on the coset 7 <w> — the input of commit_quotient_device."""
+    import torch
+    q_bits = common.quotient_degree_bits
+    Q = 1 << (common.degree_bits + q_bits)
+    b, g, a = (_u64(np.asarray(v, dtype=np.uint64)) for v in (betas, gammas, alphas))
+    if not (b.shape == g.shape == a.shape) or b.ndim != 1:
+        raise ValueError("one beta, gamma and alpha per challenge")
+    for t in (constants_sigmas_lde, wires_lde, zs_partial_products_lde):
+        if not t.is_cuda or t.stride(1) != 1 or t.shape[1] < Q:
+            raise ValueError("LDEs must be CUDA tensors of at least n << quotient_degree_bits leaves per column")
+    chunks = -(-common.num_routed_wires // common.quotient_degree_factor)
+    if constants_sigmas_lde.shape[0] != common.num_selectors + 2 + common.num_routed_wires or wires_lde.shape[0] < 135 \
+            or zs_partial_products_lde.shape[0] != b.size * chunks:
+        raise ValueError("batch widths do not match the circuit description")
+    d = _VanishingDesc()
+    d.degree_bits, d.quotient_degree_bits, d.quotient_degree_factor = common.degree_bits, q_bits, common.quotient_degree_factor
+    d.num_routed_wires, d.num_challenges, d.num_selectors, d.n_gates = common.num_routed_wires, b.size, common.num_selectors, len(common.gates)
+    for i, (kind, sel, grp) in enumerate(common.gates):
+        d.gate_kind[i], d.gate_selector_index[i], d.gate_group_begin[i], d.gate_group_end[i] = kind, sel, grp[0], grp[1]
+    k = _u64(common.k_is)
+    d.k_is, d.betas, d.gammas, d.alphas = k.ctypes.data, b.ctypes.data, g.ctypes.data, a.ctypes.data
+    for i, v in enumerate(public_inputs_hash):
+        d.public_inputs_hash[i] = int(v)
+    if out is None:
+        out = torch.empty((b.size, Q), dtype=torch.int64, device=wires_lde.device)
+    ctx.check(ctx._lib.b200zkp_dev_quotient_values(ctx._h, C.byref(d), C.c_void_p(constants_sigmas_lde.data_ptr()), constants_sigmas_lde.stride(0),
+                                                   C.c_void_p(wires_lde.data_ptr()), wires_lde.stride(0),
+                                                   C.c_void_p(zs_partial_products_lde.data_ptr()), zs_partial_products_lde.stride(0),
+                                                   C.c_void_p(out.data_ptr()), out.stride(0)))
+    return out
