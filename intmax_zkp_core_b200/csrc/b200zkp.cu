@@ -2228,7 +2228,8 @@ extern "C" int b200zkp_dev_quotient_values(b200zkp_ctx* ctx, const b200zkp_vanis
     const u64 shift_n = hostgl::pw(7, n), wq = d->quotient_degree_bits ? hostgl::root(d->quotient_degree_bits) : 1;
     u64 wpow = 1;
     for (u32 i = 0; i < qn; i++) {
-        const u64 zh = (hostgl::mul(shift_n, wpow) + hostgl::P - 1) % hostgl::P;       // x^n - 1 = 7^n w_(2^q)^i - 1
+        const u64 xn = hostgl::mul(shift_n, wpow);                  // x^n = 7^n w_(2^q)^i
+        const u64 zh = xn ? xn - 1 : hostgl::P - 1;
         if (zh == 0) BAD(ctx, "Z_H vanishes on the coset");
         pack[R + (size_t)Cn * p.n_terms + i] = zh;
         pack[R + (size_t)Cn * p.n_terms + qn + i] = hostgl::inv(zh);

@@ -175,12 +175,10 @@ GL_FN void poseidon_gate(const u64* __restrict__ w, u64 stride, Fold& f) {
     for (int i = 0; i < 12; i++) f.add(gl::sub(s[i], wire(W_OUT + i)));
 }
 
-#ifndef B200ZKP_HOST_EMU
-__global__ void __launch_bounds__(128)
-quotient_values_kernel(const Params p) {
+// everything one thread does: leaf position t of the quotient coset (also stepped on the host by tests/emu)
+GL_FN void quotient_point(const Params& p, u64 t) {
     const u32 Q_log = p.n_log + p.q_bits;
     const u64 Q = (u64)1 << Q_log;
-    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;      // leaf position
     if (t >= Q) return;
     const u32 C = p.num_challenges;
     const u64 i = Q_log ? (gl::brev64(t) >> (64 - Q_log)) : 0;       // natural index on the quotient coset
@@ -215,7 +213,7 @@ quotient_values_kernel(const Params p) {
             const u64 next = (l + 1 < chunks) ? zp[(u64)(C + c * p.num_prods + l) * p.zpp_stride]
                                               : p.zpp[(u64)c * p.zpp_stride + t_next];
             u64 num = 1, den = 1;
-            const u32 j1 = min(p.num_routed, (l + 1) * p.degree);
+            const u32 j1 = p.num_routed < (l + 1) * p.degree ? p.num_routed : (l + 1) * p.degree;
             for (u32 j = l * p.degree; j < j1; j++) {
                 const u64 wj = wr[(u64)j * p.wires_stride];
                 const u64 wg = gl::add(wj, gamma);
@@ -266,6 +264,10 @@ quotient_values_kernel(const Params p) {
     }
     for (u32 c = 0; c < C; c++) p.out[(u64)c * p.out_stride + i] = gl::mul(acc[c], zh_inv);
 }
+
+#ifndef B200ZKP_HOST_EMU
+__global__ void __launch_bounds__(128)
+quotient_values_kernel(const Params p) { quotient_point(p, (u64)blockIdx.x * blockDim.x + threadIdx.x); }
 #endif
 
 }  // namespace vanish

@@ -9,6 +9,7 @@
 
 #include "../../intmax_zkp_core_b200/csrc/merkle_kernels.cuh"
 #include "../../intmax_zkp_core_b200/csrc/perm_kernels.cuh"
+#include "../../intmax_zkp_core_b200/csrc/vanishing_kernels.cuh"
 #include "../../intmax_zkp_core_b200/csrc/host_plan.hpp"
 
 using gl::u32;
@@ -140,6 +141,37 @@ int emu_ct_lde(const u64* coeffs, u64* lde, u32 n_log, u32 k, u32 rate_bits, u32
     if (!ntc::make_plan(&plan, coeffs, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, k, b1 - b0, n, false, z.data(), zf.data(), 0, false)) return 0;
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
     return 1;
+}
+// row N1b: vanish::quotient_point stepped over every leaf of the quotient coset; LDEs [columns][Q] in leaf order,
+// gates: n_gates x (kind, selector_index, group_begin, group_end); out [C][Q] natural order
+void emu_quotient_values(const u64* cs, const u64* wires, const u64* zpp, u32 n_log, u32 q_bits, u32 num_selectors, u32 C, u32 degree,
+                         const u32* gates, u32 n_gates, const u64* k_is, const u64* betas, const u64* gammas, const u64* alphas,
+                         const u64* pi_hash, u64* out) {
+    vanish::Params p{};
+    const u32 R = 80, Q_log = n_log + q_bits;
+    const u64 Q = (u64)1 << Q_log, n = (u64)1 << n_log;
+    p.cs = cs; p.wires = wires; p.zpp = zpp; p.cs_stride = p.wires_stride = p.zpp_stride = Q;
+    p.n_log = n_log; p.q_bits = q_bits; p.num_selectors = num_selectors; p.num_gate_consts = 2; p.num_routed = R;
+    p.num_challenges = C; p.degree = degree; p.num_prods = (R + degree - 1) / degree - 1; p.n_gates = n_gates;
+    u32 max_c = 0;
+    for (u32 i = 0; i < n_gates; i++) {
+        p.gates[i] = vanish::GateDesc{gates[4 * i], gates[4 * i + 1], gates[4 * i + 2], gates[4 * i + 3]};
+        const u32 nc[5] = {0, 2, 4, R / 4, 123};
+        if (nc[gates[4 * i]] > max_c) max_c = nc[gates[4 * i]];
+    }
+    p.n_terms = C + C * (p.num_prods + 1) + max_c;
+    std::vector<u64> apw((size_t)C * p.n_terms), zh(1u << q_bits), zhi(1u << q_bits), lo, hi;
+    for (u32 c = 0; c < C; c++) { u64 x = 1; for (u32 t = 0; t < p.n_terms; t++) { apw[(size_t)c * p.n_terms + t] = x; x = hostgl::mul(x, alphas[c]); } p.betas[c] = betas[c]; p.gammas[c] = gammas[c]; }
+    const u64 shift_n = hostgl::pw(7, n), wq = q_bits ? hostgl::root(q_bits) : 1;
+    u64 wp = 1;
+    for (u32 i = 0; i < (1u << q_bits); i++) { { const u64 xn = hostgl::mul(shift_n, wp); zh[i] = xn ? xn - 1 : hostgl::P - 1; } zhi[i] = hostgl::inv(zh[i]); wp = hostgl::mul(wp, wq); }
+    p.tw_lo_bits = hostgl::two_level_powers(hostgl::root(Q_log), Q_log, &lo, &hi);
+    p.tw_lo = lo.data(); p.tw_hi = hi.data();
+    for (int i = 0; i < 4; i++) p.pi_hash[i] = pi_hash[i];
+    p.k_is = k_is; p.alpha_pows = apw.data(); p.zh = zh.data(); p.zh_inv = zhi.data();
+    p.n_inv = hostgl::inv(n % hostgl::P);
+    p.out = out; p.out_stride = Q;
+    for (u64 t = 0; t < Q; t++) vanish::quotient_point(p, t);
 }
 u64 emu_inverse(u64 x) { return perm::inverse(x); }
 // rows of the permutation argument (perm::row_chunk_products): running[(c * chunks + l) * n + i]

@@ -161,3 +161,28 @@ def test_permutation_argument_rows(emu):
                 for l in range(num_prods):
                     assert int(running[c, l, i]) * z[i] % P == cols[Cn + c * num_prods + l][i]
                 assert int(running[c, chunks - 1, i]) * z[i] % P == (z[i + 1] if i + 1 < n else 1)
+
+
+def test_quotient_point_body(emu, oracle):
+    """row N1b: the per-point body of vanishing_kernels.cuh against oracle/vanishing_ref.py on a satisfied synthetic circuit"""
+    import random
+    from oracle import perm_ref as PR
+    from oracle import vanishing_ref as V
+    n_log, r = 3, 3
+    c = V.Circuit(n_log, seed=1)
+    rnd = random.Random(8)
+    betas, gammas, alphas = ([rnd.randrange(P) for _ in range(2)] for _ in range(3))
+    zs_pp = PR.partial_products_and_zs([c.wires[j] for j in range(80)], c.sigmas, c.k_is, betas, gammas, 8)
+    lde = lambda cols: [oracle.coset_lde(oracle.ifft(np.array(col, np.uint64)), r) for col in cols]
+    l_cs, l_w, l_z = lde(c.constants + c.sigmas), lde(c.wires), lde(zs_pp)
+    want = np.array(V.quotient_values(c, l_cs, l_w, l_z, betas, gammas, alphas, 8, r, 3), np.uint64)
+    perm = bitrev_perm(n_log + r)
+    leaf = lambda cols: np.ascontiguousarray(np.stack([col[perm] for col in cols]))
+    gates = np.array([[g, c.selector_indices[i], *c.groups[c.selector_indices[i]]] for i, g in enumerate(c.gates)], np.uint32)
+    out = np.zeros((2, 1 << (n_log + r)), np.uint64)
+    u32p = C.POINTER(C.c_uint32)
+    a = lambda v: np.array(v, np.uint64)
+    cs_l, w_l, z_l = leaf(l_cs), leaf(l_w), leaf(l_z)
+    emu.emu_quotient_values(ptr(cs_l), ptr(w_l), ptr(z_l), n_log, 3, c.num_selectors, 2, 8, gates.ctypes.data_as(u32p), len(c.gates),
+                            ptr(a(c.k_is)), ptr(a(betas)), ptr(a(gammas)), ptr(a(alphas)), ptr(a(c.pi_hash)), ptr(out))
+    assert (out == want).all()
