@@ -394,9 +394,50 @@ def latency_block(torch, np, ctx, reps=20):
         out["opening_proof_2^16 (85+135+20+16 polys, standard_recursion_config, host wall clock)"] = round(statistics.median(ts), 4)
         del oracles
         hctx.close()
+        out.update(prove_chain_latency(torch, np, ctx, n_log))
     except Exception as e:      # the latency block must never take the headline down with it
         out["opening_proof_2^16"] = f"failed: {e!r}"
     return out
+
+
+def prove_chain_latency(torch, np, ctx, n_log=16, reps=5):
+    """The device-resident middle of plonky2's prove() for a 2^n_log-row standard_recursion_config circuit whose gate set is
+    Noop / Constant / PublicInput / Arithmetic / Poseidon: wires commitment -> Z + partial products (N1a) -> their commitment ->
+    vanishing polynomial on the coset / Z_H (N1b) -> coset_ifft + quotient chunk commitment (N1c).  Only challenges and caps would
+    cross PCIe.  Timing is data independent, so the matrices are random (the satisfied-circuit checks live in tests/)."""
+    from intmax_zkp_core_b200 import device as D, prover as zp
+    n = 1 << n_log
+    gates = [(zp.GATE_NOOP, 0, (0, 4)), (zp.GATE_CONSTANT, 0, (0, 4)), (zp.GATE_PUBLIC_INPUT, 0, (0, 4)), (zp.GATE_ARITHMETIC, 0, (0, 4)),
+             (zp.GATE_POSEIDON, 1, (4, 5))]
+    common = zp.CommonCircuitData(n_log, gates, 2)
+    rnd = lambda k: torch.randint(0, 2**62, (k, n), dtype=torch.int64, device="cuda")
+    cs, wires = rnd(84), rnd(135)
+    com_cs = D.commit_device(ctx, cs, RATE_BITS, CAP_HEIGHT)         # CircuitBuilder::build, not part of prove()
+    com_w = D.DeviceCommitment(n_log, 135, RATE_BITS, CAP_HEIGHT, wires.device)
+    com_z = D.DeviceCommitment(n_log, 20, RATE_BITS, CAP_HEIGHT, wires.device)
+    betas, gammas, alphas = [3, 5], [7, 11], [13, 17]
+    k_is = common.k_is
+    stages = {"wires_commit": [], "zs_partial_products": [], "zs_commit": [], "quotient_values": [], "quotient_commit": [], "total": []}
+    for it in range(reps + 2):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev[0].record()
+        D.commit_device(ctx, wires, RATE_BITS, CAP_HEIGHT, out=com_w)
+        ev[1].record()
+        zpp = zp.zs_partial_products_device(ctx, wires[:80], cs[4:84], k_is, betas, gammas, 8)
+        ev[2].record()
+        D.commit_device(ctx, zpp, RATE_BITS, CAP_HEIGHT, out=com_z)
+        ev[3].record()
+        q = zp.compute_quotient_values_device(ctx, common, com_cs.lde, com_w.lde, com_z.lde, betas, gammas, alphas, [1, 2, 3, 4])
+        ev[4].record()
+        zp.commit_quotient_device(ctx, q, n_log, RATE_BITS, CAP_HEIGHT)
+        ev[5].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            for name, a, b in zip(list(stages)[:5], ev[:5], ev[1:]):
+                stages[name].append(a.elapsed_time(b))
+            stages["total"].append(ev[0].elapsed_time(ev[5]))
+    return {f"prove_middle_2^{n_log} (wires commit -> Z -> commit -> quotient -> commit; device resident)":
+            {k: round(statistics.median(v), 4) for k, v in stages.items()}}
 
 
 def leaf_mix():
