@@ -197,6 +197,17 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm helpers
+def bind_to_gpu_numa_node(gpu_index):
+    """N > 1: run this rank (and allocate its pinned staging memory) on the CPUs next to its GPU, so that eight uploads do not
+    all cross the same socket link (NVML's ideal CPU affinity of the device); harmless where NVML or the call is unavailable"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(gpu_index))
+    except Exception:
+        pass
+
+
 def synth_host(torch, np, col_begin, col_end, n, rows_alloc=None):
     """pinned (rows_alloc, n) int64 tensor holding v[c][i] = splitmix64(c*n + i) mod p for columns [col_begin, col_end)"""
     idx = np.arange(col_begin * n, col_end * n, dtype=np.uint64)
@@ -470,6 +481,7 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("gloo")        # bootstrap, barriers and the max over ranks only; the data path is NCCL from C
     n_log = int(os.environ.get("B200ZKP_BENCH_N_LOG", str(N_LOG)))
     k = int(os.environ.get("B200ZKP_BENCH_K", str(K)))

@@ -370,8 +370,9 @@ static int sharded_commit_rank(b200zkp_sharded* sh, int i, const u64* input, int
 
     // ---- 2. exchange of the coefficient shards in point-to-point groups on the exchange stream, and the coset transforms
     //         of every shard as soon as it is here (own shard first)
-    auto lde_shard = [&](u32 src) -> int {
-        u32 a = std::min(sh->k, src * sh->kp), b = std::min(sh->k, (src + 1) * sh->kp);
+    // coset transforms of the shards of ranks [src_lo, src_hi] (adjacent ranks hold adjacent columns: one launch sequence)
+    auto lde_shards = [&](u32 src_lo, u32 src_hi) -> int {
+        u32 a = std::min(sh->k, src_lo * sh->kp), b = std::min(sh->k, (src_hi + 1) * sh->kp);
         if (b == a) return 0;
         return dev_lde_locked(ctx, s.coeffs_all + (u64)a * n, n, s.lde + (u64)a * sh->N_local, sh->N_local, sh->n_log, b - a,
                               sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr);
@@ -380,7 +381,7 @@ static int sharded_commit_rank(b200zkp_sharded* sh, int i, const u64* input, int
         CUDA_TRY(ctx, cudaEventRecord(ev[0], main_s));            // own coefficients ready; earlier readers of coeffs_all done
         CUDA_TRY(ctx, cudaStreamWaitEvent(xs, ev[0], 0));
     }
-    TRY(lde_shard(g));
+    TRY(lde_shards(g, g));
     if (G > 1) {
         const u32 per_group = c->peers_per_group ? c->peers_per_group : (G - 1);
         const size_t count = (size_t)sh->kp * n;
@@ -397,7 +398,14 @@ static int sharded_commit_rank(b200zkp_sharded* sh, int i, const u64* input, int
             ctx->launches++;
             CUDA_TRY(ctx, cudaEventRecord(ev[2 + gi], xs));
             CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, ev[2 + gi], 0));
-            for (u32 d = d0; d < d1; d++) TRY(lde_shard((g + G - d) % G));
+            // sources g - d0, g - d0 - 1, ..., g - (d1 - 1) (mod G): descending ranks, split where the index wraps below 0
+            u32 hi = (g + G - d0) % G, lo = hi;
+            for (u32 d = d0 + 1; d <= d1; d++) {
+                const u32 src = (g + G - d) % G;
+                if (d < d1 && src + 1 == lo) { lo = src; continue; }
+                TRY(lde_shards(lo, hi));
+                hi = lo = src;
+            }
         }
     }
 

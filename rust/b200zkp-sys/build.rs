@@ -12,4 +12,6 @@ fn main() {
         .include(root.join("include"))
         .file(src)
         .compile("b200zkp");
+    // libnccl.so.2 is loaded at run time (dlopen) by the multi-GPU entry points only
+    println!("cargo:rustc-link-lib=dl");
 }

@@ -7,6 +7,31 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct b200zkp_batch { _p: [u8; 0] }
 #[repr(C)] pub struct b200zkp_fri { _p: [u8; 0] }
 #[repr(C)] pub struct b200zkp_tree { _p: [u8; 0] }
+#[repr(C)] pub struct b200zkp_comm { _p: [u8; 0] }
+#[repr(C)] pub struct b200zkp_sharded { _p: [u8; 0] }
+
+pub const B200ZKP_COMM_ID_BYTES: usize = 128;
+pub const B200ZKP_MAX_GATES: usize = 16;
+/// include/b200zkp.h `b200zkp_vanishing_desc` (row N1b: what compute_quotient_polys reads of CommonCircuitData)
+#[repr(C)]
+pub struct b200zkp_vanishing_desc {
+    pub degree_bits: u32,
+    pub quotient_degree_bits: u32,
+    pub quotient_degree_factor: u32,
+    pub num_routed_wires: u32,
+    pub num_challenges: u32,
+    pub num_selectors: u32,
+    pub n_gates: u32,
+    pub gate_kind: [u32; B200ZKP_MAX_GATES],
+    pub gate_selector_index: [u32; B200ZKP_MAX_GATES],
+    pub gate_group_begin: [u32; B200ZKP_MAX_GATES],
+    pub gate_group_end: [u32; B200ZKP_MAX_GATES],
+    pub k_is: *const u64,
+    pub betas: *const u64,
+    pub gammas: *const u64,
+    pub alphas: *const u64,
+    pub public_inputs_hash: [u64; 4],
+}
 
 extern "C" {
     pub fn b200zkp_ctx_create(device: c_int, stream: *mut c_void, out: *mut *mut b200zkp_ctx) -> c_int;
@@ -58,4 +83,34 @@ extern "C" {
     pub fn b200zkp_dev_partial_products_and_zs(ctx: *mut b200zkp_ctx, wires_dev: *const u64, wires_col_stride: u64,
         sigmas_dev: *const u64, sigmas_col_stride: u64, n_log: u32, num_routed: u32, degree: u32, k_is: *const u64,
         betas: *const u64, gammas: *const u64, num_challenges: u32, out_dev: *mut u64, out_col_stride: u64) -> c_int;
+    // Fiat-Shamir transcript: any number of duplexing steps in one launch (iop/challenger.rs)
+    pub fn b200zkp_duplex_chain(ctx: *mut b200zkp_ctx, state: *mut u64, inputs: *const u64, n_inputs: u64, n_squeeze: u32,
+        squeezed: *mut u64) -> c_int;
+    // row N1b: compute_quotient_polys up to its coset_ifft, on the device-resident LDEs
+    pub fn b200zkp_dev_quotient_values(ctx: *mut b200zkp_ctx, desc: *const b200zkp_vanishing_desc, constants_sigmas: *const u64,
+        cs_stride: u64, wires: *const u64, wires_stride: u64, zs_partial_products: *const u64, zpp_stride: u64,
+        out_dev: *mut u64, out_stride: u64) -> c_int;
+    pub fn b200zkp_ctx_trim(ctx: *mut b200zkp_ctx) -> c_int;
+    pub fn b200zkp_ctx_set_pool_limit(ctx: *mut b200zkp_ctx, bytes: u64) -> c_int;
+
+    // one commitment partitioned over every GPU of the box, driven by this (single, rayon) process: NCCL inside the library
+    pub fn b200zkp_comm_init_all(ctxs: *const *mut b200zkp_ctx, n: c_int, out: *mut *mut b200zkp_comm) -> c_int;
+    pub fn b200zkp_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn b200zkp_comm_init_rank(ctx: *mut b200zkp_ctx, id: *const u8, rank: c_int, world: c_int, out: *mut *mut b200zkp_comm) -> c_int;
+    pub fn b200zkp_comm_destroy(comm: *mut b200zkp_comm);
+    pub fn b200zkp_comm_last_error(comm: *const b200zkp_comm) -> *const c_char;
+    pub fn b200zkp_comm_shape(comm: *const b200zkp_comm, shape: *mut i32) -> c_int;
+    pub fn b200zkp_comm_set_exchange_group(comm: *mut b200zkp_comm, peers_per_group: u32) -> c_int;
+    pub fn b200zkp_sharded_create(comm: *mut b200zkp_comm, n_log: u32, k: u32, rate_bits: u32, cap_height: u32,
+        out: *mut *mut b200zkp_sharded) -> c_int;
+    pub fn b200zkp_sharded_free(sh: *mut b200zkp_sharded);
+    pub fn b200zkp_sharded_layout(sh: *const b200zkp_sharded, local: c_int, lay: *mut u64) -> c_int;
+    pub fn b200zkp_sharded_commit(sh: *mut b200zkp_sharded, inputs: *const *const u64, inputs_on_device: c_int, is_coeffs: c_int,
+        cap_out: *mut u64) -> c_int;
+    pub fn b200zkp_sharded_commit_from_values(comm: *mut b200zkp_comm, values: *const u64, n_log: u32, k: u32, rate_bits: u32,
+        cap_height: u32, cap_out: *mut u64, out: *mut *mut b200zkp_sharded) -> c_int;
+    pub fn b200zkp_sharded_synchronize(sh: *mut b200zkp_sharded) -> c_int;
+    pub fn b200zkp_sharded_device_ptrs(sh: *mut b200zkp_sharded, local: c_int, coeffs: *mut *const u64, lde: *mut *const u64,
+        digests: *mut *const u64, cap: *mut *const u64) -> c_int;
+    pub fn b200zkp_sharded_rows(sh: *mut b200zkp_sharded, idx: *const u64, n_idx: u64, rows: *mut u64, siblings: *mut u64) -> c_int;
 }
