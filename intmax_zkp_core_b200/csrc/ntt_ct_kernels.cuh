@@ -140,7 +140,8 @@ GL_FN void run_round(const u64* __restrict__ src, u64* __restrict__ dst, const u
     }
 }
 
-// all rounds of a B-bit pass: the short round (B mod 3 levels) first, radix-8 rounds after it
+// all rounds of a B-bit pass: the short round (B mod 3 levels) first, radix-8 rounds after it.  The caller places the barrier
+// after the last round (the TMA store path needs its proxy fence between the last writes and that barrier).
 template <int B, bool SCALE>
 GL_FN void run_rounds(const u64* first_src, u64* tile, const u64* tw, u32 tw_pitch, u32 T_log, u32 pitch, u64 a_scale) {
     u32 u0 = 0;
@@ -154,7 +155,6 @@ GL_FN void run_rounds(const u64* first_src, u64* tile, const u64* tw, u32 tw_pit
         NTC_SYNC();
     }
     NTC_FOR_THREADS(tid) { run_round<3, SCALE>(src, tile, tw, tw_pitch, B, T_log, pitch, u0, a_scale, tid); }
-    NTC_SYNC();
 }
 
 // ---------------------------------------------------------------------------------------------------- TMA / mbarrier
@@ -286,6 +286,7 @@ GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_o
             continue;
         }
 #endif
+        NTC_SYNC();
         NTC_FOR_THREADS(tid) {
 #pragma unroll
             for (u32 it = 0; it < IT; it++) {
@@ -372,6 +373,7 @@ GL_FN void final_body(const PassParams& p, u64* smem, u32 bid) {
 
     if (p.a_scale) run_rounds<B, true>(tile, tile, swb, TWP, T_log, TP, p.a_scale);
     else run_rounds<B, false>(tile, tile, swb, TWP, T_log, TP, 0);
+    NTC_SYNC();
 
     NTC_FOR_THREADS(tid) {
         if (NATURAL) {
