@@ -57,7 +57,7 @@ def bench_config(n_log, k, world):
             "cells_per_step": k << n_log,
             "l2": "no flush needed: every step streams 8nk bytes of input and 64nk of LDE (>> 126 MB L2)",
             "partition": "single GPU" if world == 1 else
-            f"one commitment over {world} GPUs: column-sharded iNTT, NCCL exchange of the coefficient shards, leaf-range LDE+Merkle, all-gather cap"}
+            f"one commitment over {world} GPUs: column-sharded iNTT, all-gather of the coefficient shards (fused into the first LDE pass over NVLink peer memory; NCCL point-to-point as fallback), leaf-range LDE+Merkle, all-gather cap"}
 
 
 def algorithmic_bytes(n_log, k, r=RATE_BITS, h=CAP_HEIGHT):
@@ -640,7 +640,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 << CAP_HEIGHT,
                     "api": "b200zkp_commit_from_values + b200zkp_batch_cap (pinned host buffers)" if world == 1 else
-                           "b200zkp_sharded_commit (host inputs): pinned column shard H2D (chunked, overlapped with the inverse transform) + commit + cap D2H per rank"},
+                           "b200zkp_sharded_commit (host inputs): pinned column shard H2D in column chunks, pipelined with the inverse transforms, the gather and the coset transforms + commit + cap D2H per rank"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "merkle::leaf_hash_kernel", "bound": "int", "hbm": {
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -658,6 +658,9 @@ def run_b200(args):
             "poseidon_perms_per_s": perms / (ms_step * 1e-3),
             "cap_checksum": cap_checksum,
         }
+        if world > 1:
+            line["exchange"] = ("peer memory (coefficient tiles pulled over NVLink inside ntc::ct_pull_kernel, flags in peer memory)"
+                                if comm.peer_exchange else "NCCL point-to-point groups")
         if e2e_strict:
             line["e2e_strict"] = e2e_strict
         if parity is not None:

@@ -301,12 +301,19 @@ int b200zkp_dev_quotient_values(b200zkp_ctx* ctx, const b200zkp_vanishing_desc* 
                                 uint64_t cs_stride, const uint64_t* wires, uint64_t wires_stride,
                                 const uint64_t* zs_partial_products, uint64_t zpp_stride, uint64_t* out_dev, uint64_t out_stride);
 
-/* ---- one commitment partitioned over several GPUs (NCCL over NVLink / NVSwitch) ----------------------
+/* ---- one commitment partitioned over several GPUs (NVLink / NVSwitch peer memory + NCCL) --------------
  * north_star's partition: rank g of G (a power of two, G <= 2^rate_bits and G <= 2^cap_height) inverse-transforms columns
- * [g*kp, (g+1)*kp), kp = ceil(k/G); the coefficient shards are exchanged with NCCL point-to-point groups (a few peers per
- * group, so the coset transforms of the shards already received overlap the rest of the exchange); every rank then extends
- * ALL k columns on its 2^rate_bits/G coset blocks = leaves [g*N/G, (g+1)*N/G), hashes them and builds its 2^cap_height/G
- * cap subtrees without further communication; one ncclAllGather of 32 * 2^cap_height bytes hands every rank the cap.
+ * [g*kp, (g+1)*kp), kp = ceil(k/G), into its "exchange window"; every rank then extends ALL k columns on its
+ * 2^rate_bits/G coset blocks = leaves [g*N/G, (g+1)*N/G), hashes them and builds its 2^cap_height/G cap subtrees without
+ * further communication; one ncclAllGather of 32 * 2^cap_height bytes hands every rank the cap.
+ * The all-gather of the coefficients in between has two forms:
+ *   peer exchange (default when every rank can map every other rank's memory: peer access inside one process, CUDA IPC
+ *     between processes, at most 8 ranks): the first pass of the coset transforms reads its coefficient tiles straight from
+ *     the owners' windows over NVLink and files them in the local coefficient matrix on the way (one fused kernel, no NCCL
+ *     call, no staging); ordering by epoch-stamped flags in peer memory.  Host inputs are cut into column chunks whose
+ *     upload, inverse transform, gather and coset transforms form a pipeline.
+ *   NCCL exchange (fallback, or b200zkp_comm_set_peer_exchange(comm, 0) / B200ZKP_PEER_EXCHANGE=0): point-to-point groups of a
+ *     few peers, so the coset transforms of the shards already received overlap the rest of the exchange.
  *
  * Two ways to form the communicator, matching how the caller is deployed:
  *   b200zkp_comm_init_all   ONE process drives n GPUs (what a single rayon `prove()` process needs; plonky2 is one process,
@@ -327,8 +334,12 @@ void b200zkp_comm_destroy(b200zkp_comm* comm);
 const char* b200zkp_comm_last_error(const b200zkp_comm* comm);
 /* shape: world size, ranks driven by this process (1 after init_rank, world after init_all), global rank of local rank 0 */
 int b200zkp_comm_shape(const b200zkp_comm* comm, int32_t shape[3]);
-/* peers per exchange group (default 2; 0 = the whole exchange in one group, i.e. no overlap with the transforms) */
+/* NCCL exchange: peers per group (default 2; 0 = the whole exchange in one group, i.e. no overlap with the transforms) */
 int b200zkp_comm_set_exchange_group(b200zkp_comm* comm, uint32_t peers_per_group);
+/* choose between the two forms of the exchange (collective: the same value on every process, between commits);
+ * b200zkp_comm_peer_exchange: 1 when the peer form is the one in use (it was set up successfully and is switched on) */
+int b200zkp_comm_set_peer_exchange(b200zkp_comm* comm, int enabled);
+int b200zkp_comm_peer_exchange(const b200zkp_comm* comm);
 
 /* buffers of one partitioned commitment on every local rank (coefficients of all k columns, the rank's leaf range of the
  * LDE, its digests, the full cap); reusable for any number of commits of that shape */
@@ -339,7 +350,8 @@ void b200zkp_sharded_free(b200zkp_sharded* sh);
 int b200zkp_sharded_layout(const b200zkp_sharded* sh, int local, uint64_t lay[8]);
 /* PolynomialBatch::from_values / from_coeffs, partitioned.  inputs[i]: columns [col_begin, col_end) of local rank i,
  * column-major (col_end - col_begin) * n words, host memory (pinned for full PCIe speed; the upload is chunked and
- * overlaps the inverse transforms) or, with inputs_on_device, memory of that rank's device (read on the ctx stream).
+ * overlaps the transforms) or, with inputs_on_device, memory of that rank's device (read on the ctx stream); the same
+ * kind of input on every rank.
  * cap_out: NULL -> the call only enqueues (results are complete after b200zkp_sharded_synchronize); else 4 * 2^cap_height
  * words of host memory, written before the call returns.  Collective: every process of the communicator calls it. */
 int b200zkp_sharded_commit(b200zkp_sharded* sh, const uint64_t* const* inputs, int inputs_on_device, int is_coeffs,

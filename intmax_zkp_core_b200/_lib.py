@@ -153,6 +153,8 @@ _SIGS = {
     "b200zkp_comm_last_error": (C.c_char_p, [C.c_void_p]),
     "b200zkp_comm_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "b200zkp_comm_set_exchange_group": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "b200zkp_comm_set_peer_exchange": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200zkp_comm_peer_exchange": (C.c_int, [C.c_void_p]),
     "b200zkp_sharded_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "b200zkp_sharded_free": (None, [C.c_void_p]),
     "b200zkp_sharded_layout": (C.c_int, [C.c_void_p, C.c_int, u64p]),

@@ -344,21 +344,24 @@ static bool encode_tile_map(CUtensorMap* map, const u64* base, u32 B, u32 S, u32
 }
 
 template <int B>
-static int launch_ct_b(b200zkp_ctx* ctx, int kind, const ntc::PassParams& p, u64 grid, const CUtensorMap& tm_in, const CUtensorMap& tm_out) {
+static int launch_ct_b(b200zkp_ctx* ctx, int kind, const ntc::PassParams& p, u64 grid, const CUtensorMap& tm_in, const CUtensorMap& tm_out,
+                       const ntc::PullMaps* tm_src, const CUtensorMap* tm_copy) {
     const void* fn = nullptr;
     u32 smem = 0;
     switch (kind) {
         case ntc::KIND_STRIDED: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_STRIDED>; smem = ntc::StridedSmem<B, false>::bytes; break;
         case ntc::KIND_STRIDED_LOOP: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_STRIDED_LOOP>; smem = ntc::StridedSmem<B, true>::bytes; break;
         case ntc::KIND_FINAL_INPLACE: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_FINAL_INPLACE>; smem = ntc::FinalSmem<B>::bytes; break;
+        case ntc::KIND_PULL_LOOP: fn = (const void*)ntc::ct_pull_kernel<B>; smem = ntc::StridedSmem<B, true>::bytes; break;
         default: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_FINAL_NATURAL>; smem = ntc::FinalSmem<B>::bytes; break;
     }
-    const u32 bit = 1u << ((B - ntc::MIN_BITS) * 4 + kind);
+    const u32 bit = 1u << ((B - ntc::MIN_BITS) * 5 + kind);
     if (smem > 48 * 1024 && !(ctx->ct_smem_set & bit)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->ct_smem_set |= bit;
     }
-    void* args[3] = {(void*)&p, (void*)&tm_in, (void*)&tm_out};
+    void* args[4] = {(void*)&p, (void*)&tm_in, (void*)&tm_out, nullptr};
+    if (kind == ntc::KIND_PULL_LOOP) { args[1] = (void*)tm_src; args[2] = (void*)&tm_out; args[3] = (void*)tm_copy; }
     CUDA_TRY(ctx, cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(ntc::THREADS), args, smem, ctx->stream));
     ctx->launches++;
     return 0;
@@ -370,21 +373,31 @@ static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan) {
         const u32 B = plan.bits[pi];
         const int kind = plan.kind[pi];
         if (plan.grid[pi] > 0x7fffffffull) BAD(ctx, "transform too large for one launch");
-        alignas(64) CUtensorMap tm_in, tm_out;
-        memset(&tm_in, 0, sizeof tm_in); memset(&tm_out, 0, sizeof tm_out);
+        alignas(64) CUtensorMap tm_in, tm_out, tm_copy;
+        alignas(64) ntc::PullMaps tm_src;
+        memset(&tm_in, 0, sizeof tm_in); memset(&tm_out, 0, sizeof tm_out); memset(&tm_copy, 0, sizeof tm_copy);
+        const bool pull = kind == ntc::KIND_PULL_LOOP;
+        if (pull) memset(&tm_src, 0, sizeof tm_src);
+        // physical columns the maps must cover (a column set addresses columns [0, col_limit) of the buffers)
+        const u32 map_cols = p.col_run ? p.col_limit : p.ncols;
         if (p.use_tma) {
             // the staged side of a coset loop has a single block; every other side walks the blocks of its buffer
-            const bool loop = kind == ntc::KIND_STRIDED_LOOP;
-            if (!ctx->ntt_tma ||
-                !encode_tile_map(&tm_in, p.in, B, p.S, p.C_log, loop ? 1 : p.n_blk, loop ? 0 : p.in_blk_stride, p.ncols, p.in_col_stride) ||
-                !encode_tile_map(&tm_out, p.out, B, p.S, p.C_log, p.n_blk, p.out_blk_stride, p.ncols, p.out_col_stride))
-                p.use_tma = 0;
+            const bool loop = kind == ntc::KIND_STRIDED_LOOP || pull;
+            bool ok = ctx->ntt_tma && encode_tile_map(&tm_out, p.out, B, p.S, p.C_log, p.n_blk, p.out_blk_stride, map_cols, p.out_col_stride);
+            if (ok && pull) {
+                ok = encode_tile_map(&tm_copy, p.copy_out, B, p.S, p.C_log, 1, 0, map_cols, p.copy_col_stride);
+                for (u32 q = 0; ok && q < (u32)ntc::MAX_SRC && p.src[q]; q++)
+                    ok = encode_tile_map(&tm_src.m[q], p.src[q], B, p.S, p.C_log, 1, 0, p.src_col0 + p.col_run, p.in_col_stride);
+            } else if (ok) {
+                ok = encode_tile_map(&tm_in, p.in, B, p.S, p.C_log, loop ? 1 : p.n_blk, loop ? 0 : p.in_blk_stride, map_cols, p.in_col_stride);
+            }
+            if (!ok) p.use_tma = 0;
         }
         switch (B) {
-            case 5: TRY(launch_ct_b<5>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
-            case 6: TRY(launch_ct_b<6>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
-            case 7: TRY(launch_ct_b<7>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
-            case 8: TRY(launch_ct_b<8>(ctx, kind, p, plan.grid[pi], tm_in, tm_out)); break;
+            case 5: TRY(launch_ct_b<5>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
+            case 6: TRY(launch_ct_b<6>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
+            case 7: TRY(launch_ct_b<7>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
+            case 8: TRY(launch_ct_b<8>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
             default: BAD(ctx, "internal: bad pass width");
         }
     }
@@ -661,6 +674,25 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
     // by the powers of its shift and writes leaves [(b - b0) * n, (b - b0 + 1) * n) of every column
     return run_transform(ctx, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, k, /*dir=*/0, /*bitrev_out=*/true,
                          cs + (u64)b0 * n, n, /*inverse_scale=*/false, /*canon_in=*/true, b1 - b0, n);
+}
+
+// Coset transforms of a column set of a partitioned LDE (sharded.inl): `cols` names run x n_src columns of the local LDE;
+// with cols.pull the first pass gathers the coefficients from the sources' exchange windows (peer memory) on the way.
+// Returns B200ZKP_ERR_UNSUPPORTED (nothing launched) when the block-twiddle passes do not cover the shape.
+static int dev_lde_cols_locked(b200zkp_ctx* ctx, const ntc::ColumnSet& cols, const u64* coeffs, u64 coeff_stride, u64* lde,
+                               u64 lde_stride, u32 n_log, u32 rate_bits, u32 b0, u32 b1) {
+    if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "rate_bits / n_log out of range");
+    if (b0 >= b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
+    const u64 n = (u64)1 << n_log;
+    if (!ctx->ntt_ct || !ntc::covers(n_log)) return B200ZKP_ERR_UNSUPPORTED;
+    b200zkp_ctx::ZTables z;
+    TRY(get_ztab_lde(ctx, n_log, rate_bits, &z));
+    ntc::Plan plan;
+    if (!ntc::make_plan(&plan, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, 0, b1 - b0, n, /*natural_out=*/false,
+                        z.strided + (u64)b0 * ntc::ztab_entries(n_log), z.final_ + (u64)b0 * ntc::zfinal_words(n_log), 0, ctx->ntt_tma, &cols))
+        return B200ZKP_ERR_UNSUPPORTED;
+    StageTimer tm(ctx, B200ZKP_STAGE_LDE);
+    return run_ct_plan(ctx, plan);
 }
 
 extern "C" int b200zkp_dev_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,

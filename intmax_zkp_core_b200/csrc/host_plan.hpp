@@ -214,10 +214,29 @@ static inline std::vector<u64> zfinal_host(u32 n_log, const std::vector<u64>& z,
     return f;
 }
 
+// The columns of one launch sequence of a partitioned LDE (sharded.inl): `run` columns from each of n_src sources; column i of
+// source q is physical column col0 + q * period + i of the LDE (dropped when >= limit).  pull: the first pass reads source q's
+// coefficients from column src_col0 + i of the matrix at src[q] (a peer's exchange window) and also stores them to `copy_out`.
+struct ColumnSet {
+    u32 run = 0, period = 0, col0 = 0, limit = 0, n_src = 0;
+    bool pull = false;
+    const u64* src[MAX_SRC] = {};
+    u32 src_col0 = 0;
+    u64 src_col_stride = 0;
+    u64* copy_out = nullptr;
+    u64 copy_col_stride = 0;
+};
+
 // ztab / zfinal: the strided table (ztab_entries per block) and the tile-ordered last-pass table (zfinal_words per block)
+// cols (optional): see ColumnSet; `ncols` is then ignored (run * n_src grid columns) and `in` is only read when !cols->pull
 static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch, u32 n_log,
                              u32 ncols, u32 n_blk, u64 out_blk_stride, bool natural_out, const u64* ztab, const u64* zfinal,
-                             u64 a_scale, bool use_tma) {
+                             u64 a_scale, bool use_tma, const ColumnSet* cols = nullptr) {
+    if (cols) {
+        if (natural_out || cols->run == 0 || cols->n_src == 0 || cols->n_src > (u32)MAX_SRC) return false;
+        if (cols->pull && n_blk > (u32)MAX_LOOP_BLOCKS) return false;
+        ncols = cols->run * cols->n_src;
+    }
     if (!covers(n_log) || ncols == 0 || n_blk == 0) return false;
     if (natural_out && (!scratch || n_blk != 1)) return false;
     u32 P;
@@ -242,8 +261,21 @@ static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
         int kind;
         if (last) kind = natural_out ? KIND_FINAL_NATURAL : KIND_FINAL_INPLACE;
         else kind = (pi == 0 && n_blk > 1 && n_blk <= (u32)MAX_LOOP_BLOCKS) ? KIND_STRIDED_LOOP : KIND_STRIDED;
+        if (cols) {
+            p.col_run = cols->run; p.col_period = cols->period; p.col0 = cols->col0; p.col_limit = cols->limit;
+            if (pi == 0 && cols->pull) {
+                kind = KIND_PULL_LOOP;
+                p.in = nullptr; p.in_col_stride = cols->src_col_stride; p.src_col0 = cols->src_col0;
+                p.copy_out = cols->copy_out; p.copy_col_stride = cols->copy_col_stride;
+                for (u32 q = 0; q < cols->n_src; q++) {
+                    p.src[q] = cols->src[q];
+                    if ((uintptr_t)cols->src[q] & 15) p.use_tma = 0;
+                }
+                if (((uintptr_t)p.copy_out & 15) || (p.copy_col_stride & 1)) p.use_tma = 0;
+            }
+        }
         // TMA needs 16-byte aligned bases and strides, and a real (non-zero) block stride wherever a block coordinate moves
-        if (kind == KIND_STRIDED || kind == KIND_STRIDED_LOOP) {
+        if (kind == KIND_STRIDED || kind == KIND_STRIDED_LOOP || kind == KIND_PULL_LOOP) {
             const bool in_blk_moves = kind == KIND_STRIDED && n_blk > 1;
             if (((uintptr_t)p.in | (uintptr_t)p.out) & 15) p.use_tma = 0;
             if ((p.in_col_stride | p.out_col_stride | p.out_blk_stride) & 1) p.use_tma = 0;
@@ -256,7 +288,7 @@ static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
         }
         plan->kind[pi] = kind;
         plan->pass[pi] = p;
-        plan->grid[pi] = (n >> 11) * (u64)ncols * (kind == KIND_STRIDED_LOOP ? 1 : n_blk);
+        plan->grid[pi] = (n >> 11) * (u64)ncols * ((kind == KIND_STRIDED_LOOP || kind == KIND_PULL_LOOP) ? 1 : n_blk);
         S += B;
     }
     return true;

@@ -41,12 +41,15 @@ static constexpr int TILE = 2048;      // elements per tile
 static constexpr int THREADS = 256;    // 8 elements per thread
 static constexpr int MIN_BITS = 5, MAX_BITS = 8;      // pass widths this generation is instantiated for
 static constexpr int MAX_LOOP_BLOCKS = 8;             // coset blocks one CTA produces from one staged tile
+static constexpr int MAX_SRC = 8;                     // sources (ranks of one NVLink domain) of a pull pass
 
 enum Kind : int {
     KIND_STRIDED = 0,        // [A][2^B][C] view, C >= T: tile = 2^B rows x T contiguous elements; coset blocks are grid columns
     KIND_STRIDED_LOOP = 1,   // same tile, read once, every coset block produced by the same CTA (first pass of an LDE)
     KIND_FINAL_INPLACE = 2,  // C = 1: tile = T batches of 2^B contiguous elements, stored where they came from (LDE leaf order)
     KIND_FINAL_NATURAL = 3,  // C = 1: batches picked by bit-reversed index, stored in natural order (inverse transform)
+    KIND_PULL_LOOP = 4,      // KIND_STRIDED_LOOP whose coefficient tiles come from per-source matrices (peer memory) and are
+                             // copied to a local matrix on the way: all-gather + first pass of a partitioned LDE in one kernel
 };
 
 struct PassParams {
@@ -62,7 +65,26 @@ struct PassParams {
     u64 ztab_blk_stride;      // final passes: the tile-ordered image of the last levels (see FinalSmem), block stride in words
     u64 a_scale;    // 0, or n^-1: multiplies the sum operand of the LAST level (its twiddles carry the same factor)
     u32 use_tma;
+    // column sets of a partitioned LDE (sharded.inl).  col_run = 0: grid column v is column v of in / out.  Otherwise v stands
+    // for column i = v % col_run of source q = v / col_run, which is physical column col0 + q * col_period + i of `out` (the
+    // CTA leaves when that is >= col_limit: the last source may hold fewer columns).
+    u32 col_run, col_period, col0, col_limit;
+    // pull pass (KIND_PULL_LOOP): source q's coefficients are column src_col0 + i of the matrix at src[q] (in_col_stride
+    // apart; a peer GPU's exchange window, read over NVLink), and the staged tile is also stored to column `physical` of
+    // copy_out, so that the all-gather of the coefficients happens tile by tile inside the transform
+    const u64* src[MAX_SRC];
+    u32 src_col0;
+    u64* copy_out;
+    u64 copy_col_stride;
 };
+
+// physical column of grid column v, or 0xFFFFFFFF when the CTA has nothing to do; q, i: source and column inside the source
+GL_FN u32 map_column(const PassParams& p, u32 v, u32& q, u32& i) {
+    if (p.col_run == 0) { q = 0; i = v; return v; }
+    q = v / p.col_run; i = v - q * p.col_run;
+    const u32 phys = p.col0 + q * p.col_period + i;
+    return phys < p.col_limit ? phys : 0xFFFFFFFFu;
+}
 
 GL_FN u32 ulog2(u32 e) {
 #ifdef B200ZKP_HOST_EMU
@@ -209,8 +231,10 @@ struct StridedSmem {
     static constexpr u32 bytes = tiles * TILE * 8 + sw_words * 8 + 16;
 };
 
-template <int B, bool LOOP, typename TMap>
-GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_out, u64* smem, u32 bid) {
+// PULL (LOOP only): tm_in points to MAX_SRC maps (one per source), tm_copy maps the local copy of the coefficients
+template <int B, bool LOOP, typename TMap, bool PULL = false>
+GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_out, u64* smem, u32 bid, const TMap* tm_copy = nullptr) {
+    static_assert(!PULL || LOOP, "a pull pass stages its tile apart from the work tiles");
     constexpr u32 NPTS = 1u << B;
     constexpr u32 T_log = 11 - B, T = 1u << T_log;
     constexpr u32 IT = TILE / THREADS;
@@ -221,15 +245,18 @@ GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_o
 
     const u32 V = LOOP ? p.ncols : p.ncols * p.n_blk;
     const u32 vcol = bid % V, tile_i = bid / V;
-    const u32 col = LOOP ? vcol : vcol / p.n_blk;
+    u32 src_q, src_i;
+    const u32 col = map_column(p, LOOP ? vcol : vcol / p.n_blk, src_q, src_i);
+    if (col == 0xFFFFFFFFu) return;                            // (CTA-uniform) a short last source
+    const u32 in_col = PULL ? p.src_col0 + src_i : col;
     const u32 blk_fixed = LOOP ? 0u : vcol % p.n_blk;
     const u32 tiles_per_a_log = p.C_log - T_log;
     const u32 a = tile_i >> tiles_per_a_log;
     const u32 c0 = (tile_i & ((1u << tiles_per_a_log) - 1)) << T_log;
     const u64 prefix = ((u64)1 << p.S) + a;
     const u64 elem0 = ((u64)a << (B + p.C_log)) + c0;            // element (row 0, t = 0) inside a column block
-    const u64* __restrict__ in = p.in + (u64)col * p.in_col_stride + (u64)blk_fixed * p.in_blk_stride + elem0;
-    (void)tm_in; (void)tm_out; (void)bar;
+    const u64* __restrict__ in = (PULL ? p.src[src_q] : p.in) + (u64)in_col * p.in_col_stride + (u64)blk_fixed * p.in_blk_stride + elem0;
+    (void)tm_in; (void)tm_out; (void)tm_copy; (void)bar;
 
     // ---- stage the input tile and the sub-twiddles
 #ifndef B200ZKP_HOST_EMU
@@ -239,7 +266,7 @@ GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_o
         __syncthreads();
         if (threadIdx.x == 0) {
             mbar_expect_tx(bar, TILE * 8);
-            tma_load_tile(stage, tm_in, c0, a, blk_fixed, col, bar);
+            tma_load_tile(stage, PULL ? tm_in + src_q : tm_in, c0, a, blk_fixed, in_col, bar);
         }
     }
 #else
@@ -260,10 +287,23 @@ GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_o
             }
 #pragma unroll
             for (u32 it = 0; it < IT; it++) stage[tid + it * THREADS] = v[it];
+            if (PULL) {
+                u64* __restrict__ cp = p.copy_out + (u64)col * p.copy_col_stride + elem0;
+#pragma unroll
+                for (u32 it = 0; it < IT; it++) {
+                    const u32 i = tid + it * THREADS;
+                    cp[((u64)(i >> T_log) << p.C_log) + (i & (T - 1))] = v[it];
+                }
+            }
         }
     }
 #ifndef B200ZKP_HOST_EMU
-    if (tma) mbar_wait(bar, 0);
+    if (tma) {
+        mbar_wait(bar, 0);
+        // the gathered tile goes to the local coefficient matrix straight from shared memory (the async proxy wrote it, the
+        // async proxy reads it: no fence); the group is the oldest of this CTA and completes under the first coset's rounds
+        if (PULL && threadIdx.x == 0) { tma_store_tile(tm_copy, c0, a, 0, col, stage); tma_commit(); }
+    }
 #endif
     NTC_SYNC();
 
@@ -327,7 +367,9 @@ GL_FN void final_body(const PassParams& p, u64* smem, u32 bid) {
     const u32 batches_log = p.n_log - B;                       // = S
     const u32 V = p.ncols * p.n_blk;
     const u32 vcol = bid % V, tile_i = bid / V;
-    const u32 col = vcol / p.n_blk, blk = vcol % p.n_blk;
+    u32 src_q, src_i;
+    const u32 col = map_column(p, vcol / p.n_blk, src_q, src_i), blk = vcol % p.n_blk;
+    if (col == 0xFFFFFFFFu) return;
     const u32 batch0 = tile_i << T_log;
     const u64* __restrict__ in = p.in + (u64)col * p.in_col_stride + (u64)blk * p.in_blk_stride;
     u64* __restrict__ out = p.out + (u64)col * p.out_col_stride + (u64)blk * p.out_blk_stride;
@@ -411,6 +453,18 @@ ct_pass_kernel(const PassParams p, const __grid_constant__ CUtensorMap tm_in, co
     else if (KIND == KIND_STRIDED_LOOP) strided_body<B, true>(p, &tm_in, &tm_out, smem, blockIdx.x);
     else if (KIND == KIND_FINAL_INPLACE) final_body<B, false>(p, smem, blockIdx.x);
     else final_body<B, true>(p, smem, blockIdx.x);
+}
+
+// all-gather + first pass of a partitioned LDE (sharded.inl): tile by tile, the coefficients of every source rank come over
+// NVLink from that rank's exchange window into shared memory, from where they are both stored to the local coefficient
+// matrix and transformed for this rank's coset blocks
+struct PullMaps { CUtensorMap m[MAX_SRC]; };
+template <int B>
+__global__ void __launch_bounds__(THREADS, 4)
+ct_pull_kernel(const PassParams p, const __grid_constant__ PullMaps tm_src, const __grid_constant__ CUtensorMap tm_out,
+               const __grid_constant__ CUtensorMap tm_copy) {
+    extern __shared__ __align__(128) unsigned char ntc_smem_raw[];
+    strided_body<B, true, CUtensorMap, true>(p, tm_src.m, &tm_out, reinterpret_cast<u64*>(ntc_smem_raw), blockIdx.x, &tm_copy);
 }
 
 // Z[i], i in [1, n):  l = floor(log2 i), j = i - 2^l:  Z[i] = spow[L - 1 - l] * w^(bitrev_l(j) << (L - 1 - l)) * (l == L-1 ? last_scale : 1)

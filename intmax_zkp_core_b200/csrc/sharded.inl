@@ -8,7 +8,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <condition_variable>
 #include <thread>
+
+#include "peer_kernels.cuh"
 
 namespace {
 
@@ -62,6 +65,39 @@ NcclApi& nccl_api() {
 
 }  // namespace
 
+// Peer-memory exchange (the default inside one NVLink domain): every rank owns an "exchange window" that holds the coefficients
+// of its own columns and that every other rank can read (peer access in one process, CUDA IPC between processes), plus the flag
+// words of peer_kernels.cuh.  The all-gather of the coefficients then happens inside the first pass of the coset transforms
+// (ntc::ct_pull_kernel): no NCCL call, no copy kernel, no staging of the shards between the exchange and the transform.
+struct PeerRank {
+    u64* win = nullptr;                 // this rank's window, [kp][n] of the largest shape created so far
+    size_t win_b = 0;
+    u32* flags = nullptr;               // peer::FLAG_WORDS words
+    std::vector<const u64*> peer_win;   // [world]: rank s's window as seen from this rank's device (own rank: win)
+    peer::PeerFlags peer_flags{};       // [world]: rank s's flags as seen from this rank's device
+    std::vector<void*> imported_win, imported_flags;   // CUDA IPC mappings to close
+};
+
+// rendezvous of the host threads that drive the ranks of a one-process communicator (CUDA events order work between the
+// devices of one process, but a wait must be issued after the record it refers to); abort() releases everyone when a rank fails
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 1, arrived = 0;
+    u64 gen = 0;
+    bool broken = false;
+    void reset(int n_) { std::lock_guard<std::mutex> lk(m); n = n_; arrived = 0; broken = false; }
+    bool wait() {
+        std::unique_lock<std::mutex> lk(m);
+        if (broken) return false;
+        const u64 g0 = gen;
+        if (++arrived == n) { arrived = 0; gen++; cv.notify_all(); return true; }
+        cv.wait(lk, [&] { return gen != g0 || broken; });
+        return !broken;
+    }
+    void abort() { std::lock_guard<std::mutex> lk(m); broken = true; cv.notify_all(); }
+};
+
 struct b200zkp_comm {
     int world = 0;
     std::vector<int> rank;             // global rank of local rank i
@@ -70,9 +106,21 @@ struct b200zkp_comm {
     std::vector<cudaStream_t> xstream; // exchange stream per local rank (NCCL point-to-point groups)
     std::vector<cudaEvent_t> ev;       // per local rank: [2 + world] events (coefficients ready, buffers free, one per group)
     uint32_t peers_per_group = 2;
+    bool peer_ok = false;              // peer memory reaches every rank from every rank (decided collectively at init)
+    bool peer_on = true;               // b200zkp_comm_set_peer_exchange / B200ZKP_PEER_EXCHANGE=0: use the NCCL exchange instead
+    u32 epoch = 0;                     // commits issued on this communicator (the same number on every rank)
+    u64 chunk_bytes = (u64)16 << 20;   // host inputs: bytes per upload chunk of the pipeline (B200ZKP_PEER_CHUNK_BYTES, for tests)
+    std::vector<PeerRank> pr;          // per local rank
+    // one process driving every rank: the ordering between devices is CUDA events (no spinning kernels), issued in step
+    std::vector<cudaEvent_t> ready_ev; // [local rank * MAX_CHUNKS + chunk]
+    std::vector<cudaEvent_t> done_ev;  // [local rank]
+    bool done_valid = false;
+    HostBarrier hb;
+    bool one_process() const { return n_local() == world; }
     std::mutex mu;                     // serialises the collective entry points of this process
     std::string err;
     int n_local() const { return (int)rank.size(); }
+    bool peer_exchange() const { return peer_ok && peer_on; }
 };
 
 struct ShardRank {
@@ -114,6 +162,277 @@ extern "C" int b200zkp_comm_unique_id(uint8_t id[B200ZKP_COMM_ID_BYTES]) {
     return 0;
 }
 
+// runs f(local rank index) for every local rank: inline for one rank, one host thread per rank otherwise (each rank has its
+// own device, ctx, NCCL communicator and streams; NCCL point-to-point groups of different ranks must be issued concurrently)
+template <typename F>
+static int for_each_rank(b200zkp_comm* c, F f) {
+    const int n = c->n_local();
+    if (n == 1) {
+        int rc1 = f(0);
+        if (rc1) c->err = c->ctx[0]->err;
+        return rc1;
+    }
+    std::vector<int> rc(n, 0);
+    std::vector<std::thread> th;
+    th.reserve(n);
+    for (int i = 0; i < n; i++) th.emplace_back([&, i] { rc[i] = f(i); });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; i++)
+        if (rc[i]) { c->err = "rank " + std::to_string(c->rank[i]) + ": " + c->ctx[i]->err; return rc[i]; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- peer-memory exchange
+static constexpr u64 PEER_WAIT_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;
+
+// every rank of the communicator agrees on the AND of `ok` (one small NCCL all-reduce per local rank; also a barrier)
+static int comm_all_ok(b200zkp_comm* c, const std::vector<int>& ok_local, bool* all) {
+    std::vector<u32> res(c->n_local(), 0);
+    int rc = for_each_rank(c, [&](int i) -> int {
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        u32* d = nullptr;
+        TRY(dev_alloc(ctx, 256, (void**)&d));
+        u32 v = ok_local[i] ? 1u : 0u;
+        int r = 0;
+        if (cudaMemcpyAsync(d, &v, 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) r = B200ZKP_ERR_CUDA;
+        if (!r) {
+            ncclResult_t nr = nccl_api().AllReduce(d, d, 1, ncclUint32, ncclMin, c->nc[i], ctx->stream);
+            if (nr != ncclSuccess) r = nccl_fail(&ctx->err, "ncclAllReduce", nr);
+        }
+        if (!r && (cudaMemcpyAsync(&res[i], d, 4, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                   cudaStreamSynchronize(ctx->stream) != cudaSuccess)) r = B200ZKP_ERR_CUDA;
+        if (r == B200ZKP_ERR_CUDA) { ctx->err = "CUDA error in the communicator handshake"; (void)cudaGetLastError(); }
+        dev_release(ctx, d, 256);
+        return r;
+    });
+    if (rc) return rc;
+    *all = true;
+    for (u32 v : res) *all = *all && v == 1u;
+    return 0;
+}
+
+// own[i]: a whole cudaMalloc allocation of local rank i.  Fills views[i][s] = rank s's allocation as addressable from local
+// rank i's device: the pointer itself inside one process (peer access), a CUDA IPC mapping between processes (recorded in
+// imported[i]).  ok_local[i] is cleared when a mapping cannot be made; the caller decides collectively what to do then.
+static int comm_exchange_ptrs(b200zkp_comm* c, const std::vector<void*>& own, std::vector<std::vector<void*>>* views,
+                              std::vector<std::vector<void*>>* imported, std::vector<int>* ok_local) {
+    const int nl = c->n_local(), W = c->world;
+    views->assign(nl, std::vector<void*>(W, nullptr));
+    if (nl == W) {
+        for (int i = 0; i < nl; i++)
+            for (int sidx = 0; sidx < W; sidx++) (*views)[i][sidx] = own[sidx];     // local rank index == global rank (init_all)
+        return 0;
+    }
+    return for_each_rank(c, [&](int i) -> int {
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        const int me = c->rank[i];
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+        std::vector<cudaIpcMemHandle_t> h(W);
+        memset(h.data(), 0, sizeof(cudaIpcMemHandle_t) * W);
+        if (!own[i] || cudaIpcGetMemHandle(&h[me], own[i]) != cudaSuccess) { (void)cudaGetLastError(); (*ok_local)[i] = 0; }
+        unsigned char* d = nullptr;
+        TRY(dev_alloc(ctx, (size_t)W * 64, (void**)&d));
+        int r = 0;
+        if (cudaMemcpyAsync(d + (size_t)me * 64, &h[me], 64, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) r = B200ZKP_ERR_CUDA;
+        if (!r) {
+            ncclResult_t nr = nccl_api().AllGather(d + (size_t)me * 64, d, 64, ncclChar, c->nc[i], ctx->stream);
+            if (nr != ncclSuccess) r = nccl_fail(&ctx->err, "ncclAllGather", nr);
+        }
+        if (!r && (cudaMemcpyAsync(h.data(), d, (size_t)W * 64, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                   cudaStreamSynchronize(ctx->stream) != cudaSuccess)) r = B200ZKP_ERR_CUDA;
+        dev_release(ctx, d, (size_t)W * 64);
+        if (r) { if (r == B200ZKP_ERR_CUDA) { ctx->err = "CUDA error while exchanging IPC handles"; (void)cudaGetLastError(); } return r; }
+        for (int sidx = 0; sidx < W; sidx++) {
+            if (sidx == me) { (*views)[i][sidx] = own[i]; continue; }
+            void* ptr = nullptr;
+            if (!(*ok_local)[i] || cudaIpcOpenMemHandle(&ptr, h[sidx], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                (void)cudaGetLastError();
+                (*ok_local)[i] = 0;
+                continue;
+            }
+            (*views)[i][sidx] = ptr;
+            (*imported)[i].push_back(ptr);
+        }
+        return 0;
+    });
+}
+
+static void peer_close_imports(std::vector<void*>* v) {
+    for (void* q : *v) if (q) cudaIpcCloseMemHandle(q);
+    (void)cudaGetLastError();
+    v->clear();
+}
+
+// flags of every rank, mapped into every rank; decides collectively whether the peer-memory exchange can be used at all
+static int comm_peer_init(b200zkp_comm* c) {
+    const int nl = c->n_local(), W = c->world;
+    c->pr.assign(nl, PeerRank());
+    c->peer_ok = false;
+    const char* env = getenv("B200ZKP_PEER_EXCHANGE");
+    if (env && env[0] == '0') c->peer_on = false;
+    if (const char* cb = getenv("B200ZKP_PEER_CHUNK_BYTES")) { const u64 v = strtoull(cb, nullptr, 10); if (v >= 8) c->chunk_bytes = v; }
+    if (W < 2) return 0;
+    std::vector<int> ok(nl, 1);
+    std::vector<void*> own(nl, nullptr);
+    for (int i = 0; i < nl; i++) {
+        if (W > (int)peer::MAX_RANKS || (nl != W && nl != 1)) { ok[i] = 0; continue; }
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        if (nl == W) {
+            // one process: direct peer access between every pair of devices
+            for (int j = 0; j < nl && ok[i]; j++) {
+                if (j == i) continue;
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, ctx->device, c->ctx[j]->device) != cudaSuccess || !can) { ok[i] = 0; break; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(c->ctx[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok[i] = 0;
+                (void)cudaGetLastError();
+            }
+        }
+        if (ok[i]) {
+            // (a whole 2 MB block of its own: what CUDA IPC exports is the block, not the words)
+            if (cudaMalloc((void**)&c->pr[i].flags, (size_t)2 << 20) != cudaSuccess ||
+                cudaMemsetAsync(c->pr[i].flags, 0, (size_t)2 << 20, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess) { (void)cudaGetLastError(); ok[i] = 0; }
+            own[i] = c->pr[i].flags;
+        }
+    }
+    bool all = false;
+    TRY(comm_all_ok(c, ok, &all));
+    if (all) {
+        std::vector<std::vector<void*>> views, imported(nl);
+        TRY(comm_exchange_ptrs(c, own, &views, &imported, &ok));
+        for (int i = 0; i < nl; i++) {
+            for (int sidx = 0; sidx < W; sidx++) c->pr[i].peer_flags.p[sidx] = (u32*)views[i][sidx];
+            c->pr[i].imported_flags = imported[i];
+        }
+        TRY(comm_all_ok(c, ok, &all));
+    }
+    if (all && c->one_process()) {
+        for (int i = 0; i < nl && all; i++) {
+            cudaSetDevice(c->ctx[i]->device);
+            for (u32 e = 0; e <= peer::MAX_CHUNKS && all; e++) {
+                cudaEvent_t ev = nullptr;
+                if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); all = false; break; }
+                if (e < peer::MAX_CHUNKS) c->ready_ev.push_back(ev); else c->done_ev.push_back(ev);
+            }
+        }
+    }
+    c->peer_ok = all;
+    if (!all) {
+        for (int i = 0; i < nl; i++) {
+            cudaSetDevice(c->ctx[i]->device);
+            peer_close_imports(&c->pr[i].imported_flags);
+        }
+        // the owners free only after every importer has closed
+        std::vector<int> one(nl, 1);
+        bool dummy;
+        TRY(comm_all_ok(c, one, &dummy));
+        for (int i = 0; i < nl; i++) {
+            cudaSetDevice(c->ctx[i]->device);
+            if (c->pr[i].flags) cudaFree(c->pr[i].flags);
+            c->pr[i].flags = nullptr;
+        }
+        (void)cudaGetLastError();
+    }
+    return 0;
+}
+
+// the window of every rank holds at least `bytes` (collective; the same request on every rank).  Growing it is a full
+// rendezvous: readers finish, importers close, owners reallocate, the new handles travel.
+static int comm_ensure_window(b200zkp_comm* c, size_t bytes) {
+    if (!c->peer_ok || c->pr.empty() || bytes <= c->pr[0].win_b) return 0;
+    const int nl = c->n_local(), W = c->world;
+    bytes = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    std::vector<int> ok(nl, 1);
+    // 1. nobody reads a window any more: every rank has seen `done` of the last commit from every peer
+    TRY(for_each_rank(c, [&](int i) -> int {
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        // (one process: every reader's stream is drained by this very loop before anything is freed)
+        if (!c->one_process()) {
+            peer::wait_kernel<<<1, 32, 0, ctx->stream>>>(c->pr[i].flags, peer::DONE0, 1, (u32)W, (u32)c->rank[i], c->epoch, PEER_WAIT_TIMEOUT_NS);
+            LAUNCH_CHECK(ctx);
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        peer_close_imports(&c->pr[i].imported_win);
+        return 0;
+    }));
+    bool all = false;
+    TRY(comm_all_ok(c, ok, &all));                 // barrier: every importer has closed
+    std::vector<void*> own(nl, nullptr);
+    for (int i = 0; i < nl; i++) {
+        b200zkp_ctx* ctx = c->ctx[i];
+        Guard g(ctx);
+        if (c->pr[i].win) cudaFree(c->pr[i].win);
+        c->pr[i].win = nullptr; c->pr[i].win_b = 0;
+        if (cudaMalloc((void**)&c->pr[i].win, bytes) != cudaSuccess) {
+            (void)cudaGetLastError();
+            pool_drop(ctx);
+            if (cudaMalloc((void**)&c->pr[i].win, bytes) != cudaSuccess) { (void)cudaGetLastError(); c->pr[i].win = nullptr; ok[i] = 0; }
+        }
+        own[i] = c->pr[i].win;
+    }
+    std::vector<std::vector<void*>> views, imported(nl);
+    TRY(comm_exchange_ptrs(c, own, &views, &imported, &ok));
+    for (int i = 0; i < nl; i++) {
+        c->pr[i].peer_win.assign(W, nullptr);
+        for (int sidx = 0; sidx < W; sidx++) c->pr[i].peer_win[sidx] = (const u64*)views[i][sidx];
+        c->pr[i].imported_win = imported[i];
+        c->pr[i].win_b = bytes;
+    }
+    TRY(comm_all_ok(c, ok, &all));
+    if (!all) {
+        // (out of memory on some rank, or a mapping failed) fall back to the NCCL exchange for good
+        for (int i = 0; i < nl; i++) { cudaSetDevice(c->ctx[i]->device); peer_close_imports(&c->pr[i].imported_win); }
+        std::vector<int> one(nl, 1);
+        bool dummy;
+        TRY(comm_all_ok(c, one, &dummy));
+        for (int i = 0; i < nl; i++) {
+            cudaSetDevice(c->ctx[i]->device);
+            if (c->pr[i].win) cudaFree(c->pr[i].win);
+            c->pr[i].win = nullptr; c->pr[i].win_b = 0;
+        }
+        (void)cudaGetLastError();
+        c->peer_ok = false;
+    }
+    return 0;
+}
+
+// before the communicator goes away: readers finish, importers close (barrier), owners free
+static void comm_peer_shutdown(b200zkp_comm* c) {
+    if (c->pr.empty()) return;
+    const int nl = c->n_local();
+    if (c->peer_ok) {
+        (void)for_each_rank(c, [&](int i) -> int {
+            b200zkp_ctx* ctx = c->ctx[i];
+            Guard g(ctx);
+            if (!c->one_process())
+                peer::wait_kernel<<<1, 32, 0, ctx->stream>>>(c->pr[i].flags, peer::DONE0, 1, (u32)c->world, (u32)c->rank[i], c->epoch, PEER_WAIT_TIMEOUT_NS);
+            cudaStreamSynchronize(ctx->stream);
+            peer_close_imports(&c->pr[i].imported_win);
+            peer_close_imports(&c->pr[i].imported_flags);
+            return 0;
+        });
+        std::vector<int> one(nl, 1);
+        bool dummy;
+        (void)comm_all_ok(c, one, &dummy);
+    }
+    for (int i = 0; i < nl; i++) {
+        cudaSetDevice(c->ctx[i]->device);
+        if (c->pr[i].win) cudaFree(c->pr[i].win);
+        if (c->pr[i].flags) cudaFree(c->pr[i].flags);
+    }
+    for (size_t e = 0; e < c->ready_ev.size(); e++) { cudaSetDevice(c->ctx[e / peer::MAX_CHUNKS]->device); cudaEventDestroy(c->ready_ev[e]); }
+    for (size_t e = 0; e < c->done_ev.size(); e++) { cudaSetDevice(c->ctx[e]->device); cudaEventDestroy(c->done_ev[e]); }
+    c->ready_ev.clear(); c->done_ev.clear();
+    (void)cudaGetLastError();
+    c->pr.clear();
+    c->peer_ok = false;
+}
+
 static int comm_finish_init(b200zkp_comm* c) {
     // side stream + events of every local rank
     for (int i = 0; i < c->n_local(); i++) {
@@ -142,19 +461,26 @@ extern "C" int b200zkp_comm_init_rank(b200zkp_ctx* ctx, const uint8_t id[B200ZKP
     if (!out) return B200ZKP_ERR_BAD_ARG;
     *out = nullptr;
     if (!ctx) return B200ZKP_ERR_BAD_ARG;
-    Guard g(ctx);
-    if (!id || !valid_world(world) || rank < 0 || rank >= world) BAD(ctx, "bad communicator shape (world must be a power of two)");
-    if (int rc = nccl_ready(&ctx->err)) return rc;
-    b200zkp_comm* c = new (std::nothrow) b200zkp_comm();
-    if (!c) return B200ZKP_ERR_OOM;
-    c->world = world;
-    ncclUniqueId u;
-    memcpy(&u, id, sizeof(u));
-    ncclComm_t nc = nullptr;
-    ncclResult_t r = nccl_api().CommInitRank(&nc, world, u, rank);
-    if (r != ncclSuccess) { int rc = nccl_fail(&ctx->err, "ncclCommInitRank", r); delete c; return rc; }
-    c->rank.push_back(rank); c->ctx.push_back(ctx); c->nc.push_back(nc);
-    if (int rc = comm_finish_init(c)) { ctx->err = c->err; b200zkp_comm_destroy(c); return rc; }
+    b200zkp_comm* c = nullptr;
+    int rc = 0;
+    {
+        Guard g(ctx);           // (released before the peer handshake, whose steps lock the ctx themselves)
+        if (!id || !valid_world(world) || rank < 0 || rank >= world) BAD(ctx, "bad communicator shape (world must be a power of two)");
+        if ((rc = nccl_ready(&ctx->err))) return rc;
+        c = new (std::nothrow) b200zkp_comm();
+        if (!c) return B200ZKP_ERR_OOM;
+        c->world = world;
+        ncclUniqueId u;
+        memcpy(&u, id, sizeof(u));
+        ncclComm_t nc = nullptr;
+        ncclResult_t r = nccl_api().CommInitRank(&nc, world, u, rank);
+        if (r != ncclSuccess) { rc = nccl_fail(&ctx->err, "ncclCommInitRank", r); delete c; return rc; }
+        c->rank.push_back(rank); c->ctx.push_back(ctx); c->nc.push_back(nc);
+        rc = comm_finish_init(c);
+        if (rc) ctx->err = c->err;
+    }
+    if (!rc) rc = comm_peer_init(c);
+    if (rc) { b200zkp_comm_destroy(c); return rc; }
     *out = c;
     return 0;
 }
@@ -178,12 +504,14 @@ extern "C" int b200zkp_comm_init_all(b200zkp_ctx* const* ctxs, int n, b200zkp_co
     ncclResult_t r = nccl_api().CommInitAll(c->nc.data(), n, devs.data());
     if (r != ncclSuccess) { int rc = nccl_fail(&ctxs[0]->err, "ncclCommInitAll", r); c->nc.clear(); delete c; return rc; }
     if (int rc = comm_finish_init(c)) { ctxs[0]->err = c->err; b200zkp_comm_destroy(c); return rc; }
+    if (int rc = comm_peer_init(c)) { ctxs[0]->err = c->err; b200zkp_comm_destroy(c); return rc; }
     *out = c;
     return 0;
 }
 
 extern "C" void b200zkp_comm_destroy(b200zkp_comm* c) {
     if (!c) return;
+    comm_peer_shutdown(c);
     for (int i = 0; i < c->n_local(); i++) {
         cudaSetDevice(c->ctx[i]->device);
         if (i < (int)c->xstream.size()) { cudaStreamSynchronize(c->xstream[i]); }
@@ -214,25 +542,14 @@ extern "C" int b200zkp_comm_set_exchange_group(b200zkp_comm* c, uint32_t peers_p
     return 0;
 }
 
-// runs f(local rank index) for every local rank: inline for one rank, one host thread per rank otherwise (each rank has its
-// own device, ctx, NCCL communicator and streams; NCCL point-to-point groups of different ranks must be issued concurrently)
-template <typename F>
-static int for_each_rank(b200zkp_comm* c, F f) {
-    const int n = c->n_local();
-    if (n == 1) {
-        int rc1 = f(0);
-        if (rc1) c->err = c->ctx[0]->err;
-        return rc1;
-    }
-    std::vector<int> rc(n, 0);
-    std::vector<std::thread> th;
-    th.reserve(n);
-    for (int i = 0; i < n; i++) th.emplace_back([&, i] { rc[i] = f(i); });
-    for (auto& t : th) t.join();
-    for (int i = 0; i < n; i++)
-        if (rc[i]) { c->err = "rank " + std::to_string(c->rank[i]) + ": " + c->ctx[i]->err; return rc[i]; }
+extern "C" int b200zkp_comm_set_peer_exchange(b200zkp_comm* c, int enabled) {
+    if (!c) return B200ZKP_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->peer_on = enabled != 0;
     return 0;
 }
+
+extern "C" int b200zkp_comm_peer_exchange(const b200zkp_comm* c) { return (c && c->peer_exchange()) ? 1 : 0; }
 
 static void sharded_release(b200zkp_sharded* sh) {
     for (size_t i = 0; i < sh->r.size(); i++) {
@@ -288,6 +605,7 @@ extern "C" int b200zkp_sharded_create(b200zkp_comm* c, uint32_t n_log, uint32_t 
         CUDA_TRY(ctx, cudaMemsetAsync(s.coeffs_all, 0, s.coeffs_b, ctx->stream));
         return 0;
     });
+    if (!rc && c->peer_exchange()) rc = comm_ensure_window(c, (size_t)sh->kp * n * 8);
     if (rc) { sharded_release(sh); return rc; }
     *out = sh;
     return 0;
@@ -311,8 +629,8 @@ extern "C" int b200zkp_sharded_layout(const b200zkp_sharded* sh, int local, uint
     return 0;
 }
 
-// everything one rank does for one commit; asynchronous (returns after enqueueing)
-static int sharded_commit_rank(b200zkp_sharded* sh, int i, const u64* input, int on_device, int is_coeffs) {
+// everything one rank does for one commit; asynchronous (returns after enqueueing).  NCCL form of the exchange.
+static int sharded_commit_rank_nccl(b200zkp_sharded* sh, int i, const u64* input, int on_device, int is_coeffs) {
     b200zkp_comm* c = sh->comm;
     b200zkp_ctx* ctx = c->ctx[i];
     NcclApi& nc = nccl_api();
@@ -421,17 +739,188 @@ static int sharded_commit_rank(b200zkp_sharded* sh, int i, const u64* input, int
     return 0;
 }
 
+// ---- ordering between the ranks of a peer exchange: flags in peer memory between processes (peer_kernels.cuh), CUDA events
+//      plus a rendezvous of the rank threads inside one process
+static int peer_wait_window_free(b200zkp_comm* c, int i, u32 epoch) {
+    b200zkp_ctx* ctx = c->ctx[i];
+    if (c->one_process()) {
+        if (c->done_valid)
+            for (int sidx = 0; sidx < c->n_local(); sidx++)
+                if (sidx != i) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, c->done_ev[sidx], 0));
+        return 0;
+    }
+    peer::wait_kernel<<<1, 32, 0, ctx->stream>>>(c->pr[i].flags, peer::DONE0, 1, (u32)c->world, (u32)c->rank[i], epoch - 1, PEER_WAIT_TIMEOUT_NS);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+// chunk j of this rank's window is written (stream order); returns when the stream also waits for chunk j of every peer
+static int peer_publish_and_wait_chunk(b200zkp_comm* c, int i, u32 j, u32 epoch) {
+    b200zkp_ctx* ctx = c->ctx[i];
+    if (c->one_process()) {
+        CUDA_TRY(ctx, cudaEventRecord(c->ready_ev[(size_t)i * peer::MAX_CHUNKS + j], ctx->stream));
+        if (!c->hb.wait()) { ctx->err = "another rank of the communicator failed"; return B200ZKP_ERR_CUDA; }
+        for (int sidx = 0; sidx < c->n_local(); sidx++)
+            if (sidx != i) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, c->ready_ev[(size_t)sidx * peer::MAX_CHUNKS + j], 0));
+        return 0;
+    }
+    const u32 G = (u32)c->world, g = (u32)c->rank[i];
+    peer::signal_kernel<<<1, 32, 0, ctx->stream>>>(c->pr[i].peer_flags, G, g, peer::READY0 + g * peer::MAX_CHUNKS + j, epoch);
+    LAUNCH_CHECK(ctx);
+    peer::wait_kernel<<<1, 32, 0, ctx->stream>>>(c->pr[i].flags, peer::READY0 + j, peer::MAX_CHUNKS, G, g, epoch, PEER_WAIT_TIMEOUT_NS);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+// this rank has read every window (stream order)
+static int peer_publish_done(b200zkp_comm* c, int i, u32 epoch) {
+    b200zkp_ctx* ctx = c->ctx[i];
+    if (c->one_process()) {
+        CUDA_TRY(ctx, cudaEventRecord(c->done_ev[i], ctx->stream));
+        return 0;
+    }
+    peer::signal_kernel<<<1, 32, 0, ctx->stream>>>(c->pr[i].peer_flags, (u32)c->world, (u32)c->rank[i], peer::DONE0 + (u32)c->rank[i], epoch);
+    LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Peer-memory form of the same commit (the default inside one NVLink domain).  The rank's columns are cut into the same
+// chunks on every rank; per chunk:  [upload ->] inverse transform into the rank's exchange window -> "ready" flag to every
+// peer -> wait for every peer's flag -> ONE launch sequence of coset transforms over that chunk's columns of ALL ranks, whose
+// first pass reads the coefficient tiles straight from the peers' windows over NVLink and also files them in the local
+// coefficient matrix (ntc::ct_pull_kernel).  With host inputs the upload of chunk j + 1 runs under the transforms of chunk j,
+// so only the leaf hashing waits for the last byte.
+static int sharded_commit_rank_peer(b200zkp_sharded* sh, int i, const u64* input, int on_device, int is_coeffs, u32 epoch) {
+    b200zkp_comm* c = sh->comm;
+    b200zkp_ctx* ctx = c->ctx[i];
+    NcclApi& nc = nccl_api();
+    Guard guard(ctx);
+    ShardRank& s = sh->r[i];
+    PeerRank& pr = c->pr[i];
+    const u32 G = (u32)c->world, g = (u32)c->rank[i];
+    const u64 n = (u64)1 << sh->n_log;
+    const u32 kp = sh->kp;
+    const u32 c0 = std::min(sh->k, g * kp), c1 = std::min(sh->k, (g + 1) * kp), kl = c1 - c0;
+    cudaStream_t main_s = ctx->stream;
+    if (kl && !input) BAD(ctx, "null input shard");
+    if (!pr.win || pr.win_b < (size_t)kp * n * 8 || pr.peer_win.size() != G) BAD(ctx, "internal: exchange window missing");
+    const bool fused = ctx->ntt_ct && ntc::covers(sh->n_log) && sh->bpr <= (u32)ntc::MAX_LOOP_BLOCKS;
+    // tables first: their builders synchronise the stream, and nothing of this commit may be waiting on a peer by then
+    if (ctx->ntt_ct && ntc::covers(sh->n_log)) {
+        b200zkp_ctx::ZTables z;
+        TRY(get_ztab_lde(ctx, sh->n_log, sh->rate_bits, &z));
+        if (!is_coeffs) TRY(get_ztab_inv(ctx, sh->n_log, &z));
+    }
+    // chunks of the rank-local column range [0, kp): the same cut on every rank (host inputs: >= 16 MB per upload)
+    u32 C = 1;
+    if (!on_device) {
+        const u32 cols_per = (u32)std::max<u64>(1, (c->chunk_bytes + n * 8 - 1) / (n * 8));
+        C = std::max(1u, std::min((u32)peer::MAX_CHUNKS, (kp + cols_per - 1) / cols_per));
+    }
+    const u32 per = (kp + C - 1) / C;
+    C = (kp + per - 1) / per;
+
+    std::vector<cudaEvent_t> up(C, nullptr);
+    if (!on_device && kl) {
+        if (s.stage_b < (size_t)kp * n * 8) {
+            dev_release(ctx, s.stage, s.stage_b);
+            s.stage = nullptr; s.stage_b = 0;
+            TRY(dev_alloc(ctx, (size_t)kp * n * 8, (void**)&s.stage));
+            s.stage_b = (size_t)kp * n * 8;
+        }
+        if (!ctx->stream2) {
+            int lo = 0, hi = 0;
+            CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+        }
+        cudaEvent_t e_free;
+        TRY(get_sync_event(ctx, 0, &e_free));
+        CUDA_TRY(ctx, cudaEventRecord(e_free, main_s));                  // the staging buffer may still feed the previous step
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, e_free, 0));
+        for (u32 j = 0; j < C; j++) {
+            const u32 a = std::min(kl, j * per), b = std::min(kl, (j + 1) * per);
+            TRY(get_sync_event(ctx, 1 + j, &up[j]));
+            if (b > a) CUDA_TRY(ctx, cudaMemcpyAsync(s.stage + (u64)a * n, input + (u64)a * n, (size_t)(b - a) * n * 8, cudaMemcpyHostToDevice, ctx->stream2));
+            CUDA_TRY(ctx, cudaEventRecord(up[j], ctx->stream2));
+        }
+    }
+    const u64* src = on_device ? input : s.stage;
+    u64* scratch = s.lde + (u64)c0 * sh->N_local;         // the rank's own columns of the LDE shard, not written before their chunk
+    // the window is free again once every peer has read the previous commit out of it
+    TRY(peer_wait_window_free(c, i, epoch));
+    for (u32 j = 0; j < C; j++) {
+        const u32 a = std::min(kp, j * per), b = std::min(kp, (j + 1) * per);
+        const u32 am = std::min(kl, a), bm = std::min(kl, b);
+        if (bm > am) {
+            if (!on_device) CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, up[j], 0));
+            if (is_coeffs) TRY(launch_canon_copy(ctx, src + (u64)am * n, pr.win + (u64)am * n, (u64)(bm - am) * n));
+            else TRY(dev_intt_locked(ctx, src + (u64)am * n, n, pr.win + (u64)am * n, n, scratch + (u64)am * sh->N_local, sh->n_log, bm - am));
+        }
+        TRY(peer_publish_and_wait_chunk(c, i, j, epoch));
+        if (fused) {
+            ntc::ColumnSet cs;
+            cs.run = b - a; cs.period = kp; cs.col0 = a; cs.limit = sh->k; cs.n_src = G; cs.pull = true;
+            for (u32 q = 0; q < G; q++) cs.src[q] = pr.peer_win[q];
+            cs.src_col0 = a; cs.src_col_stride = n; cs.copy_out = s.coeffs_all; cs.copy_col_stride = n;
+            int rc = dev_lde_cols_locked(ctx, cs, nullptr, n, s.lde, sh->N_local, sh->n_log, sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr);
+            if (rc == B200ZKP_ERR_UNSUPPORTED) BAD(ctx, "internal: pull transform refused a covered shape");
+            TRY(rc);
+        } else {
+            // small transforms (one pass) and wide blow-ups: plain peer copies into the coefficient matrix, transforms after the loop
+            for (u32 q = 0; q < G; q++) {
+                const u32 ca = std::min(sh->k, q * kp + a), cb = std::min(sh->k, q * kp + b);
+                if (cb > ca) CUDA_TRY(ctx, cudaMemcpyAsync(s.coeffs_all + (u64)ca * n, pr.peer_win[q] + (u64)a * n, (size_t)(cb - ca) * n * 8, cudaMemcpyDefault, main_s));
+            }
+        }
+    }
+    // every window has been read by this rank
+    TRY(peer_publish_done(c, i, epoch));
+    if (!fused)
+        TRY(dev_lde_locked(ctx, s.coeffs_all, n, s.lde, sh->N_local, sh->n_log, sh->k, sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr));
+
+    TRY(dev_merkle_locked(ctx, s.lde, /*row_stride=*/1, /*col_stride=*/sh->N_local, sh->k, sh->N_local, sh->cap_height_local,
+                          s.digests, s.cap_local));
+    NCCL_TRY(&ctx->err, nc.AllGather(s.cap_local, s.cap, s.cap_local_b / 8, ncclUint64, c->nc[i], main_s));
+    ctx->launches++;
+    return 0;
+}
+
+// a wait of this rank's commits gave up (a peer never raised its flag): the results are not valid
+static int peer_check_error(b200zkp_comm* c, int i) {
+    if (!c->peer_ok || !c->pr[i].flags) return 0;
+    b200zkp_ctx* ctx = c->ctx[i];
+    u32 e = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&e, c->pr[i].flags + peer::ERROR_WORD, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (e) { ctx->err = "peer exchange timed out (a rank of the communicator did not take part in the commit)"; return B200ZKP_ERR_NCCL; }
+    return 0;
+}
+
 static int sharded_commit_locked(b200zkp_sharded* sh, const u64* const* inputs, int on_device, int is_coeffs, u64* cap_out) {
     b200zkp_comm* c = sh->comm;
     if (!inputs) COMM_BAD(c, "null inputs");
-    TRY(for_each_rank(c, [&](int i) -> int { return sharded_commit_rank(sh, i, inputs[i], on_device, is_coeffs); }));
+    const bool use_peer = c->peer_exchange() && c->world > 1;
+    if (use_peer) {
+        TRY(comm_ensure_window(c, (size_t)sh->kp * ((size_t)8 << sh->n_log)));        // (a no-op unless the exchange was switched on after create)
+    }
+    if (use_peer && c->peer_exchange()) {
+        const u32 epoch = ++c->epoch;
+        c->hb.reset(c->n_local());
+        int rc = for_each_rank(c, [&](int i) -> int {
+            const int r = sharded_commit_rank_peer(sh, i, inputs[i], on_device, is_coeffs, epoch);
+            if (r) c->hb.abort();          // the other rank threads must not wait for this one
+            return r;
+        });
+        if (c->one_process()) c->done_valid = rc == 0;
+        TRY(rc);
+    } else {
+        TRY(for_each_rank(c, [&](int i) -> int { return sharded_commit_rank_nccl(sh, i, inputs[i], on_device, is_coeffs); }));
+    }
     if (cap_out) {
         TRY(for_each_rank(c, [&](int i) -> int {
             b200zkp_ctx* ctx = c->ctx[i];
             Guard g(ctx);
-            if (i == 0) return d2h(ctx, cap_out, sh->r[0].cap, sh->r[0].cap_b);
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            return 0;
+            if (i == 0) TRY(d2h(ctx, cap_out, sh->r[0].cap, sh->r[0].cap_b));
+            else CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            return use_peer ? peer_check_error(c, i) : 0;
         }));
     }
     return 0;
@@ -471,7 +960,7 @@ extern "C" int b200zkp_sharded_synchronize(b200zkp_sharded* sh) {
     return for_each_rank(c, [&](int i) -> int {
         Guard g(c->ctx[i]);
         CUDA_TRY(c->ctx[i], cudaStreamSynchronize(c->ctx[i]->stream));
-        return 0;
+        return peer_check_error(c, i);
     });
 }
 

@@ -154,6 +154,15 @@ class Comm:
     def set_exchange_group(self, peers_per_group: int):
         self.check(self._lib.b200zkp_comm_set_exchange_group(self._h, peers_per_group))
 
+    def set_peer_exchange(self, enabled: bool):
+        """peer-memory form of the coefficient exchange (default where available) or the NCCL form; collective"""
+        self.check(self._lib.b200zkp_comm_set_peer_exchange(self._h, int(bool(enabled))))
+
+    @property
+    def peer_exchange(self) -> bool:
+        """True when commits gather the coefficients through peer memory inside the transform (b200zkp_comm_peer_exchange)"""
+        return bool(self._lib.b200zkp_comm_peer_exchange(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.b200zkp_comm_destroy(self._h)

@@ -101,6 +101,8 @@ extern "C" {
     pub fn b200zkp_comm_last_error(comm: *const b200zkp_comm) -> *const c_char;
     pub fn b200zkp_comm_shape(comm: *const b200zkp_comm, shape: *mut i32) -> c_int;
     pub fn b200zkp_comm_set_exchange_group(comm: *mut b200zkp_comm, peers_per_group: u32) -> c_int;
+    pub fn b200zkp_comm_set_peer_exchange(comm: *mut b200zkp_comm, enabled: c_int) -> c_int;
+    pub fn b200zkp_comm_peer_exchange(comm: *const b200zkp_comm) -> c_int;
     pub fn b200zkp_sharded_create(comm: *mut b200zkp_comm, n_log: u32, k: u32, rate_bits: u32, cap_height: u32,
         out: *mut *mut b200zkp_sharded) -> c_int;
     pub fn b200zkp_sharded_free(sh: *mut b200zkp_sharded);

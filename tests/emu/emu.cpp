@@ -104,6 +104,7 @@ static void run_ct_pass(const ntc::PassParams& p, u32 B, int kind, u64 grid) {
     case BB:                                                                                                             \
         if (kind == ntc::KIND_STRIDED) ntc::strided_body<BB, false, int>(p, nullptr, nullptr, smem.data(), (u32)bid);     \
         else if (kind == ntc::KIND_STRIDED_LOOP) ntc::strided_body<BB, true, int>(p, nullptr, nullptr, smem.data(), (u32)bid); \
+        else if (kind == ntc::KIND_PULL_LOOP) ntc::strided_body<BB, true, int, true>(p, nullptr, nullptr, smem.data(), (u32)bid); \
         else if (kind == ntc::KIND_FINAL_INPLACE) ntc::final_body<BB, false>(p, smem.data(), (u32)bid);                  \
         else ntc::final_body<BB, true>(p, smem.data(), (u32)bid);                                                        \
         break;
@@ -139,6 +140,29 @@ int emu_ct_lde(const u64* coeffs, u64* lde, u32 n_log, u32 k, u32 rate_bits, u32
     }
     ntc::Plan plan;
     if (!ntc::make_plan(&plan, coeffs, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, k, b1 - b0, n, false, z.data(), zf.data(), 0, false)) return 0;
+    for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
+    return 1;
+}
+// partitioned LDE (sharded.inl): columns [ca, cb) of each of n_src sources (source q's coefficients: src[q], [kp][n]; its column i
+// is column q * kp + i of the commitment, dropped when >= k) gathered into coeffs_copy [k][n] and transformed for coset blocks
+// [b0, b1) into lde [k][(b1 - b0) * n]; pull = 0: the same column set read from coeffs_copy (already gathered)
+int emu_ct_lde_cols(const u64* const* src, u32 n_src, u32 kp, u32 k, u32 ca, u32 cb, int pull, u64* coeffs_copy, u64* lde, u32 n_log,
+                    u32 rate_bits, u32 b0, u32 b1) {
+    u64 n = (u64)1 << n_log;
+    if (!ntc::covers(n_log)) return 0;
+    std::vector<u64> z, zf;
+    for (u32 b = b0; b < b1; b++) {
+        std::vector<u64> zb = ntc::ztab_host(n_log, hostgl::coset_shift_of_block(n_log, rate_bits, b), 0, 0);
+        std::vector<u64> fb = ntc::zfinal_host(n_log, zb, false);
+        z.insert(z.end(), zb.begin(), zb.begin() + ntc::ztab_entries(n_log));
+        zf.insert(zf.end(), fb.begin(), fb.end());
+    }
+    ntc::ColumnSet cs;
+    cs.run = cb - ca; cs.period = kp; cs.col0 = ca; cs.limit = k; cs.n_src = n_src; cs.pull = pull != 0;
+    for (u32 q = 0; q < n_src; q++) cs.src[q] = src[q];
+    cs.src_col0 = ca; cs.src_col_stride = n; cs.copy_out = coeffs_copy; cs.copy_col_stride = n;
+    ntc::Plan plan;
+    if (!ntc::make_plan(&plan, coeffs_copy, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, 0, b1 - b0, n, false, z.data(), zf.data(), 0, false, &cs)) return 0;
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
     return 1;
 }

@@ -124,6 +124,40 @@ def test_ct_pass_bodies(emu, oracle, n_log):
             assert (lde[c] == oracle.coset_lde(v[c], r)[perm][b0 * n:b1 * n]).all(), (r, b0, b1)
 
 
+@pytest.mark.parametrize("n_log,k,G,chunks", [(11, 7, 2, 1), (12, 7, 4, 2), (13, 5, 2, 2), (11, 9, 8, 1)])
+def test_ct_pull_pass_bodies(emu, oracle, n_log, k, G, chunks):
+    """partitioned LDE (sharded.inl): the first pass gathers column chunks from per-rank coefficient windows (KIND_PULL_LOOP,
+    stepped on the host with the plain-load staging), later passes walk the same column set in place; rank g keeps coset
+    blocks [g * 2^r / G, (g + 1) * 2^r / G)"""
+    rng = np.random.default_rng(300 + n_log)
+    n, r = 1 << n_log, 3
+    kp = -(-k // G)
+    c = rng.integers(0, 2**64, size=(k, n), dtype=np.uint64)
+    win = [np.zeros((kp, n), np.uint64) for _ in range(G)]
+    for q in range(G):
+        lo, hi = min(k, q * kp), min(k, (q + 1) * kp)
+        win[q][:hi - lo] = c[lo:hi]
+    srcs = (u64p * G)(*[ptr(w) for w in win])
+    bpr = (1 << r) // G
+    for g in (0, G - 1):
+        b0, b1 = g * bpr, (g + 1) * bpr
+        copy = np.zeros((k, n), np.uint64)
+        lde = np.zeros((k, (b1 - b0) * n), np.uint64)
+        per = -(-kp // chunks)
+        for j in range(chunks):
+            ca, cb = min(kp, j * per), min(kp, (j + 1) * per)
+            if cb > ca:
+                assert emu.emu_ct_lde_cols(srcs, G, kp, k, ca, cb, 1, ptr(copy), ptr(lde), n_log, r, b0, b1) == 1
+        assert (copy == c).all()
+        want = np.zeros_like(lde)
+        assert emu.emu_ct_lde(ptr(c), ptr(want), n_log, k, r, b0, b1) == 1
+        assert (lde == want).all()
+        # the same column sets without the gather (coefficients already local)
+        lde2 = np.zeros_like(lde)
+        assert emu.emu_ct_lde_cols(srcs, G, kp, k, 0, kp, 0, ptr(copy), ptr(lde2), n_log, r, b0, b1) == 1
+        assert (lde2 == want).all()
+
+
 def test_ntt_hostile_columns(emu, oracle):
     v = hostile_columns(64)
     out = np.zeros_like(v)

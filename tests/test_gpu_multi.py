@@ -87,18 +87,38 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     cf = np.ascontiguousarray(ref["coeffs"][lay["col_begin"]:lay["col_end"]])
     sh.run(torch.from_numpy(cf.view(np.int64)).to(dev) if cf.size else None, is_coeffs=True)
     ok &= _check_rank(O, sh, 0, lay, ref, n_log, k, r, h)
+    # other data through the same buffers and exchange windows (a stale read of a peer's window would show here), in both
+    # forms of the exchange: peer memory inside the transform (CUDA IPC between these processes) and NCCL point-to-point
+    peer = comm.peer_exchange
+    v2 = O.synthetic_values(k, n, seed=4)
+    ref2 = O.commit(v2, r, h)
+    mine2 = np.ascontiguousarray(v2[lay["col_begin"]:lay["col_end"]])
+    dv2 = torch.from_numpy(mine2.view(np.int64)).to(dev) if mine2.size else None
+    hv2 = torch.from_numpy(mine2.view(np.int64)).pin_memory() if mine2.size else None
+    for form in ((True, False) if peer else (False,)):
+        comm.set_peer_exchange(form)
+        ok &= comm.peer_exchange == form
+        sh.run(dv2)
+        ok &= _check_rank(O, sh, 0, lay, ref2, n_log, k, r, h)
+        sh.run(dv)
+        ok &= _check_rank(O, sh, 0, lay, ref, n_log, k, r, h)
+        cap_host.zero_()
+        sh.run_from_host(hv2, cap_out=cap_host)
+        ok &= bool((cap_host.numpy().view(np.uint64) == ref2["cap"]).all())
+        ok &= _check_rank(O, sh, 0, lay, ref2, n_log, k, r, h)
     sh.close()
     comm.close()
-    q.put((rank, ok))
+    q.put((rank, ok, peer))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_log,k,r,h", [(10, 135, 3, 4), (13, 7, 3, 4), (6, 3, 1, 1)])
-def test_two_gpu_sharded_commitment(n_log, k, r, h):
+@pytest.mark.parametrize("n_log,k,r,h", [(10, 135, 3, 4), (13, 7, 3, 4), (6, 3, 1, 1), (14, 21, 3, 4), (12, 5, 1, 2)])
+def test_two_gpu_sharded_commitment(n_log, k, r, h, monkeypatch):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("B200ZKP_PEER_CHUNK_BYTES", str(3 * 8 << n_log))     # host inputs: chunks of 3 columns
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -108,11 +128,12 @@ def test_two_gpu_sharded_commitment(n_log, k, r, h):
     res = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, True), (1, True)]
+    assert sorted(r_[:2] for r_ in res) == [(0, True), (1, True)]
+    print("peer exchange between processes:", [r_[2] for r_ in res])
 
 
-@pytest.mark.parametrize("n_log,k,r,h", [(10, 135, 3, 4), (12, 7, 2, 3), (4, 3, 1, 1)])
-def test_one_process_drives_all_gpus(oracle, n_log, k, r, h):
+@pytest.mark.parametrize("n_log,k,r,h", [(10, 135, 3, 4), (12, 7, 2, 3), (4, 3, 1, 1), (13, 19, 3, 4)])
+def test_one_process_drives_all_gpus(oracle, n_log, k, r, h, monkeypatch):
     """b200zkp_comm_init_all: the deployment a single-process (rayon) prove() needs"""
     import torch
     import intmax_zkp_core_b200 as z
@@ -123,6 +144,7 @@ def test_one_process_drives_all_gpus(oracle, n_log, k, r, h):
         G *= 2
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("B200ZKP_PEER_CHUNK_BYTES", str(2 * 8 << n_log))     # host inputs: chunks of 2 columns
     ctxs = [z.Context(g) for g in range(G)]
     comm = D.Comm.init_all(ctxs)
     assert (comm.world, comm.n_local, comm.rank0) == (G, G, 0)
@@ -134,13 +156,23 @@ def test_one_process_drives_all_gpus(oracle, n_log, k, r, h):
     host = [torch.from_numpy(np.ascontiguousarray(v[l["col_begin"]:l["col_end"]]).view(np.int64)).pin_memory()
             if l["col_end"] > l["col_begin"] else None for l in lays]
     cap_host = torch.zeros((1 << h, 4), dtype=torch.int64).pin_memory()
-    for groups in (2, 0, 1):
-        comm.set_exchange_group(groups)
-        cap_host.zero_()
-        sh.run_from_host(host, cap_out=cap_host)
-        assert (cap_host.numpy().view(np.uint64) == ref["cap"]).all()
-        for i, lay in enumerate(lays):
-            assert _check_rank(O, sh, i, lay, ref, n_log, k, r, h), (groups, i)
+    assert comm.peer_exchange, "peer access between the GPUs of one box"
+    v2 = O.synthetic_values(k, n, seed=6)
+    ref2 = O.commit(v2, r, h)
+    host2 = [torch.from_numpy(np.ascontiguousarray(v2[l["col_begin"]:l["col_end"]]).view(np.int64)).pin_memory()
+             if l["col_end"] > l["col_begin"] else None for l in lays]
+    for groups in (None, 2, 0, 1):          # None: peer-memory exchange; else the NCCL exchange with that group size
+        comm.set_peer_exchange(groups is None)
+        assert comm.peer_exchange == (groups is None)
+        if groups is not None:
+            comm.set_exchange_group(groups)
+        for hh, rr in ((host, ref), (host2, ref2), (host, ref)):
+            cap_host.zero_()
+            sh.run_from_host(hh, cap_out=cap_host)
+            assert (cap_host.numpy().view(np.uint64) == rr["cap"]).all()
+            for i, lay in enumerate(lays):
+                assert _check_rank(O, sh, i, lay, rr, n_log, k, r, h), (groups, i)
+    comm.set_peer_exchange(True)
     assert _check_rows(O, sh, ref, n_log, r, h)
     dv = [h_.to(torch.device("cuda", i)) if h_ is not None else None for i, h_ in enumerate(host)]
     sh.run(dv)

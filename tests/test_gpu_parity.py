@@ -392,6 +392,24 @@ def test_full_size_properties(z, ctx, oracle):
     tctx.close()
 
 
+def test_benchmark_shape_against_the_cpu_port(z, ctx, oracle):
+    """All 16 cap entries, every digest, every coefficient and every LDE word of a 2^18 x 135 commitment (the benchmarked column
+    count, 1/4 of its rows; 3 passes of 6 bits in the second-generation transforms) against the multithreaded CPU port
+    (oracle/cpu_baseline.c: plonky2's own algorithm — radix-2 fft_classic, transpose + reverse_index_bits, recursive
+    fill_subtree — written independently of the kernels).  bench.py runs the same comparison on the full 2^20 x 135 input
+    (`parity_check`)."""
+    import os
+    n_log, k, r, h = 18, 135, 3, 4
+    v = oracle.synthetic_values(k, 1 << n_log)
+    oracle.baseline_set_threads(len(os.sched_getaffinity(0)))
+    ref, _ = oracle.baseline_commit(v, r, h)
+    b = z.PolynomialBatch.from_values(v, r, False, h, ctx=ctx)
+    assert (b.merkle_tree.cap.elements == ref["cap"]).all()
+    assert (b.polynomials == ref["coeffs"]).all()
+    assert (b.merkle_tree.digests == ref["digests"]).all()
+    assert (b.merkle_tree.leaves == ref["leaves"]).all()
+
+
 # ------------------------------------------------------------------------------------------------ openings (N3)
 @pytest.mark.parametrize("n_log,k", [(0, 3), (3, 5), (10, 135), (13, 20), (17, 7)])
 def test_eval_ext2_matches_oracle(z, ctx, oracle, n_log, k):
