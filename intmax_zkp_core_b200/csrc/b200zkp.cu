@@ -58,6 +58,7 @@ struct b200zkp_ctx {
     bool ntt_ct = true;                                 // B200ZKP_NTT_CT=0: every transform through ntt_kernels.cuh (A/B testing)
     bool ntt_tma = true;                                // B200ZKP_NTT_TMA=0: the new passes stage their tiles with plain loads
     u32 ct_smem_set = 0;                                // kernels whose dynamic shared memory limit has been raised on this device
+    u32 sm_count = 0;                                   // (queried on first use)
     // mailbox: 64 KB of mapped pinned host memory the small host-buffer calls (single hashes, the Fiat-Shamir transcript)
     // read and write directly from the kernel: no cudaMemcpy on those paths, one launch + one stream synchronise per call
     void* mailbox = nullptr;
@@ -345,14 +346,14 @@ static bool encode_tile_map(CUtensorMap* map, const u64* base, u32 B, u32 S, u32
 
 template <int B>
 static int launch_ct_b(b200zkp_ctx* ctx, int kind, const ntc::PassParams& p, u64 grid, const CUtensorMap& tm_in, const CUtensorMap& tm_out,
-                       const ntc::PullMaps* tm_src, const CUtensorMap* tm_copy) {
+                       const ntc::PullMaps* tm_src, const CUtensorMap* tm_copy, u32 pull_ctas_per_sm) {
     const void* fn = nullptr;
     u32 smem = 0;
     switch (kind) {
         case ntc::KIND_STRIDED: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_STRIDED>; smem = ntc::StridedSmem<B, false>::bytes; break;
         case ntc::KIND_STRIDED_LOOP: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_STRIDED_LOOP>; smem = ntc::StridedSmem<B, true>::bytes; break;
         case ntc::KIND_FINAL_INPLACE: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_FINAL_INPLACE>; smem = ntc::FinalSmem<B>::bytes; break;
-        case ntc::KIND_PULL_LOOP: fn = (const void*)ntc::ct_pull_kernel<B>; smem = ntc::StridedSmem<B, true>::bytes; break;
+        case ntc::KIND_PULL_LOOP: fn = (const void*)ntc::ct_pull_kernel<B>; smem = ntc::PullSmem<B>::bytes; break;
         default: fn = (const void*)ntc::ct_pass_kernel<B, ntc::KIND_FINAL_NATURAL>; smem = ntc::FinalSmem<B>::bytes; break;
     }
     const u32 bit = 1u << ((B - ntc::MIN_BITS) * 5 + kind);
@@ -360,15 +361,36 @@ static int launch_ct_b(b200zkp_ctx* ctx, int kind, const ntc::PassParams& p, u64
         CUDA_TRY(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->ct_smem_set |= bit;
     }
-    void* args[4] = {(void*)&p, (void*)&tm_in, (void*)&tm_out, nullptr};
-    if (kind == ntc::KIND_PULL_LOOP) { args[1] = (void*)tm_src; args[2] = (void*)&tm_out; args[3] = (void*)tm_copy; }
+    void* args[5] = {(void*)&p, (void*)&tm_in, (void*)&tm_out, nullptr, nullptr};
+    u32 total = (u32)grid;
+    if (kind == ntc::KIND_PULL_LOOP) {
+        // persistent: a few CTAs per SM walk all `total` tiles
+        args[1] = (void*)tm_src; args[2] = (void*)&tm_out; args[3] = (void*)tm_copy; args[4] = (void*)&total;
+        if (!ctx->sm_count) {
+            int sms = 0;
+            CUDA_TRY(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+            ctx->sm_count = (u32)std::max(1, sms);
+        }
+        grid = std::min<u64>(grid, (u64)std::max(1u, pull_ctas_per_sm) * ctx->sm_count);
+    }
     CUDA_TRY(ctx, cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(ntc::THREADS), args, smem, ctx->stream));
     ctx->launches++;
     return 0;
 }
 
-static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan) {
+// later_stream (optional): the passes after the first run there, behind an event recorded after the first pass on the ctx
+// stream (a partitioned LDE: the NVLink-bound gather pass of the next column group runs beside them); pull_ctas_per_sm:
+// width of the persistent gather launch
+static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan, cudaStream_t later_stream = nullptr, cudaEvent_t first_done = nullptr,
+                       u32 pull_ctas_per_sm = 4) {
+    cudaStream_t const first_stream = ctx->stream;
+    struct Restore { b200zkp_ctx* c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{ctx, first_stream};
     for (u32 pi = 0; pi < plan.n_passes; pi++) {
+        if (pi == 1 && later_stream && later_stream != first_stream) {
+            CUDA_TRY(ctx, cudaEventRecord(first_done, first_stream));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(later_stream, first_done, 0));
+            ctx->stream = later_stream;
+        }
         ntc::PassParams& p = plan.pass[pi];
         const u32 B = plan.bits[pi];
         const int kind = plan.kind[pi];
@@ -394,10 +416,10 @@ static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan) {
             if (!ok) p.use_tma = 0;
         }
         switch (B) {
-            case 5: TRY(launch_ct_b<5>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
-            case 6: TRY(launch_ct_b<6>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
-            case 7: TRY(launch_ct_b<7>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
-            case 8: TRY(launch_ct_b<8>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy)); break;
+            case 5: TRY(launch_ct_b<5>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy, pull_ctas_per_sm)); break;
+            case 6: TRY(launch_ct_b<6>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy, pull_ctas_per_sm)); break;
+            case 7: TRY(launch_ct_b<7>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy, pull_ctas_per_sm)); break;
+            case 8: TRY(launch_ct_b<8>(ctx, kind, p, plan.grid[pi], tm_in, tm_out, &tm_src, &tm_copy, pull_ctas_per_sm)); break;
             default: BAD(ctx, "internal: bad pass width");
         }
     }
@@ -680,7 +702,8 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
 // with cols.pull the first pass gathers the coefficients from the sources' exchange windows (peer memory) on the way.
 // Returns B200ZKP_ERR_UNSUPPORTED (nothing launched) when the block-twiddle passes do not cover the shape.
 static int dev_lde_cols_locked(b200zkp_ctx* ctx, const ntc::ColumnSet& cols, const u64* coeffs, u64 coeff_stride, u64* lde,
-                               u64 lde_stride, u32 n_log, u32 rate_bits, u32 b0, u32 b1) {
+                               u64 lde_stride, u32 n_log, u32 rate_bits, u32 b0, u32 b1, cudaStream_t later_stream = nullptr,
+                               cudaEvent_t first_done = nullptr, u32 pull_ctas_per_sm = 4) {
     if (rate_bits > 8 || n_log + rate_bits > 32) BAD(ctx, "rate_bits / n_log out of range");
     if (b0 >= b1 || b1 > (1u << rate_bits)) BAD(ctx, "bad coset block range");
     const u64 n = (u64)1 << n_log;
@@ -691,8 +714,9 @@ static int dev_lde_cols_locked(b200zkp_ctx* ctx, const ntc::ColumnSet& cols, con
     if (!ntc::make_plan(&plan, coeffs, coeff_stride, lde, lde_stride, nullptr, n_log, 0, b1 - b0, n, /*natural_out=*/false,
                         z.strided + (u64)b0 * ntc::ztab_entries(n_log), z.final_ + (u64)b0 * ntc::zfinal_words(n_log), 0, ctx->ntt_tma, &cols))
         return B200ZKP_ERR_UNSUPPORTED;
+    if (later_stream) return run_ct_plan(ctx, plan, later_stream, first_done, pull_ctas_per_sm);   // (the caller times the whole pipeline)
     StageTimer tm(ctx, B200ZKP_STAGE_LDE);
-    return run_ct_plan(ctx, plan);
+    return run_ct_plan(ctx, plan, nullptr, nullptr, pull_ctas_per_sm);
 }
 
 extern "C" int b200zkp_dev_lde(b200zkp_ctx* ctx, const uint64_t* coeffs, uint64_t coeff_stride, uint64_t* lde,

@@ -3,6 +3,7 @@
 // CUDA calls, no kernels; the transforms themselves only exist as CUDA kernels (ntt_kernels.cuh).
 // Replaces plonky2_field `fft_root_table` (field/src/fft.rs, plonky2 @ f99ed9c).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <vector>
 
@@ -192,6 +193,11 @@ static inline u32 last_pass_bits(u32 n_log) {
     ntt::split_passes(n_log, bits, &P);
     return bits[P - 1];
 }
+static inline u32 first_pass_bits(u32 n_log) {
+    u32 bits[ntt::MAX_PASSES], P;
+    ntt::split_passes(n_log, bits, &P);
+    return bits[0];
+}
 static inline u64 ztab_entries(u32 n_log) { return (u64)1 << (n_log - last_pass_bits(n_log)); }
 static inline u64 zfinal_words(u32 n_log) {
     const u32 B = last_pass_bits(n_log);
@@ -235,7 +241,17 @@ static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
     if (cols) {
         if (natural_out || cols->run == 0 || cols->n_src == 0 || cols->n_src > (u32)MAX_SRC) return false;
         if (cols->pull && n_blk > (u32)MAX_LOOP_BLOCKS) return false;
-        ncols = cols->run * cols->n_src;
+        // grid columns = the columns that exist: every source before the first short one is full and every source after it is
+        // empty (period >= run, sources in rank order), so they are a prefix of the (source, column) enumeration
+        ncols = 0;
+        bool short_seen = false;
+        for (u32 q = 0; q < cols->n_src; q++) {
+            const u64 first = (u64)cols->col0 + (u64)q * cols->period;
+            const u32 cnt = first >= cols->limit ? 0u : (u32)std::min<u64>(cols->run, cols->limit - first);
+            if (short_seen && cnt) return false;
+            if (cnt < cols->run) short_seen = true;
+            ncols += cnt;
+        }
     }
     if (!covers(n_log) || ncols == 0 || n_blk == 0) return false;
     if (natural_out && (!scratch || n_blk != 1)) return false;

@@ -457,14 +457,90 @@ ct_pass_kernel(const PassParams p, const __grid_constant__ CUtensorMap tm_in, co
 
 // all-gather + first pass of a partitioned LDE (sharded.inl): tile by tile, the coefficients of every source rank come over
 // NVLink from that rank's exchange window into shared memory, from where they are both stored to the local coefficient
-// matrix and transformed for this rank's coset blocks
+// matrix and transformed for this rank's coset blocks.
+// Persistent: the launch has a few CTAs per SM (the host picks how many) that walk the tiles with a stride of the grid, and
+// the load of a CTA's next tile is in flight while it transforms the current one (two staging slots, one mbarrier each).
+// The pass is bound by NVLink, not by the SMs, so it is launched narrow on purpose: the in-place passes of the column
+// group gathered before it run beside it on a second stream and fill the rest of every SM.
 struct PullMaps { CUtensorMap m[MAX_SRC]; };
+template <int B>
+struct PullSmem {
+    static constexpr u32 NPTS = 1u << B;
+    static constexpr u32 sw_words = (u32)MAX_LOOP_BLOCKS * NPTS;
+    static constexpr u32 bytes = 4 * TILE * 8 + sw_words * 8 + 32;     // [stage 0][stage 1][work 0][work 1][sw][2 mbarriers]
+};
+
+template <int B>
+__device__ __forceinline__ void pull_decode(const PassParams& p, u32 bid, u32& col, u32& in_col, u32& q, u32& a, u32& c0) {
+    constexpr u32 T_log = 11 - B;
+    const u32 vcol = bid % p.ncols, tile_i = bid / p.ncols;
+    u32 i;
+    col = map_column(p, vcol, q, i);
+    in_col = p.src_col0 + i;
+    const u32 tiles_per_a_log = p.C_log - T_log;
+    a = tile_i >> tiles_per_a_log;
+    c0 = (tile_i & ((1u << tiles_per_a_log) - 1)) << T_log;
+}
+
 template <int B>
 __global__ void __launch_bounds__(THREADS, 4)
 ct_pull_kernel(const PassParams p, const __grid_constant__ PullMaps tm_src, const __grid_constant__ CUtensorMap tm_out,
-               const __grid_constant__ CUtensorMap tm_copy) {
+               const __grid_constant__ CUtensorMap tm_copy, const u32 total) {
     extern __shared__ __align__(128) unsigned char ntc_smem_raw[];
-    strided_body<B, true, CUtensorMap, true>(p, tm_src.m, &tm_out, reinterpret_cast<u64*>(ntc_smem_raw), blockIdx.x, &tm_copy);
+    u64* const smem = reinterpret_cast<u64*>(ntc_smem_raw);
+    if (!p.use_tma) {
+        // plain-load staging (no tensor maps): the tile body of the coset loop, one tile after the other
+        for (u32 bid = blockIdx.x; bid < total; bid += gridDim.x) {
+            strided_body<B, true, CUtensorMap, true>(p, tm_src.m, &tm_out, smem, bid, &tm_copy);
+            __syncthreads();
+        }
+        return;
+    }
+    constexpr u32 NPTS = 1u << B;
+    constexpr u32 T_log = 11 - B, T = 1u << T_log;
+    u64* const stage0 = smem;
+    u64* const work0 = smem + 2 * TILE;
+    u64* const sw = smem + 4 * TILE;
+    u64* const bar = sw + PullSmem<B>::sw_words;
+    if (blockIdx.x >= total) return;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_barrier_init(); }
+    __syncthreads();
+    u32 col, in_col, q, a, c0;
+    if (threadIdx.x == 0) {
+        pull_decode<B>(p, blockIdx.x, col, in_col, q, a, c0);
+        mbar_expect_tx(bar, TILE * 8);
+        tma_load_tile(stage0, &tm_src.m[q], c0, a, 0, in_col, bar);
+    }
+    u32 it = 0;
+    for (u32 bid = blockIdx.x; bid < total; bid += gridDim.x, it++) {
+        const u32 slot = it & 1;
+        u64* const stage = stage0 + slot * TILE;
+        // the other slot is free (every read of the tile before this one was waited for at the end of the last iteration)
+        if (threadIdx.x == 0 && bid + gridDim.x < total) {
+            pull_decode<B>(p, bid + gridDim.x, col, in_col, q, a, c0);
+            mbar_expect_tx(bar + (slot ^ 1), TILE * 8);
+            tma_load_tile(stage0 + (slot ^ 1) * TILE, &tm_src.m[q], c0, a, 0, in_col, bar + (slot ^ 1));
+        }
+        pull_decode<B>(p, bid, col, in_col, q, a, c0);
+        const u64 prefix = ((u64)1 << p.S) + a;
+        for (u32 i = threadIdx.x; i < p.n_blk * NPTS; i += THREADS) {
+            const u32 b = i >> B, e = i & (NPTS - 1);
+            if (e) sw[i] = gl::ldg(p.ztab + (u64)b * p.ztab_blk_stride + z_index(prefix, e));
+        }
+        mbar_wait(bar + slot, (it >> 1) & 1);
+        if (threadIdx.x == 0) { tma_store_tile(&tm_copy, c0, a, 0, col, stage); tma_commit(); }
+        __syncthreads();
+        for (u32 lb = 0; lb < p.n_blk; lb++) {
+            u64* const tile = work0 + (lb & 1) * TILE;
+            if (lb >= 2) { if (threadIdx.x == 0) tma_wait_read<1>(); __syncthreads(); }
+            run_rounds<B, false>(stage, tile, sw + lb * NPTS, 0, T_log, T, 0);
+            fence_proxy_async();
+            __syncthreads();
+            if (threadIdx.x == 0) { tma_store_tile(&tm_out, c0, a, lb, col, tile); tma_commit(); }
+        }
+        if (threadIdx.x == 0) tma_wait_read<0>();          // stage, work tiles and sw are free for the next tile after this
+        __syncthreads();
+    }
 }
 
 // Z[i], i in [1, n):  l = floor(log2 i), j = i - 2^l:  Z[i] = spow[L - 1 - l] * w^(bitrev_l(j) << (L - 1 - l)) * (l == L-1 ? last_scale : 1)

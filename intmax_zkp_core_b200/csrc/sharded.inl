@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <condition_variable>
+#include <memory>
 #include <thread>
 
 #include "peer_kernels.cuh"
@@ -109,6 +110,7 @@ struct b200zkp_comm {
     bool peer_ok = false;              // peer memory reaches every rank from every rank (decided collectively at init)
     bool peer_on = true;               // b200zkp_comm_set_peer_exchange / B200ZKP_PEER_EXCHANGE=0: use the NCCL exchange instead
     u32 epoch = 0;                     // commits issued on this communicator (the same number on every rank)
+    u32 pull_groups = 4;               // device inputs: column groups of the gather / in-place pipeline (B200ZKP_PEER_GROUPS)
     u64 chunk_bytes = (u64)16 << 20;   // host inputs: bytes per upload chunk of the pipeline (B200ZKP_PEER_CHUNK_BYTES, for tests)
     std::vector<PeerRank> pr;          // per local rank
     // one process driving every rank: the ordering between devices is CUDA events (no spinning kernels), issued in step
@@ -272,6 +274,7 @@ static int comm_peer_init(b200zkp_comm* c) {
     c->peer_ok = false;
     const char* env = getenv("B200ZKP_PEER_EXCHANGE");
     if (env && env[0] == '0') c->peer_on = false;
+    if (const char* pg = getenv("B200ZKP_PEER_GROUPS")) { const u32 v = (u32)strtoul(pg, nullptr, 10); if (v >= 1 && v <= 16) c->pull_groups = v; }
     if (const char* cb = getenv("B200ZKP_PEER_CHUNK_BYTES")) { const u64 v = strtoull(cb, nullptr, 10); if (v >= 8) c->chunk_bytes = v; }
     if (W < 2) return 0;
     std::vector<int> ok(nl, 1);
@@ -802,7 +805,10 @@ static int sharded_commit_rank_peer(b200zkp_sharded* sh, int i, const u64* input
     cudaStream_t main_s = ctx->stream;
     if (kl && !input) BAD(ctx, "null input shard");
     if (!pr.win || pr.win_b < (size_t)kp * n * 8 || pr.peer_win.size() != G) BAD(ctx, "internal: exchange window missing");
-    const bool fused = ctx->ntt_ct && ntc::covers(sh->n_log) && sh->bpr <= (u32)ntc::MAX_LOOP_BLOCKS;
+    // the gather inside the first pass wants tile rows of 128 bytes and more (first passes of <= 7 bits) unless the upload of
+    // host inputs hides the transfer anyway
+    const bool fused = ctx->ntt_ct && ntc::covers(sh->n_log) && sh->bpr <= (u32)ntc::MAX_LOOP_BLOCKS &&
+                       (!on_device || ntc::first_pass_bits(sh->n_log) <= 7 || getenv("B200ZKP_PEER_FUSED_ALWAYS"));
     // tables first: their builders synchronise the stream, and nothing of this commit may be waiting on a peer by then
     if (ctx->ntt_ct && ntc::covers(sh->n_log)) {
         b200zkp_ctx::ZTables z;
@@ -844,6 +850,9 @@ static int sharded_commit_rank_peer(b200zkp_sharded* sh, int i, const u64* input
     }
     const u64* src = on_device ? input : s.stage;
     u64* scratch = s.lde + (u64)c0 * sh->N_local;         // the rank's own columns of the LDE shard, not written before their chunk
+    cudaStream_t side_s = c->xstream[i];
+    u32 n_side = 0, n_copy = 0;
+    std::unique_ptr<StageTimer> lde_timer;                // device inputs: gather + coset transforms as one span of the main stream
     // the window is free again once every peer has read the previous commit out of it
     TRY(peer_wait_window_free(c, i, epoch));
     for (u32 j = 0; j < C; j++) {
@@ -856,25 +865,57 @@ static int sharded_commit_rank_peer(b200zkp_sharded* sh, int i, const u64* input
         }
         TRY(peer_publish_and_wait_chunk(c, i, j, epoch));
         if (fused) {
-            ntc::ColumnSet cs;
-            cs.run = b - a; cs.period = kp; cs.col0 = a; cs.limit = sh->k; cs.n_src = G; cs.pull = true;
-            for (u32 q = 0; q < G; q++) cs.src[q] = pr.peer_win[q];
-            cs.src_col0 = a; cs.src_col_stride = n; cs.copy_out = s.coeffs_all; cs.copy_col_stride = n;
-            int rc = dev_lde_cols_locked(ctx, cs, nullptr, n, s.lde, sh->N_local, sh->n_log, sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr);
-            if (rc == B200ZKP_ERR_UNSUPPORTED) BAD(ctx, "internal: pull transform refused a covered shape");
-            TRY(rc);
+            // device inputs arrive as one chunk: cut it into column groups, so that the gather pass of group t + 1 (NVLink
+            // bound, launched two CTAs per SM wide) runs beside the in-place passes of group t on the side stream
+            const u32 n_grp = on_device ? std::min(c->pull_groups, std::max(1u, (b - a) / 2)) : 1u;
+            const u32 gw = (b - a + n_grp - 1) / n_grp;
+            for (u32 ga = a; ga < b; ga += gw) {
+                const u32 gb = std::min(b, ga + gw);
+                ntc::ColumnSet cs;
+                cs.run = gb - ga; cs.period = kp; cs.col0 = ga; cs.limit = sh->k; cs.n_src = G; cs.pull = true;
+                for (u32 q = 0; q < G; q++) cs.src[q] = pr.peer_win[q];
+                cs.src_col0 = ga; cs.src_col_stride = n; cs.copy_out = s.coeffs_all; cs.copy_col_stride = n;
+                cudaEvent_t e_first;
+                TRY(get_sync_event(ctx, 24 + (n_side++ & 31), &e_first));
+                if (!lde_timer && on_device) lde_timer.reset(new StageTimer(ctx, B200ZKP_STAGE_LDE));
+                int rc = dev_lde_cols_locked(ctx, cs, nullptr, n, s.lde, sh->N_local, sh->n_log, sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr,
+                                             side_s, e_first, /*pull_ctas_per_sm=*/2);
+                if (rc == B200ZKP_ERR_UNSUPPORTED) BAD(ctx, "internal: pull transform refused a covered shape");
+                TRY(rc);
+            }
         } else {
-            // small transforms (one pass) and wide blow-ups: plain peer copies into the coefficient matrix, transforms after the loop
-            for (u32 q = 0; q < G; q++) {
+            // shapes the gather pass does not serve well (one-pass transforms, wide blow-ups, and first passes of 8 bits, whose
+            // tiles are rows of 64 bytes — too short for NVLink — when nothing else hides the transfer): the copy engine pulls
+            // shard after shard from the peers' windows on the side stream, own shard first, and the coset transforms of a
+            // shard run on the main stream while the next one is in flight
+            cudaEvent_t e_ready;
+            TRY(get_sync_event(ctx, 22, &e_ready));
+            CUDA_TRY(ctx, cudaEventRecord(e_ready, main_s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(side_s, e_ready, 0));
+            for (u32 d = 0; d < G; d++) {
+                const u32 q = (g + d) % G;
                 const u32 ca = std::min(sh->k, q * kp + a), cb = std::min(sh->k, q * kp + b);
-                if (cb > ca) CUDA_TRY(ctx, cudaMemcpyAsync(s.coeffs_all + (u64)ca * n, pr.peer_win[q] + (u64)a * n, (size_t)(cb - ca) * n * 8, cudaMemcpyDefault, main_s));
+                if (cb == ca) continue;
+                cudaEvent_t e_here;
+                TRY(get_sync_event(ctx, 24 + (n_copy++ & 31), &e_here));
+                CUDA_TRY(ctx, cudaMemcpyAsync(s.coeffs_all + (u64)ca * n, pr.peer_win[q] + (u64)a * n, (size_t)(cb - ca) * n * 8, cudaMemcpyDefault, side_s));
+                CUDA_TRY(ctx, cudaEventRecord(e_here, side_s));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, e_here, 0));
+                TRY(dev_lde_locked(ctx, s.coeffs_all + (u64)ca * n, n, s.lde + (u64)ca * sh->N_local, sh->N_local, sh->n_log, cb - ca,
+                                   sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr));
             }
         }
     }
+    if (n_side) {
+        // the in-place passes on the side stream join the main stream before the leaves are hashed
+        cudaEvent_t e_join;
+        TRY(get_sync_event(ctx, 23, &e_join));
+        CUDA_TRY(ctx, cudaEventRecord(e_join, side_s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, e_join, 0));
+    }
+    lde_timer.reset();
     // every window has been read by this rank
     TRY(peer_publish_done(c, i, epoch));
-    if (!fused)
-        TRY(dev_lde_locked(ctx, s.coeffs_all, n, s.lde, sh->N_local, sh->n_log, sh->k, sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr));
 
     TRY(dev_merkle_locked(ctx, s.lde, /*row_stride=*/1, /*col_stride=*/sh->N_local, sh->k, sh->N_local, sh->cap_height_local,
                           s.digests, s.cap_local));
