@@ -276,9 +276,20 @@ int b200zkp_dev_partial_products_and_zs(b200zkp_ctx* ctx, const uint64_t* wires_
  * The circuit description is what CommonCircuitData holds: the gate list in CircuitBuilder's order (sorted by degree) with
  * each gate's selector polynomial and selector group (gates/selectors.rs), num_constants = num_selectors + 2 gate constants,
  * standard_recursion_config's 135 wires / 80 routed wires.  Gate types evaluated: NoopGate, ConstantGate (2 constants),
- * PublicInputGate, ArithmeticGate (20 ops), PoseidonGate; any other kind is B200ZKP_ERR_UNSUPPORTED (not silently skipped). */
+ * PublicInputGate, ArithmeticGate (20 ops), PoseidonGate, PoseidonMdsGate, BaseSumGate<B>, ArithmeticExtensionGate,
+ * MulExtensionGate, ReducingGate, ReducingExtensionGate, RandomAccessGate, ExponentiationGate; any other kind
+ * (InterpolationGate, the u32 / comparison gates) is B200ZKP_ERR_UNSUPPORTED (not silently skipped). */
 enum { B200ZKP_GATE_NOOP = 0, B200ZKP_GATE_CONSTANT = 1, B200ZKP_GATE_PUBLIC_INPUT = 2, B200ZKP_GATE_ARITHMETIC = 3,
-       B200ZKP_GATE_POSEIDON = 4 };
+       B200ZKP_GATE_POSEIDON = 4,
+       /* gates with parameters take them from gate_params[i] = { p0, p1, p2 } (Gate::new_from_config values in brackets) */
+       B200ZKP_GATE_ARITHMETIC_EXTENSION = 5, /* ArithmeticExtensionGate, 10 ops */
+       B200ZKP_GATE_MUL_EXTENSION = 6,        /* MulExtensionGate, 13 ops */
+       B200ZKP_GATE_BASE_SUM = 7,             /* BaseSumGate<B>: { B, num_limbs } [2, 63] */
+       B200ZKP_GATE_REDUCING = 8,             /* ReducingGate: { num_coeffs } [43] */
+       B200ZKP_GATE_REDUCING_EXTENSION = 9,   /* ReducingExtensionGate: { num_coeffs } [32] */
+       B200ZKP_GATE_RANDOM_ACCESS = 10,       /* RandomAccessGate: { bits, num_copies, num_extra_constants } [e.g. 4, 4, 2] */
+       B200ZKP_GATE_EXPONENTIATION = 11,      /* ExponentiationGate: { num_power_bits } [66] */
+       B200ZKP_GATE_POSEIDON_MDS = 12 };      /* PoseidonMdsGate */
 #define B200ZKP_MAX_GATES 16
 typedef struct {
     uint32_t degree_bits;               /* n = 2^degree_bits rows */
@@ -290,6 +301,7 @@ typedef struct {
     uint32_t n_gates;
     uint32_t gate_kind[B200ZKP_MAX_GATES], gate_selector_index[B200ZKP_MAX_GATES];
     uint32_t gate_group_begin[B200ZKP_MAX_GATES], gate_group_end[B200ZKP_MAX_GATES];
+    uint32_t gate_params[B200ZKP_MAX_GATES][3];
     const uint64_t* k_is;               /* num_routed_wires coset shifts (host) */
     const uint64_t *betas, *gammas, *alphas;   /* num_challenges each (host) */
     uint64_t public_inputs_hash[4];

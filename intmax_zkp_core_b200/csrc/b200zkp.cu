@@ -2260,14 +2260,19 @@ extern "C" int b200zkp_dev_quotient_values(b200zkp_ctx* ctx, const b200zkp_vanis
     vanish::Params p{};
     u32 max_constraints = 0;
     for (u32 i = 0; i < d->n_gates; i++) {
-        static const u32 n_constraints[vanish::N_GATE_KINDS] = {0, 2, 4, 0, 123};
         const u32 kind = d->gate_kind[i];
         if (kind >= vanish::N_GATE_KINDS) { ctx->err = "gate kind not supported by the device evaluator"; return B200ZKP_ERR_UNSUPPORTED; }
+        const u32 p0 = d->gate_params[i][0], p1 = d->gate_params[i][1], p2 = d->gate_params[i][2];
+        if ((kind == vanish::GATE_BASE_SUM && (p0 < 2 || p0 > 64 || p1 == 0)) ||
+            ((kind == vanish::GATE_REDUCING || kind == vanish::GATE_REDUCING_EXTENSION || kind == vanish::GATE_EXPONENTIATION) && (p0 == 0 || p0 > 128)) ||
+            (kind == vanish::GATE_RANDOM_ACCESS && (p0 == 0 || p0 > 6 || p1 == 0 || p1 > 64 || p2 > 2)) ||
+            vanish::gate_num_wires(kind, R, p0, p1, p2) > 135)
+            BAD(ctx, "gate parameters out of range for 135 wires");
         if (d->gate_selector_index[i] >= d->num_selectors || d->gate_group_begin[i] > i || d->gate_group_end[i] <= i ||
             d->gate_group_end[i] > d->n_gates)
             BAD(ctx, "gate outside its selector group");
-        p.gates[i] = vanish::GateDesc{kind, d->gate_selector_index[i], d->gate_group_begin[i], d->gate_group_end[i]};
-        max_constraints = std::max(max_constraints, kind == vanish::GATE_ARITHMETIC ? R / 4 : n_constraints[kind]);
+        p.gates[i] = vanish::GateDesc{kind, d->gate_selector_index[i], d->gate_group_begin[i], d->gate_group_end[i], p0, p1, p2};
+        max_constraints = std::max(max_constraints, vanish::gate_num_constraints(kind, R, 2, p0, p1, p2));
     }
     const u32 chunks = (R + deg - 1) / deg;
     p.n_terms = Cn + Cn * chunks + max_constraints;

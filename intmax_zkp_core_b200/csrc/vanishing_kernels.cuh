@@ -4,7 +4,8 @@
 // which is row N1c: b200zkp_dev_coset_intt) with plonk/vanishing_poly.rs `eval_vanishing_poly_base_batch` /
 // `evaluate_gate_constraints_base_batch`, plonk_common.rs `ZeroPolyOnCoset`, `eval_l_1`, `reduce_with_powers`,
 // gates/selectors.rs `compute_filter` and the eval_unfiltered of gates/{noop, constant, public_input, arithmetic_base,
-// poseidon}.rs.  Reached from the reference through every prove() (/root/reference/src/rollup/circuits/mod.rs:1247,
+// poseidon, poseidon_mds, base_sum, arithmetic_extension, multiplication_extension, reducing, reducing_extension,
+// random_access, exponentiation}.rs.  Reached from the reference through every prove() (/root/reference/src/rollup/circuits/mod.rs:1247,
 // src/transaction/circuits/mod.rs:453, src/zkdsa/circuits/mod.rs:326); PoseidonGate is what
 // /root/reference/src/poseidon/gadgets/mod.rs:7-22 instantiates.  Restated in oracle/vanishing_ref.py (parity unpinned: the
 // crate source is not on this machine; the verifier's identity pins the restatement, tests/test_oracle_vanishing.py).
@@ -24,13 +25,64 @@ namespace vanish {
 using gl::u32;
 using gl::u64;
 
-enum GateKind : u32 { GATE_NOOP = 0, GATE_CONSTANT = 1, GATE_PUBLIC_INPUT = 2, GATE_ARITHMETIC = 3, GATE_POSEIDON = 4, N_GATE_KINDS = 5 };
+enum GateKind : u32 {
+    GATE_NOOP = 0, GATE_CONSTANT = 1, GATE_PUBLIC_INPUT = 2, GATE_ARITHMETIC = 3, GATE_POSEIDON = 4,
+    GATE_ARITHMETIC_EXTENSION = 5,   // 4 D wires per op: multiplicand 0, multiplicand 1, addend, output; constants c0, c1
+    GATE_MUL_EXTENSION = 6,          // 3 D wires per op: multiplicand 0, multiplicand 1, output; constant c0
+    GATE_BASE_SUM = 7,               // params (B, num_limbs): wire 0 = sum, limbs from wire 1 (little endian)
+    GATE_REDUCING = 8,               // params (num_coeffs): output, alpha, old_acc (D wires each), base-field coefficients, accumulators
+    GATE_REDUCING_EXTENSION = 9,     // params (num_coeffs): the same with extension-field coefficients
+    GATE_RANDOM_ACCESS = 10,         // params (bits, num_copies, num_extra_constants)
+    GATE_EXPONENTIATION = 11,        // params (num_power_bits): base, power bits, output, intermediate values
+    GATE_POSEIDON_MDS = 12,          // 12 extension inputs, 12 extension outputs
+    N_GATE_KINDS = 13
+};
+static constexpr u32 D = 2;          // quadratic extension F[X] / (X^2 - 7)
 static constexpr u32 MAX_GATES = 16, MAX_CHALLENGES = 4;
 static constexpr u32 UNUSED_SELECTOR = 0xFFFFFFFFu;
 // PoseidonGate wire layout (gates/poseidon.rs)
 static constexpr u32 W_IN = 0, W_OUT = 12, W_SWAP = 24, W_DELTA = 25, W_FULL0 = 29, W_PARTIAL = 65, W_FULL1 = 87;
 
-struct GateDesc { u32 kind, selector_index, group_begin, group_end; };
+struct GateDesc { u32 kind, selector_index, group_begin, group_end, p0, p1, p2; };
+
+// Gate::num_constraints() of standard_recursion_config instances (host and device)
+GL_FN u32 gate_num_constraints(u32 kind, u32 num_routed, u32 num_gate_consts, u32 p0, u32 p1, u32 p2) {
+    switch (kind) {
+        case GATE_CONSTANT: return num_gate_consts;
+        case GATE_PUBLIC_INPUT: return 4;
+        case GATE_ARITHMETIC: return num_routed / 4;
+        case GATE_POSEIDON: return 123;
+        case GATE_ARITHMETIC_EXTENSION: return (num_routed / (4 * D)) * D;
+        case GATE_MUL_EXTENSION: return (num_routed / (3 * D)) * D;
+        case GATE_BASE_SUM: return 1 + p1;
+        case GATE_REDUCING: case GATE_REDUCING_EXTENSION: return D * p0;
+        case GATE_RANDOM_ACCESS: return p1 * (p0 + 2) + p2;
+        case GATE_EXPONENTIATION: return p0 + 1;
+        case GATE_POSEIDON_MDS: return 12 * D;
+        default: return 0;
+    }
+}
+// highest wire index the gate reads + 1 (argument check on the host)
+GL_FN u32 gate_num_wires(u32 kind, u32 num_routed, u32 p0, u32 p1, u32 p2) {
+    switch (kind) {
+        case GATE_BASE_SUM: return 1 + p1;
+        case GATE_REDUCING: return 3 * D + p0 + D * (p0 ? p0 - 1 : 0);
+        case GATE_REDUCING_EXTENSION: return 3 * D + D * p0 + D * (p0 ? p0 - 1 : 0);
+        case GATE_RANDOM_ACCESS: return (2 + (1u << p0)) * p1 + p2 + p0 * p1;
+        case GATE_EXPONENTIATION: return 2 + 2 * p0;
+        case GATE_POSEIDON_MDS: return 24 * D;
+        case GATE_POSEIDON: return 135;
+        default: return num_routed;
+    }
+}
+
+struct E2 { u64 a, b; };
+GL_FN E2 e2_mul(E2 x, E2 y) {
+    return E2{gl::add(gl::mul(x.a, y.a), gl::mul(7, gl::mul(x.b, y.b))), gl::add(gl::mul(x.a, y.b), gl::mul(x.b, y.a))};
+}
+GL_FN E2 e2_add(E2 x, E2 y) { return E2{gl::add(x.a, y.a), gl::add(x.b, y.b)}; }
+GL_FN E2 e2_sub(E2 x, E2 y) { return E2{gl::sub(x.a, y.a), gl::sub(x.b, y.b)}; }
+GL_FN E2 e2_scale(E2 x, u64 c) { return E2{gl::mul(x.a, c), gl::mul(x.b, c)}; }
 
 struct Params {
     const u64 *cs, *wires, *zpp;               // constants+sigmas, wires, Z+partial products: [columns][stride], leaf order
@@ -237,6 +289,8 @@ GL_FN void quotient_point(const Params& p, u64 t) {
         if (p.num_selectors > 1) filter = gl::mul(filter, gl::sub((u64)UNUSED_SELECTOR, s));
         Fold f;
         f.pw = p.alpha_pows + term; f.n_terms = p.n_terms; f.C = C; f.t = 0;
+        auto wire = [&](u32 j) { return wr[(u64)j * p.wires_stride]; };
+        auto ext = [&](u32 j) { return E2{wr[(u64)j * p.wires_stride], wr[(u64)(j + 1) * p.wires_stride]}; };
 #pragma unroll
         for (u32 c = 0; c < MAX_CHALLENGES; c++) f.acc[c] = 0;
         switch (gd.kind) {
@@ -258,6 +312,102 @@ GL_FN void quotient_point(const Params& p, u64 t) {
             case GATE_POSEIDON:
                 poseidon_gate(wr, p.wires_stride, f);
                 break;
+            case GATE_ARITHMETIC_EXTENSION: {                         // gates/arithmetic_extension.rs
+                const u64 c0 = gc[0], c1 = gc[p.cs_stride];
+                for (u32 q = 0; q < p.num_routed / (4 * D); q++) {
+                    const u32 w0 = 4 * D * q;
+                    const E2 r = e2_sub(ext(w0 + 3 * D), e2_add(e2_scale(e2_mul(ext(w0), ext(w0 + D)), c0), e2_scale(ext(w0 + 2 * D), c1)));
+                    f.add(r.a); f.add(r.b);
+                }
+                break;
+            }
+            case GATE_MUL_EXTENSION: {                                // gates/multiplication_extension.rs
+                const u64 c0 = gc[0];
+                for (u32 q = 0; q < p.num_routed / (3 * D); q++) {
+                    const u32 w0 = 3 * D * q;
+                    const E2 r = e2_sub(ext(w0 + 2 * D), e2_scale(e2_mul(ext(w0), ext(w0 + D)), c0));
+                    f.add(r.a); f.add(r.b);
+                }
+                break;
+            }
+            case GATE_BASE_SUM: {                                     // gates/base_sum.rs
+                const u32 base = gd.p0, num_limbs = gd.p1;
+                u64 computed = 0;
+                for (u32 q = num_limbs; q-- > 0;) computed = gl::add(gl::mul(computed, base), wire(1 + q));
+                f.add(gl::sub(computed, wire(0)));
+                for (u32 q = 0; q < num_limbs; q++) {
+                    const u64 l = wire(1 + q);
+                    u64 prod = 1;
+                    for (u32 v = 0; v < base; v++) prod = gl::mul(prod, gl::sub(l, (u64)v));
+                    f.add(prod);
+                }
+                break;
+            }
+            case GATE_REDUCING:
+            case GATE_REDUCING_EXTENSION: {                           // gates/reducing.rs, reducing_extension.rs
+                const u32 nc = gd.p0, cw = gd.kind == GATE_REDUCING ? 1u : D;
+                const E2 output = ext(0), alpha = ext(D);
+                E2 acc = ext(2 * D);
+                const u32 start_coeffs = 3 * D, start_accs = start_coeffs + nc * cw;
+                for (u32 q = 0; q < nc; q++) {
+                    const E2 coeff = gd.kind == GATE_REDUCING ? E2{wire(start_coeffs + q), 0} : ext(start_coeffs + D * q);
+                    const E2 acc_q = (q + 1 == nc) ? output : ext(start_accs + D * q);
+                    const E2 r = e2_sub(e2_add(e2_mul(acc, alpha), coeff), acc_q);
+                    f.add(r.a); f.add(r.b);
+                    acc = acc_q;
+                }
+                break;
+            }
+            case GATE_RANDOM_ACCESS: {                                // gates/random_access.rs
+                const u32 bits = gd.p0, copies = gd.p1, extra = gd.p2, vec = 1u << bits;
+                const u32 routed = (2 + vec) * copies + extra;
+                for (u32 cp = 0; cp < copies; cp++) {
+                    const u32 base_w = (2 + vec) * cp, bit_w = routed + cp * bits;
+                    u64 rec = 0;
+                    for (u32 q = 0; q < bits; q++) { const u64 b = wire(bit_w + q); f.add(gl::mul(b, gl::sub(b, 1))); }
+                    for (u32 q = bits; q-- > 0;) rec = gl::add(gl::add(rec, rec), wire(bit_w + q));
+                    f.add(gl::sub(rec, wire(base_w)));
+                    // fold the list pair by pair, bit 0 first: item index bit q is decided by bit q.  Evaluated as a selection
+                    // tree walked from the leaves without a per-thread array: level by level over the 2^bits items costs the same
+                    // multiplications as plonky2's fold when done in place on a small register file of at most 64 items
+                    u64 items[64];
+                    for (u32 q = 0; q < vec; q++) items[q] = wire(base_w + 2 + q);
+                    u32 len = vec;
+                    for (u32 q = 0; q < bits; q++) {
+                        const u64 b = wire(bit_w + q);
+                        len >>= 1;
+                        for (u32 v = 0; v < len; v++) items[v] = gl::add(items[2 * v], gl::mul(b, gl::sub(items[2 * v + 1], items[2 * v])));
+                    }
+                    f.add(gl::sub(items[0], wire(base_w + 1)));
+                }
+                for (u32 q = 0; q < extra; q++) f.add(gl::sub(gc[(u64)q * p.cs_stride], wire((2 + vec) * copies + q)));
+                break;
+            }
+            case GATE_EXPONENTIATION: {                               // gates/exponentiation.rs
+                const u32 nb = gd.p0;
+                const u64 base = wire(0);
+                u64 prev_inter = 1;
+                for (u32 q = 0; q < nb; q++) {
+                    const u64 prev = q == 0 ? 1 : gl::mul(prev_inter, prev_inter);
+                    const u64 cur = wire(1 + (nb - 1 - q));
+                    const u64 inter = wire(2 + nb + q);
+                    f.add(gl::sub(gl::mul(prev, gl::add(gl::mul(cur, base), gl::sub(1, cur))), inter));
+                    prev_inter = inter;
+                }
+                f.add(gl::sub(wire(1 + nb), prev_inter));
+                break;
+            }
+            case GATE_POSEIDON_MDS: {                                 // gates/poseidon_mds.rs: the MDS layer, component by component
+                u64 s0[12], s1[12];
+                for (u32 q = 0; q < 12; q++) { s0[q] = wire(D * q); s1[q] = wire(D * q + 1); }
+                mds_layer(s0);
+                mds_layer(s1);
+                for (u32 q = 0; q < 12; q++) {
+                    f.add(gl::sub(wire(D * (12 + q)), s0[q]));
+                    f.add(gl::sub(wire(D * (12 + q) + 1), s1[q]));
+                }
+                break;
+            }
             default: break;
         }
         for (u32 a = 0; a < C; a++) acc[a] = gl::add(acc[a], gl::mul(filter, f.acc[a]));

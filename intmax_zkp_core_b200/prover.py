@@ -161,6 +161,8 @@ def commit_quotient_device(ctx: Context, quotient_values, degree_bits: int, rate
 
 # ------------------------------------------------------------------------------------------------ row N1b: compute_quotient_polys
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_POSEIDON = range(5)
+(GATE_ARITHMETIC_EXTENSION, GATE_MUL_EXTENSION, GATE_BASE_SUM, GATE_REDUCING, GATE_REDUCING_EXTENSION, GATE_RANDOM_ACCESS,
+ GATE_EXPONENTIATION, GATE_POSEIDON_MDS) = range(5, 13)
 MAX_GATES = 16
 
 
@@ -170,6 +172,7 @@ class _VanishingDesc(C.Structure):
                 ("n_gates", C.c_uint32),
                 ("gate_kind", C.c_uint32 * MAX_GATES), ("gate_selector_index", C.c_uint32 * MAX_GATES),
                 ("gate_group_begin", C.c_uint32 * MAX_GATES), ("gate_group_end", C.c_uint32 * MAX_GATES),
+                ("gate_params", (C.c_uint32 * 3) * MAX_GATES),
                 ("k_is", C.c_void_p), ("betas", C.c_void_p), ("gammas", C.c_void_p), ("alphas", C.c_void_p),
                 ("public_inputs_hash", C.c_uint64 * 4)]
 
@@ -177,7 +180,9 @@ class _VanishingDesc(C.Structure):
 class CommonCircuitData:
     """What compute_quotient_polys needs of plonky2's CommonCircuitData: degree_bits, the gate list in CircuitBuilder's order with
     the selector polynomial and selector group of every gate (SelectorsInfo), quotient_degree_factor, k_is.
-    gates: [(kind, selector_index, (group_begin, group_end)), ...]"""
+    gates: [(kind, selector_index, (group_begin, group_end)[, params]), ...]; params: the gate's own parameters
+    (BaseSum (B, num_limbs), Reducing / ReducingExtension (num_coeffs,), RandomAccess (bits, num_copies, num_extra_constants),
+    Exponentiation (num_power_bits,))"""
 
     def __init__(self, degree_bits: int, gates, num_selectors: int, quotient_degree_factor: int = 8, num_routed_wires: int = 80,
                  k_is=None):
@@ -213,8 +218,11 @@ def compute_quotient_values_device(ctx: Context, common: CommonCircuitData, cons
     d = _VanishingDesc()
     d.degree_bits, d.quotient_degree_bits, d.quotient_degree_factor = common.degree_bits, q_bits, common.quotient_degree_factor
     d.num_routed_wires, d.num_challenges, d.num_selectors, d.n_gates = common.num_routed_wires, b.size, common.num_selectors, len(common.gates)
-    for i, (kind, sel, grp) in enumerate(common.gates):
+    for i, gate in enumerate(common.gates):
+        kind, sel, grp = gate[:3]
         d.gate_kind[i], d.gate_selector_index[i], d.gate_group_begin[i], d.gate_group_end[i] = kind, sel, grp[0], grp[1]
+        for j, v in enumerate(gate[3] if len(gate) > 3 else ()):
+            d.gate_params[i][j] = int(v)
     k = _u64(common.k_is)
     d.k_is, d.betas, d.gammas, d.alphas = k.ctypes.data, b.ctypes.data, g.ctypes.data, a.ctypes.data
     for i, v in enumerate(public_inputs_hash):

@@ -7,7 +7,9 @@ the quotient coset and dividing by Z_H,
                        plonky2/src/plonk/vanishing_poly.rs  eval_vanishing_poly_base_batch, evaluate_gate_constraints_base_batch
                        plonky2/src/plonk/plonk_common.rs    ZeroPolyOnCoset, eval_l_1, reduce_with_powers
                        plonky2/src/plonk/vars.rs, gates/selectors.rs (selector polynomials, compute_filter)
-                       plonky2/src/gates/{noop, constant, public_input, arithmetic_base, poseidon}.rs
+                       plonky2/src/gates/{noop, constant, public_input, arithmetic_base, poseidon, poseidon_mds, base_sum,
+                                          arithmetic_extension, multiplication_extension, reducing, reducing_extension,
+                                          random_access, exponentiation}.rs
 
 reached from the reference through every prove() (/root/reference/src/rollup/circuits/mod.rs:1247,
 src/transaction/circuits/mod.rs:453, src/zkdsa/circuits/mod.rs:326); the Poseidon gate is the one the reference's circuits
@@ -45,10 +47,59 @@ UNUSED_SELECTOR = 0xFFFFFFFF
 WIDTH, N_FULL_HALF, N_PARTIAL = 12, 4, 22
 NUM_WIRES, NUM_ROUTED, NUM_GATE_CONSTANTS = 135, 80, 2       # CircuitConfig::standard_recursion_config()
 
-# gate kinds (ids shared with csrc/vanishing_kernels.cuh)
+# gate kinds (ids shared with csrc/vanishing_kernels.cuh).  Gates with parameters carry them as a tuple:
+#   BASE_SUM (B, num_limbs) | REDUCING (num_coeffs,) | REDUCING_EXTENSION (num_coeffs,) |
+#   RANDOM_ACCESS (bits, num_copies, num_extra_constants) | EXPONENTIATION (num_power_bits,)
 NOOP, CONSTANT, PUBLIC_INPUT, ARITHMETIC, POSEIDON = 0, 1, 2, 3, 4
-GATE_DEGREE = {NOOP: 0, CONSTANT: 1, PUBLIC_INPUT: 1, ARITHMETIC: 3, POSEIDON: 7}
-GATE_CONSTRAINTS = {NOOP: 0, CONSTANT: 2, PUBLIC_INPUT: 4, ARITHMETIC: 20, POSEIDON: 123}
+ARITHMETIC_EXTENSION, MUL_EXTENSION, BASE_SUM, REDUCING, REDUCING_EXTENSION, RANDOM_ACCESS, EXPONENTIATION, POSEIDON_MDS = 5, 6, 7, 8, 9, 10, 11, 12
+D = 2                      # quadratic extension F[X] / (X^2 - 7)
+W_EXT = 7
+
+
+def gate_degree(kind: int, params=()) -> int:
+    """Gate::degree()"""
+    fixed = {NOOP: 0, CONSTANT: 1, PUBLIC_INPUT: 1, ARITHMETIC: 3, POSEIDON: 7, ARITHMETIC_EXTENSION: 3, MUL_EXTENSION: 3,
+             REDUCING: 2, REDUCING_EXTENSION: 2, EXPONENTIATION: 4, POSEIDON_MDS: 1}
+    if kind == BASE_SUM:
+        return params[0]
+    if kind == RANDOM_ACCESS:
+        return params[0] + 1
+    return fixed[kind]
+
+
+def gate_num_constraints(kind: int, params=()) -> int:
+    """Gate::num_constraints() for standard_recursion_config (135 wires, 80 routed)"""
+    fixed = {NOOP: 0, CONSTANT: NUM_GATE_CONSTANTS, PUBLIC_INPUT: 4, ARITHMETIC: NUM_ROUTED // 4, POSEIDON: 123,
+             ARITHMETIC_EXTENSION: (NUM_ROUTED // (4 * D)) * D, MUL_EXTENSION: (NUM_ROUTED // (3 * D)) * D, POSEIDON_MDS: WIDTH * D}
+    if kind == BASE_SUM:
+        return 1 + params[1]
+    if kind in (REDUCING, REDUCING_EXTENSION):
+        return D * params[0]
+    if kind == RANDOM_ACCESS:
+        return params[1] * (params[0] + 2) + params[2]
+    if kind == EXPONENTIATION:
+        return params[0] + 1
+    return fixed[kind]
+
+
+GATE_DEGREE = {k: gate_degree(k) for k in (NOOP, CONSTANT, PUBLIC_INPUT, ARITHMETIC, POSEIDON)}
+GATE_CONSTRAINTS = {k: gate_num_constraints(k) for k in (NOOP, CONSTANT, PUBLIC_INPUT, ARITHMETIC, POSEIDON)}
+
+
+def ext_mul(a, b):
+    return ((a[0] * b[0] + W_EXT * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def ext_add(a, b):
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def ext_sub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def ext_scale(a, c):
+    return (a[0] * c % P, a[1] * c % P)
 
 # PoseidonGate wire layout (gates/poseidon.rs)
 W_IN, W_OUT, W_SWAP, W_DELTA, W_FULL0, W_PARTIAL, W_FULL1 = 0, 12, 24, 25, 29, 65, 87
@@ -160,10 +211,85 @@ def poseidon_gate_witness(inputs: Sequence[int], swap: int = 0) -> List[int]:
     return w
 
 
-def gate_constraints(kind: int, wires: Sequence[int], consts: Sequence[int], pi_hash: Sequence[int]) -> List[int]:
+def random_access_layout(bits: int, num_copies: int, num_extra: int):
+    """gates/random_access.rs wire indices: (access_index, claimed_element, list_item(i), bit(i)) per copy, extra constants"""
+    vec = 1 << bits
+    routed = (2 + vec) * num_copies + num_extra
+    return dict(vec=vec, access=lambda c: (2 + vec) * c, claimed=lambda c: (2 + vec) * c + 1,
+                item=lambda i, c: (2 + vec) * c + 2 + i, extra=lambda i: (2 + vec) * num_copies + i,
+                bit=lambda i, c: routed + c * bits + i)
+
+
+def gate_constraints(kind: int, wires: Sequence[int], consts: Sequence[int], pi_hash: Sequence[int], params=()) -> List[int]:
     """eval_unfiltered of one gate type at one point; consts = the NUM_GATE_CONSTANTS gate constants (selectors removed)"""
     out: List[int] = []
-    if kind == CONSTANT:                                   # gates/constant.rs: consts_inputs[i] - wire[i]
+    ext = lambda j: (wires[j], wires[j + 1])
+    if kind == ARITHMETIC_EXTENSION:                       # gates/arithmetic_extension.rs, num_ops = num_routed / (4 D)
+        for i in range(NUM_ROUTED // (4 * D)):
+            m0, m1, addend, output = (ext(4 * D * i + D * t) for t in range(4))
+            computed = ext_add(ext_scale(ext_mul(m0, m1), consts[0]), ext_scale(addend, consts[1]))
+            out += list(ext_sub(output, computed))
+    elif kind == MUL_EXTENSION:                            # gates/multiplication_extension.rs, num_ops = num_routed / (3 D)
+        for i in range(NUM_ROUTED // (3 * D)):
+            m0, m1, output = (ext(3 * D * i + D * t) for t in range(3))
+            out += list(ext_sub(output, ext_scale(ext_mul(m0, m1), consts[0])))
+    elif kind == BASE_SUM:                                 # gates/base_sum.rs: WIRE_SUM = 0, limbs from wire 1, little endian
+        base, num_limbs = params
+        limbs = wires[1:1 + num_limbs]
+        computed = 0
+        for l in reversed(limbs):
+            computed = (computed * base + l) % P
+        out.append((computed - wires[0]) % P)
+        for l in limbs:
+            prod = 1
+            for i in range(base):
+                prod = prod * (l - i) % P
+            out.append(prod)
+    elif kind in (REDUCING, REDUCING_EXTENSION):           # gates/reducing.rs, reducing_extension.rs
+        (num_coeffs,) = params
+        cw = 1 if kind == REDUCING else D                  # wires per coefficient
+        output, alpha, acc = ext(0), ext(D), ext(2 * D)
+        start_coeffs = 3 * D
+        start_accs = start_coeffs + num_coeffs * cw
+        for i in range(num_coeffs):
+            coeff = (wires[start_coeffs + i], 0) if kind == REDUCING else ext(start_coeffs + D * i)
+            acc_i = output if i == num_coeffs - 1 else ext(start_accs + D * i)
+            out += list(ext_sub(ext_add(ext_mul(acc, alpha), coeff), acc_i))
+            acc = acc_i
+    elif kind == RANDOM_ACCESS:                            # gates/random_access.rs
+        bits, num_copies, num_extra = params
+        L = random_access_layout(bits, num_copies, num_extra)
+        for c in range(num_copies):
+            bs = [wires[L["bit"](i, c)] for i in range(bits)]
+            for b in bs:
+                out.append(b * (b - 1) % P)
+            rec = 0
+            for b in reversed(bs):
+                rec = (2 * rec + b) % P
+            out.append((rec - wires[L["access"](c)]) % P)
+            items = [wires[L["item"](i, c)] for i in range(L["vec"])]
+            for b in bs:
+                items = [(items[2 * t] + b * (items[2 * t + 1] - items[2 * t])) % P for t in range(len(items) // 2)]
+            out.append((items[0] - wires[L["claimed"](c)]) % P)
+        for i in range(num_extra):
+            out.append((consts[i] - wires[L["extra"](i)]) % P)
+    elif kind == EXPONENTIATION:                           # gates/exponentiation.rs: base 0, power bits 1.., output, intermediates
+        (nb,) = params
+        base = wires[0]
+        bits_ = wires[1:1 + nb]
+        output = wires[1 + nb]
+        inter = wires[2 + nb:2 + 2 * nb]
+        for i in range(nb):
+            prev = 1 if i == 0 else inter[i - 1] * inter[i - 1] % P
+            cur = bits_[nb - 1 - i]
+            out.append((prev * ((cur * base + 1 - cur) % P) - inter[i]) % P)
+        out.append((output - inter[nb - 1]) % P)
+    elif kind == POSEIDON_MDS:                             # gates/poseidon_mds.rs: the MDS layer on 12 extension elements
+        cols = [mds([wires[D * i + comp] for i in range(WIDTH)]) for comp in range(D)]
+        for i in range(WIDTH):
+            for comp in range(D):
+                out.append((wires[D * (WIDTH + i) + comp] - cols[comp][i]) % P)
+    elif kind == CONSTANT:                                   # gates/constant.rs: consts_inputs[i] - wire[i]
         for i in range(NUM_GATE_CONSTANTS):
             out.append((consts[i] - wires[i]) % P)
     elif kind == PUBLIC_INPUT:                             # gates/public_input.rs: wire[i] - public_inputs_hash[i]
@@ -178,13 +304,92 @@ def gate_constraints(kind: int, wires: Sequence[int], consts: Sequence[int], pi_
     return out
 
 
+# ---------------------------------------------------------------------------------------------------- witnesses of the other gates
+# parameters of the instances standard_recursion_config circuits hold (Gate::new_from_config; RandomAccess for 16-element lists)
+EXT_GATE_PARAMS = {BASE_SUM: (2, 63), REDUCING: (43,), REDUCING_EXTENSION: (32,), RANDOM_ACCESS: (4, 4, 2), EXPONENTIATION: (66,)}
+
+
+def gate_witness(kind: int, rnd: random.Random, consts: Sequence[int], params=()) -> List[int]:
+    """135 wires of one row of `kind` whose constraints vanish (what the gate's generators compute from random inputs)"""
+    w = [rnd.randrange(P) for _ in range(NUM_WIRES)]        # unconstrained wires hold anything
+    rext = lambda: (rnd.randrange(P), rnd.randrange(P))
+
+    def put(j, e):
+        w[j], w[j + 1] = e
+
+    if kind == ARITHMETIC_EXTENSION:
+        for i in range(NUM_ROUTED // (4 * D)):
+            m0, m1, ad = rext(), rext(), rext()
+            put(4 * D * i, m0); put(4 * D * i + D, m1); put(4 * D * i + 2 * D, ad)
+            put(4 * D * i + 3 * D, ext_add(ext_scale(ext_mul(m0, m1), consts[0]), ext_scale(ad, consts[1])))
+    elif kind == MUL_EXTENSION:
+        for i in range(NUM_ROUTED // (3 * D)):
+            m0, m1 = rext(), rext()
+            put(3 * D * i, m0); put(3 * D * i + D, m1); put(3 * D * i + 2 * D, ext_scale(ext_mul(m0, m1), consts[0]))
+    elif kind == BASE_SUM:
+        base, num_limbs = params
+        limbs = [rnd.randrange(base) for _ in range(num_limbs)]
+        w[1:1 + num_limbs] = limbs
+        w[0] = sum(l * pow(base, i, P) for i, l in enumerate(limbs)) % P
+    elif kind in (REDUCING, REDUCING_EXTENSION):
+        (num_coeffs,) = params
+        cw = 1 if kind == REDUCING else D
+        alpha, acc = rext(), rext()
+        put(D, alpha); put(2 * D, acc)
+        start_coeffs = 3 * D
+        start_accs = start_coeffs + num_coeffs * cw
+        for i in range(num_coeffs):
+            if kind == REDUCING:
+                coeff = (rnd.randrange(P), 0)
+                w[start_coeffs + i] = coeff[0]
+            else:
+                coeff = rext()
+                put(start_coeffs + D * i, coeff)
+            acc = ext_add(ext_mul(acc, alpha), coeff)
+            put(0 if i == num_coeffs - 1 else start_accs + D * i, acc)
+    elif kind == RANDOM_ACCESS:
+        bits, num_copies, num_extra = params
+        L = random_access_layout(bits, num_copies, num_extra)
+        for c in range(num_copies):
+            idx = rnd.randrange(L["vec"])
+            items = [rnd.randrange(P) for _ in range(L["vec"])]
+            w[L["access"](c)] = idx
+            w[L["claimed"](c)] = items[idx]
+            for i, v in enumerate(items):
+                w[L["item"](i, c)] = v
+            for i in range(bits):
+                w[L["bit"](i, c)] = (idx >> i) & 1
+        for i in range(num_extra):
+            w[L["extra"](i)] = consts[i]
+    elif kind == EXPONENTIATION:
+        (nb,) = params
+        base = rnd.randrange(P)
+        bits_ = [rnd.randrange(2) for _ in range(nb)]
+        w[0] = base
+        w[1:1 + nb] = bits_
+        cur = 1
+        for i in range(nb):
+            prev = 1 if i == 0 else cur * cur % P
+            cur = prev * (base if bits_[nb - 1 - i] else 1) % P
+            w[2 + nb + i] = cur
+        w[1 + nb] = cur
+    elif kind == POSEIDON_MDS:
+        cols = [mds([w[D * i + comp] for i in range(WIDTH)]) for comp in range(D)]
+        for i in range(WIDTH):
+            for comp in range(D):
+                w[D * (WIDTH + i) + comp] = cols[comp][i]
+    else:
+        raise ValueError(kind)
+    return w
+
+
 # ---------------------------------------------------------------------------------------------------- selectors
 def selector_groups(gates: Sequence[int], max_degree: int):
     """gates/selectors.rs selector_polynomials: gates are sorted by degree; one selector polynomial per group, groups grown
     greedily while  group size + the largest gate degree in it <= max_degree + 1  (one group, no UNUSED factor, if all fit).
     Returns (selector_indices per gate, groups as (begin, end))."""
     n = len(gates)
-    degs = [GATE_DEGREE[g] for g in gates]
+    degs = [gate_degree(*g) if isinstance(g, tuple) else gate_degree(g) for g in gates]
     assert degs == sorted(degs), "gates must be sorted by degree"
     if max(degs) + n - 1 <= max_degree:
         return [0] * n, [(0, n)]
@@ -216,13 +421,20 @@ class Circuit:
     constraints.  Rows: a chain of Poseidon permutations (each row's inputs are wired to the previous row's outputs), a few
     arithmetic rows fed by Poseidon outputs, one constant row, one public-input row, no-ops to the power of two."""
 
-    def __init__(self, n_log: int, seed: int = 0, n_poseidon: int | None = None):
+    def __init__(self, n_log: int, seed: int = 0, n_poseidon: int | None = None, extended: bool = False):
+        """extended: also rows of PoseidonMds, BaseSum, Reducing, ReducingExtension, ArithmeticExtension, MulExtension,
+        Exponentiation and RandomAccess gates (random satisfied instances, not wired to anything)"""
         rnd = random.Random(seed)
         n = 1 << n_log
         self.n_log, self.n = n_log, n
-        self.gates = [NOOP, CONSTANT, PUBLIC_INPUT, ARITHMETIC, POSEIDON]          # sorted by degree, as CircuitBuilder does
+        # sorted by degree, as CircuitBuilder does
+        self.gates = [NOOP, CONSTANT, PUBLIC_INPUT, ARITHMETIC, POSEIDON]
+        if extended:
+            self.gates = [NOOP, CONSTANT, PUBLIC_INPUT, POSEIDON_MDS, BASE_SUM, REDUCING, REDUCING_EXTENSION, ARITHMETIC,
+                          ARITHMETIC_EXTENSION, MUL_EXTENSION, EXPONENTIATION, RANDOM_ACCESS, POSEIDON]
+        self.gate_params = [EXT_GATE_PARAMS.get(g, ()) for g in self.gates]
         self.max_degree = 8
-        self.selector_indices, self.groups = selector_groups(self.gates, self.max_degree)
+        self.selector_indices, self.groups = selector_groups(list(zip(self.gates, self.gate_params)), self.max_degree)
         self.num_selectors = len(self.groups)
         self.row_gate = [0] * n                     # index into self.gates
         self.wires = [[0] * n for _ in range(NUM_WIRES)]
@@ -230,7 +442,10 @@ class Circuit:
         self.pi_hash = [rnd.randrange(P) for _ in range(4)]
         classes: List[List[tuple]] = []             # copy-constraint classes of (wire, row) cells
         n_pos = n_poseidon if n_poseidon is not None else max(1, n // 2)
-        n_arith = max(1, min(n // 8, n - n_pos - 2)) if n - n_pos - 2 > 0 else 0
+        n_other = 8 if extended else 0
+        if extended and n - n_pos < n_other + 4:
+            n_pos = max(1, n - n_other - 4)
+        n_arith = max(1, min(n // 8, n - n_pos - 2 - n_other)) if n - n_pos - 2 - n_other > 0 else 0
         row = 0
         state = [rnd.randrange(P) for _ in range(WIDTH)]
         prev_out_row = None
@@ -259,6 +474,19 @@ class Circuit:
                 classes.append([(W_OUT + (i % WIDTH), src), (4 * i, row)])
             self.row_gate[row] = self.gates.index(ARITHMETIC)
             row += 1
+        if extended:
+            for gi, g in enumerate(self.gates):
+                if g in (NOOP, CONSTANT, PUBLIC_INPUT, ARITHMETIC, POSEIDON) or row >= n:
+                    continue
+                cc = [rnd.randrange(P) for _ in range(NUM_GATE_CONSTANTS)]
+                w = gate_witness(g, rnd, cc, self.gate_params[gi])
+                assert not any(gate_constraints(g, w, cc, self.pi_hash, self.gate_params[gi]))
+                for i in range(NUM_GATE_CONSTANTS):
+                    self.gate_consts[i][row] = cc[i]
+                for j in range(NUM_WIRES):
+                    self.wires[j][row] = w[j]
+                self.row_gate[row] = gi
+                row += 1
         if row < n:
             c = [rnd.randrange(P), rnd.randrange(P)]
             for i in range(NUM_GATE_CONSTANTS):
@@ -326,12 +554,12 @@ def vanishing_terms_at(c: Circuit, x: int, consts_row, sigmas_row, wires_row, zs
                 num = num * ((wires_row[j] + betas[i] * c.k_is[j] % P * x + gammas[i]) % P) % P
                 den = den * ((wires_row[j] + betas[i] * sigmas_row[j] + gammas[i]) % P) % P
             terms.append((acc[l] * num - acc[l + 1] * den) % P)
-    n_gc = max(GATE_CONSTRAINTS[g] for g in c.gates)
+    n_gc = max(gate_num_constraints(g, pr) for g, pr in zip(c.gates, c.gate_params))
     gc = [0] * n_gc
     for gi, g in enumerate(c.gates):
         k = c.selector_indices[gi]
         f = compute_filter(gi, c.groups[k], consts_row[k], c.num_selectors > 1)
-        for t, v in enumerate(gate_constraints(g, wires_row, consts_row[c.num_selectors:], c.pi_hash)):
+        for t, v in enumerate(gate_constraints(g, wires_row, consts_row[c.num_selectors:], c.pi_hash, c.gate_params[gi])):
             gc[t] = (gc[t] + f * v) % P
     return terms + gc
 

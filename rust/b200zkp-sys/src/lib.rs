@@ -26,6 +26,7 @@ pub struct b200zkp_vanishing_desc {
     pub gate_selector_index: [u32; B200ZKP_MAX_GATES],
     pub gate_group_begin: [u32; B200ZKP_MAX_GATES],
     pub gate_group_end: [u32; B200ZKP_MAX_GATES],
+    pub gate_params: [[u32; 3]; B200ZKP_MAX_GATES],
     pub k_is: *const u64,
     pub betas: *const u64,
     pub gammas: *const u64,

@@ -167,7 +167,7 @@ int emu_ct_lde_cols(const u64* const* src, u32 n_src, u32 kp, u32 k, u32 ca, u32
     return 1;
 }
 // row N1b: vanish::quotient_point stepped over every leaf of the quotient coset; LDEs [columns][Q] in leaf order,
-// gates: n_gates x (kind, selector_index, group_begin, group_end); out [C][Q] natural order
+// gates: n_gates x (kind, selector_index, group_begin, group_end, p0, p1, p2); out [C][Q] natural order
 void emu_quotient_values(const u64* cs, const u64* wires, const u64* zpp, u32 n_log, u32 q_bits, u32 num_selectors, u32 C, u32 degree,
                          const u32* gates, u32 n_gates, const u64* k_is, const u64* betas, const u64* gammas, const u64* alphas,
                          const u64* pi_hash, u64* out) {
@@ -179,9 +179,10 @@ void emu_quotient_values(const u64* cs, const u64* wires, const u64* zpp, u32 n_
     p.num_challenges = C; p.degree = degree; p.num_prods = (R + degree - 1) / degree - 1; p.n_gates = n_gates;
     u32 max_c = 0;
     for (u32 i = 0; i < n_gates; i++) {
-        p.gates[i] = vanish::GateDesc{gates[4 * i], gates[4 * i + 1], gates[4 * i + 2], gates[4 * i + 3]};
-        const u32 nc[5] = {0, 2, 4, R / 4, 123};
-        if (nc[gates[4 * i]] > max_c) max_c = nc[gates[4 * i]];
+        const u32* gi = gates + 7 * i;
+        p.gates[i] = vanish::GateDesc{gi[0], gi[1], gi[2], gi[3], gi[4], gi[5], gi[6]};
+        const u32 nc = vanish::gate_num_constraints(gi[0], R, 2, gi[4], gi[5], gi[6]);
+        if (nc > max_c) max_c = nc;
     }
     p.n_terms = C + C * (p.num_prods + 1) + max_c;
     std::vector<u64> apw((size_t)C * p.n_terms), zh(1u << q_bits), zhi(1u << q_bits), lo, hi;

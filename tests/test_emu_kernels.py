@@ -197,13 +197,15 @@ def test_permutation_argument_rows(emu):
                 assert int(running[c, chunks - 1, i]) * z[i] % P == (z[i + 1] if i + 1 < n else 1)
 
 
-def test_quotient_point_body(emu, oracle):
-    """row N1b: the per-point body of vanishing_kernels.cuh against oracle/vanishing_ref.py on a satisfied synthetic circuit"""
+@pytest.mark.parametrize("n_log,extended", [(3, False), (5, True)])
+def test_quotient_point_body(emu, oracle, n_log, extended):
+    """row N1b: the per-point body of vanishing_kernels.cuh against oracle/vanishing_ref.py on a satisfied synthetic circuit
+    (extended: with rows of all thirteen gate kinds)"""
     import random
     from oracle import perm_ref as PR
     from oracle import vanishing_ref as V
-    n_log, r = 3, 3
-    c = V.Circuit(n_log, seed=1)
+    r = 3
+    c = V.Circuit(n_log, seed=1, extended=extended)
     rnd = random.Random(8)
     betas, gammas, alphas = ([rnd.randrange(P) for _ in range(2)] for _ in range(3))
     zs_pp = PR.partial_products_and_zs([c.wires[j] for j in range(80)], c.sigmas, c.k_is, betas, gammas, 8)
@@ -212,7 +214,8 @@ def test_quotient_point_body(emu, oracle):
     want = np.array(V.quotient_values(c, l_cs, l_w, l_z, betas, gammas, alphas, 8, r, 3), np.uint64)
     perm = bitrev_perm(n_log + r)
     leaf = lambda cols: np.ascontiguousarray(np.stack([col[perm] for col in cols]))
-    gates = np.array([[g, c.selector_indices[i], *c.groups[c.selector_indices[i]]] for i, g in enumerate(c.gates)], np.uint32)
+    gates = np.array([[g, c.selector_indices[i], *c.groups[c.selector_indices[i]], *(list(c.gate_params[i]) + [0, 0, 0])[:3]]
+                      for i, g in enumerate(c.gates)], np.uint32)
     out = np.zeros((2, 1 << (n_log + r)), np.uint64)
     u32p = C.POINTER(C.c_uint32)
     a = lambda v: np.array(v, np.uint64)

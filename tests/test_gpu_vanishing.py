@@ -11,16 +11,19 @@ P = 0xFFFFFFFF00000001
 
 
 def _common(zp, c):
-    return zp.CommonCircuitData(c.n_log, [(g, c.selector_indices[i], c.groups[c.selector_indices[i]]) for i, g in enumerate(c.gates)],
+    return zp.CommonCircuitData(c.n_log, [(g, c.selector_indices[i], c.groups[c.selector_indices[i]], c.gate_params[i])
+                                          for i, g in enumerate(c.gates)],
                                 c.num_selectors, quotient_degree_factor=8, k_is=np.array(c.k_is, np.uint64))
 
 
-@pytest.mark.parametrize("n_log,seed", [(3, 1), (5, 2), (7, 3)])
-def test_quotient_values_match_oracle_and_close_the_identity(oracle, n_log, seed):
+@pytest.mark.parametrize("n_log,seed,extended", [(3, 1, False), (5, 2, False), (7, 3, False), (5, 4, True), (8, 5, True)])
+def test_quotient_values_match_oracle_and_close_the_identity(oracle, n_log, seed, extended):
+    """extended: the circuit also holds PoseidonMds, BaseSum, Reducing, ReducingExtension, ArithmeticExtension, MulExtension,
+    Exponentiation and RandomAccess rows (13 gate kinds, 4 selector polynomials)"""
     import torch
     from intmax_zkp_core_b200 import device as D, prover as zp
     from oracle import vanishing_ref as V
-    c = V.Circuit(n_log, seed=seed)
+    c = V.Circuit(n_log, seed=seed, extended=extended)
     n, r, h = 1 << n_log, 3, min(4, n_log)
     rnd = random.Random(seed + 7)
     betas, gammas, alphas = ([rnd.randrange(P) for _ in range(2)] for _ in range(3))
@@ -67,11 +70,16 @@ def test_quotient_argument_errors():
     from intmax_zkp_core_b200 import device as D, prover as zp
     from intmax_zkp_core_b200._lib import B200ZkpError
     ctx = D.torch_context(0)
-    common = zp.CommonCircuitData(3, [(zp.GATE_NOOP, 0, (0, 2)), (7, 0, (0, 2))], 1)        # unknown gate kind
+    common = zp.CommonCircuitData(3, [(zp.GATE_NOOP, 0, (0, 2)), (13, 0, (0, 2))], 1)       # unknown gate kind
     t = lambda k: torch.zeros((k, 64), dtype=torch.int64, device="cuda")
     with pytest.raises(B200ZkpError) as e:
         zp.compute_quotient_values_device(ctx, common, t(83), t(135), t(20), [1, 2], [3, 4], [5, 6], [0, 0, 0, 0])
     assert e.value.code == -4
+    # a gate whose parameters need more than 135 wires
+    common = zp.CommonCircuitData(3, [(zp.GATE_NOOP, 0, (0, 2)), (zp.GATE_EXPONENTIATION, 0, (0, 2), (70,))], 1)
+    with pytest.raises(B200ZkpError) as e:
+        zp.compute_quotient_values_device(ctx, common, t(83), t(135), t(20), [1, 2], [3, 4], [5, 6], [0, 0, 0, 0])
+    assert e.value.code == -1
     common = zp.CommonCircuitData(3, [(zp.GATE_NOOP, 0, (0, 1))], 1)
     with pytest.raises(ValueError):
         zp.compute_quotient_values_device(ctx, common, t(83), t(135), t(19), [1, 2], [3, 4], [5, 6], [0, 0, 0, 0])

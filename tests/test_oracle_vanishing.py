@@ -12,8 +12,8 @@ from oracle import vanishing_ref as V
 P = V.P
 
 
-def build_instance(oracle, n_log, seed, rate_bits=3, degree=8):
-    c = V.Circuit(n_log, seed=seed)
+def build_instance(oracle, n_log, seed, rate_bits=3, degree=8, extended=False):
+    c = V.Circuit(n_log, seed=seed, extended=extended)
     rnd = random.Random(seed + 1)
     C = 2
     betas, gammas, alphas = ([rnd.randrange(P) for _ in range(C)] for _ in range(3))
@@ -81,6 +81,47 @@ def test_quotient_satisfies_the_verifier_identity(oracle, n_log, seed):
     # one wrong wire: the "quotient" no longer satisfies the identity
     bad = [list(col) for col in c.wires]
     bad[V.W_PARTIAL + 3][0] = (bad[V.W_PARTIAL + 3][0] + 1) % P
+    bad_coeffs = [oracle.ifft(np.array(col, np.uint64)) for col in bad]
+    bad_lde = [oracle.coset_lde(col, 3) for col in bad_coeffs]
+    qb = V.quotient_values(c, ldes["cs"], bad_lde, ldes["zpp"], betas, gammas, alphas, 8, 3, 3)
+    qbc = [coset_ifft(oracle, col) for col in qb]
+    assert not V.check_quotient_identity(c, coeffs["cs"], bad_coeffs, coeffs["zpp"], qbc, betas, gammas, alphas, 8, 12345)
+
+
+def test_other_gate_witnesses_satisfy_their_constraints():
+    """ArithmeticExtension, MulExtension, BaseSum, Reducing, ReducingExtension, RandomAccess, Exponentiation, PoseidonMds: the
+    generated row satisfies eval_unfiltered, the constraint count is Gate::num_constraints, and a changed wire breaks it"""
+    rnd = random.Random(7)
+    for g in (V.ARITHMETIC_EXTENSION, V.MUL_EXTENSION, V.BASE_SUM, V.REDUCING, V.REDUCING_EXTENSION, V.RANDOM_ACCESS,
+              V.EXPONENTIATION, V.POSEIDON_MDS):
+        pr = V.EXT_GATE_PARAMS.get(g, ())
+        cc = [rnd.randrange(P) for _ in range(2)]
+        w = V.gate_witness(g, rnd, cc, pr)
+        out = V.gate_constraints(g, w, cc, [0] * 4, pr)
+        assert len(out) == V.gate_num_constraints(g, pr) and not any(out)
+        w[0] = (w[0] + 1) % P
+        assert any(V.gate_constraints(g, w, cc, [0] * 4, pr))
+    # known values: 3^0b101 = 243 through the exponentiation gate, a base-2 sum, one quadratic-extension product
+    w = [0] * V.NUM_WIRES
+    w[0], w[1], w[3] = 3, 1, 1
+    w[2 + 3:2 + 6] = [3, 9, 243]
+    w[1 + 3] = 243
+    assert not any(V.gate_constraints(V.EXPONENTIATION, w, [0, 0], [0] * 4, (3,)))
+    assert V.ext_mul((2, 3), (5, 11)) == (2 * 5 + 7 * 3 * 11, 2 * 11 + 3 * 5)
+
+
+def test_quotient_identity_with_every_gate_kind(oracle):
+    """the same identity for a circuit that also holds rows of the other eight gate kinds (13 gates, 4 selector polynomials)"""
+    c, betas, gammas, alphas, coeffs, ldes = build_instance(oracle, 5, 11, extended=True)
+    assert c.num_selectors == 4 and len(c.gates) == 13
+    q = V.quotient_values(c, ldes["cs"], ldes["wires"], ldes["zpp"], betas, gammas, alphas, 8, 3, 3)
+    qc = [coset_ifft(oracle, col) for col in q]
+    assert V.check_quotient_identity(c, coeffs["cs"], coeffs["wires"], coeffs["zpp"], qc, betas, gammas, alphas, 8, 987654321)
+    assert V.check_quotient_identity(c, coeffs["cs"], coeffs["wires"], coeffs["zpp"], qc, betas, gammas, alphas, 8, 31337)
+    # one wrong wire on a ReducingGate row
+    row = c.row_gate.index(c.gates.index(V.REDUCING))
+    bad = [list(col) for col in c.wires]
+    bad[9][row] = (bad[9][row] + 1) % P
     bad_coeffs = [oracle.ifft(np.array(col, np.uint64)) for col in bad]
     bad_lde = [oracle.coset_lde(col, 3) for col in bad_coeffs]
     qb = V.quotient_values(c, ldes["cs"], bad_lde, ldes["zpp"], betas, gammas, alphas, 8, 3, 3)
