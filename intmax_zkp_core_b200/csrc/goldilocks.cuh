@@ -12,10 +12,12 @@
 // index logic without a GPU.  It is a test build flavour only; the product library never defines it.
 #ifdef B200ZKP_HOST_EMU
 #define GL_FN static inline
+#define GL_HD static inline
 #define GL_MFN inline
 #define GL_CONST_TABLE static const
 #else
 #define GL_FN __device__ __forceinline__
+#define GL_HD __host__ __device__ __forceinline__      /* small pure helpers the host code shares (argument checks) */
 #define GL_MFN __device__ __forceinline__
 #define GL_CONST_TABLE static __device__ __constant__
 #endif

@@ -46,7 +46,7 @@ static constexpr u32 W_IN = 0, W_OUT = 12, W_SWAP = 24, W_DELTA = 25, W_FULL0 = 
 struct GateDesc { u32 kind, selector_index, group_begin, group_end, p0, p1, p2; };
 
 // Gate::num_constraints() of standard_recursion_config instances (host and device)
-GL_FN u32 gate_num_constraints(u32 kind, u32 num_routed, u32 num_gate_consts, u32 p0, u32 p1, u32 p2) {
+GL_HD u32 gate_num_constraints(u32 kind, u32 num_routed, u32 num_gate_consts, u32 p0, u32 p1, u32 p2) {
     switch (kind) {
         case GATE_CONSTANT: return num_gate_consts;
         case GATE_PUBLIC_INPUT: return 4;
@@ -63,7 +63,7 @@ GL_FN u32 gate_num_constraints(u32 kind, u32 num_routed, u32 num_gate_consts, u3
     }
 }
 // highest wire index the gate reads + 1 (argument check on the host)
-GL_FN u32 gate_num_wires(u32 kind, u32 num_routed, u32 p0, u32 p1, u32 p2) {
+GL_HD u32 gate_num_wires(u32 kind, u32 num_routed, u32 p0, u32 p1, u32 p2) {
     switch (kind) {
         case GATE_BASE_SUM: return 1 + p1;
         case GATE_REDUCING: return 3 * D + p0 + D * (p0 ? p0 - 1 : 0);
