@@ -57,7 +57,7 @@ def bench_config(n_log, k, world):
             "cells_per_step": k << n_log,
             "l2": "no flush needed: every step streams 8nk bytes of input and 64nk of LDE (>> 126 MB L2)",
             "partition": "single GPU" if world == 1 else
-            f"one commitment over {world} GPUs: column-sharded iNTT, all-gather of the coefficient shards (fused into the first LDE pass over NVLink peer memory; NCCL point-to-point as fallback), leaf-range LDE+Merkle, all-gather cap"}
+            f"one commitment over {world} GPUs: column-sharded iNTT (columns dealt in groups of max(8, N)), all-gather of the coefficient shards (fused into the first LDE pass over NVLink peer memory; NCCL point-to-point as fallback), leaf-range LDE+Merkle, all-gather cap"}
 
 
 def algorithmic_bytes(n_log, k, r=RATE_BITS, h=CAP_HEIGHT):
@@ -208,9 +208,11 @@ def bind_to_gpu_numa_node(gpu_index):
         pass
 
 
-def synth_host(torch, np, col_begin, col_end, n, rows_alloc=None):
-    """pinned (rows_alloc, n) int64 tensor holding v[c][i] = splitmix64(c*n + i) mod p for columns [col_begin, col_end)"""
-    idx = np.arange(col_begin * n, col_end * n, dtype=np.uint64)
+def synth_host(torch, np, cols, n, rows_alloc=None):
+    """pinned (rows_alloc, n) int64 tensor holding v[c][i] = splitmix64(c*n + i) mod p for the columns `cols`"""
+    cols = np.asarray(list(cols), dtype=np.uint64)
+    col_begin, col_end = 0, int(cols.size)
+    idx = (cols[:, None] * np.uint64(n) + np.arange(n, dtype=np.uint64)[None, :]).reshape(-1)
     with np.errstate(over="ignore"):
         zed = (idx + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
         zed = (zed ^ (zed >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
@@ -296,7 +298,7 @@ def parity_sharded_small(torch, np, dist, comm, rank, world, dev):
     ref = O.commit(v, RATE_BITS, CAP_HEIGHT)
     lay = D.shard_layout(n_log, k, RATE_BITS, CAP_HEIGHT, rank, world)
     sh = D.ShardedCommitment(comm, n_log, k, RATE_BITS, CAP_HEIGHT)
-    mine = np.ascontiguousarray(v[lay["col_begin"]:lay["col_end"]])
+    mine = np.ascontiguousarray(v[lay["cols"]])
     ok = True
     for host_path in (False, True):
         t = torch.from_numpy(mine.view(np.int64)) if mine.size else None
@@ -502,7 +504,7 @@ def run_b200(args):
                       "parity_ok": parity_sharded_small(torch, np, dist, comm, rank, world, dev)}
 
     # synthetic input: v[c][i] = splitmix64(c*n + i) mod p; each rank generates only its column shard
-    host_vals = synth_host(torch, np, lay["col_begin"], lay["col_end"], n, lay["kp"] if world > 1 else k)
+    host_vals = synth_host(torch, np, lay["cols"], n, lay["kp"] if world > 1 else k)
     dev_vals = host_vals.to(dev)
 
     if world == 1:
@@ -570,7 +572,7 @@ def run_b200(args):
     else:
         def e2e_step():
             sh.run_from_host(host_vals, cap_out=cap_host)
-        h2d_bytes = 8 * n * max(lay["col_end"] - lay["col_begin"], 0)
+        h2d_bytes = 8 * n * lay["n_cols"]
     for _ in range(max(1, min(args.warmup, 2))):
         e2e_step()
     sync_all()
@@ -640,7 +642,7 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 32 << CAP_HEIGHT,
                     "api": "b200zkp_commit_from_values + b200zkp_batch_cap (pinned host buffers)" if world == 1 else
-                           "b200zkp_sharded_commit (host inputs): pinned column shard H2D in column chunks, pipelined with the inverse transforms, the gather and the coset transforms + commit + cap D2H per rank"},
+                           "b200zkp_sharded_commit (host inputs): pinned column shard H2D in column-group chunks, pipelined with the inverse transforms, the gather, the coset transforms and the leaf sponges (resumable) + tree + cap D2H per rank"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "merkle::leaf_hash_kernel", "bound": "int", "hbm": {
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
@@ -652,7 +654,7 @@ def run_b200(args):
                            "achieved_gbs": algorithmic_bytes(n_log, k) / (ms_step * 1e-3) / 1e9,
                            "frac_of_peak": algorithmic_bytes(n_log, k) / (ms_step * 1e-3) / 1e9 / (peak * world)},
             "ntt_hbm": {"lde_algorithmic_gbs": (72 * lde_cells) / (lde_ms * 1e-3) / 1e9 if lde_ms else None,
-                        "intt_algorithmic_gbs": (16 * (n * max(lay["col_end"] - lay["col_begin"], 0))) / (intt_ms * 1e-3) / 1e9 if intt_ms else None,
+                        "intt_algorithmic_gbs": (16 * (n * lay["n_cols"])) / (intt_ms * 1e-3) / 1e9 if intt_ms else None,
                         "peak": peak, "note": "SURVEY.md 8d stage bytes: LDE 72 B/cell, iNTT 16 B/cell (rank 0's share at N > 1)"},
             "stages_ms_per_step": {s: v[0] / args.steps for s, v in stages.items()},
             "poseidon_perms_per_s": perms / (ms_step * 1e-3),

@@ -314,18 +314,21 @@ int b200zkp_dev_quotient_values(b200zkp_ctx* ctx, const b200zkp_vanishing_desc* 
                                 const uint64_t* zs_partial_products, uint64_t zpp_stride, uint64_t* out_dev, uint64_t out_stride);
 
 /* ---- one commitment partitioned over several GPUs (NVLink / NVSwitch peer memory + NCCL) --------------
- * north_star's partition: rank g of G (a power of two, G <= 2^rate_bits and G <= 2^cap_height) inverse-transforms columns
- * [g*kp, (g+1)*kp), kp = ceil(k/G), into its "exchange window"; every rank then extends ALL k columns on its
- * 2^rate_bits/G coset blocks = leaves [g*N/G, (g+1)*N/G), hashes them and builds its 2^cap_height/G cap subtrees without
- * further communication; one ncclAllGather of 32 * 2^cap_height bytes hands every rank the cap.
- * The all-gather of the coefficients in between has two forms:
+ * north_star's partition: rank g of G (a power of two, G <= 2^rate_bits and G <= 2^cap_height) inverse-transforms its columns
+ * into its "exchange window"; every rank then extends ALL k columns on its 2^rate_bits/G coset blocks = leaves
+ * [g*N/G, (g+1)*N/G), hashes them and builds its 2^cap_height/G cap subtrees without further communication; one ncclAllGather
+ * of 32 * 2^cap_height bytes hands every rank the cap.
+ * Columns are dealt to the ranks in groups of L = max(8, G): rank g owns the w = L/G columns [j*L + g*w, j*L + (g+1)*w) of every
+ * group j (b200zkp_sharded_columns lists them).  A group is a whole number of sponge chunks, so with host inputs the leaves are
+ * hashed group by group while later groups are still being uploaded.
+ * The all-gather of the coefficients has two forms:
  *   peer exchange (default when every rank can map every other rank's memory: peer access inside one process, CUDA IPC
  *     between processes, at most 8 ranks): the first pass of the coset transforms reads its coefficient tiles straight from
  *     the owners' windows over NVLink and files them in the local coefficient matrix on the way (one fused kernel, no NCCL
- *     call, no staging); ordering by epoch-stamped flags in peer memory.  Host inputs are cut into column chunks whose
- *     upload, inverse transform, gather and coset transforms form a pipeline.
- *   NCCL exchange (fallback, or b200zkp_comm_set_peer_exchange(comm, 0) / B200ZKP_PEER_EXCHANGE=0): point-to-point groups of a
- *     few peers, so the coset transforms of the shards already received overlap the rest of the exchange.
+ *     call, no staging); ordering by epoch-stamped flags in peer memory (CUDA events inside one process).  Host inputs form a
+ *     pipeline of column chunks: upload / inverse transform / gather + coset transforms / sponge absorption.
+ *   NCCL exchange (fallback, or b200zkp_comm_set_peer_exchange(comm, 0) / B200ZKP_PEER_EXCHANGE=0): point-to-point groups into
+ *     a local gather buffer after the inverse transforms; the same kernels then read the shards from there.
  *
  * Two ways to form the communicator, matching how the caller is deployed:
  *   b200zkp_comm_init_all   ONE process drives n GPUs (what a single rayon `prove()` process needs; plonky2 is one process,
@@ -358,11 +361,14 @@ int b200zkp_comm_peer_exchange(const b200zkp_comm* comm);
 int b200zkp_sharded_create(b200zkp_comm* comm, uint32_t n_log, uint32_t k, uint32_t rate_bits, uint32_t cap_height,
                            b200zkp_sharded** out);
 void b200zkp_sharded_free(b200zkp_sharded* sh);
-/* partition of local rank `local`: lay = { kp, col_begin, col_end, block_begin, block_end, N_local, cap_begin, cap_end } */
+/* partition of local rank `local`: lay = { n_cols, L, w, block_begin, block_end, N_local, cap_begin, cap_end }: the rank owns
+ * n_cols columns, w of every group of L (see above); coset blocks / leaves / cap entries as ranges */
 int b200zkp_sharded_layout(const b200zkp_sharded* sh, int local, uint64_t lay[8]);
-/* PolynomialBatch::from_values / from_coeffs, partitioned.  inputs[i]: columns [col_begin, col_end) of local rank i,
- * column-major (col_end - col_begin) * n words, host memory (pinned for full PCIe speed; the upload is chunked and
- * overlaps the transforms) or, with inputs_on_device, memory of that rank's device (read on the ctx stream); the same
+/* the columns of local rank `local` in increasing order (cols may be NULL to ask for the count only) */
+int b200zkp_sharded_columns(const b200zkp_sharded* sh, int local, uint32_t* cols, uint32_t capacity, uint32_t* n_cols);
+/* PolynomialBatch::from_values / from_coeffs, partitioned.  inputs[i]: the columns of local rank i (b200zkp_sharded_columns)
+ * packed in increasing order, column-major n_cols * n words, host memory (pinned for full PCIe speed; the upload is chunked and
+ * overlaps the transforms and the hashing) or, with inputs_on_device, memory of that rank's device (read on the ctx stream); the same
  * kind of input on every rank.
  * cap_out: NULL -> the call only enqueues (results are complete after b200zkp_sharded_synchronize); else 4 * 2^cap_height
  * words of host memory, written before the call returns.  Collective: every process of the communicator calls it. */
@@ -373,7 +379,7 @@ int b200zkp_sharded_commit(b200zkp_sharded* sh, const uint64_t* const* inputs, i
 int b200zkp_sharded_commit_from_values(b200zkp_comm* comm, const uint64_t* values, uint32_t n_log, uint32_t k,
                                        uint32_t rate_bits, uint32_t cap_height, uint64_t* cap_out, b200zkp_sharded** out);
 int b200zkp_sharded_synchronize(b200zkp_sharded* sh);
-/* device views on local rank `local`: coefficients [G*kp][n] (all columns, natural column order, zero columns past k),
+/* device views on local rank `local`: coefficients [ceil(k/L)*L][n] (all columns, natural column order, zero columns past k),
  * LDE [k][N_local] (the rank's leaves, column-major), digests of its cap subtrees (plonky2 layout), the full cap */
 int b200zkp_sharded_device_ptrs(b200zkp_sharded* sh, int local, const uint64_t** coeffs, const uint64_t** lde,
                                 const uint64_t** digests, const uint64_t** cap);

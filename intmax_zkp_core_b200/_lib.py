@@ -158,6 +158,7 @@ _SIGS = {
     "b200zkp_sharded_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "b200zkp_sharded_free": (None, [C.c_void_p]),
     "b200zkp_sharded_layout": (C.c_int, [C.c_void_p, C.c_int, u64p]),
+    "b200zkp_sharded_columns": (C.c_int, [C.c_void_p, C.c_int, u32p, C.c_uint32, u32p]),
     "b200zkp_sharded_commit": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
     "b200zkp_sharded_commit_from_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
                                                    C.POINTER(C.c_void_p)]),

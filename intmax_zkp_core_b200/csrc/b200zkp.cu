@@ -408,8 +408,10 @@ static int run_ct_plan(b200zkp_ctx* ctx, ntc::Plan& plan, cudaStream_t later_str
             bool ok = ctx->ntt_tma && encode_tile_map(&tm_out, p.out, B, p.S, p.C_log, p.n_blk, p.out_blk_stride, map_cols, p.out_col_stride);
             if (ok && pull) {
                 ok = encode_tile_map(&tm_copy, p.copy_out, B, p.S, p.C_log, 1, 0, map_cols, p.copy_col_stride);
-                for (u32 q = 0; ok && q < (u32)ntc::MAX_SRC && p.src[q]; q++)
-                    ok = encode_tile_map(&tm_src.m[q], p.src[q], B, p.S, p.C_log, 1, 0, p.src_col0 + p.col_run, p.in_col_stride);
+                // a source's matrix holds col_run local columns per group of col_period columns of the commitment
+                const u32 src_cols = ((p.col_limit + p.col_period - 1) / p.col_period) * p.col_run;
+                for (u32 q = 0; ok && q < p.col_period / p.col_run; q++)
+                    ok = encode_tile_map(&tm_src.m[q], p.src[q], B, p.S, p.C_log, 1, 0, src_cols, p.in_col_stride);
             } else if (ok) {
                 ok = encode_tile_map(&tm_in, p.in, B, p.S, p.C_log, loop ? 1 : p.n_blk, loop ? 0 : p.in_blk_stride, map_cols, p.in_col_stride);
             }
@@ -698,7 +700,7 @@ static int dev_lde_locked(b200zkp_ctx* ctx, const u64* coeffs, u64 coeff_stride,
                          cs + (u64)b0 * n, n, /*inverse_scale=*/false, /*canon_in=*/true, b1 - b0, n);
 }
 
-// Coset transforms of a column set of a partitioned LDE (sharded.inl): `cols` names run x n_src columns of the local LDE;
+// Coset transforms of a column set of a partitioned LDE (sharded.inl): `cols` names cols.count columns of the local LDE;
 // with cols.pull the first pass gathers the coefficients from the sources' exchange windows (peer memory) on the way.
 // Returns B200ZKP_ERR_UNSUPPORTED (nothing launched) when the block-twiddle passes do not cover the shape.
 static int dev_lde_cols_locked(b200zkp_ctx* ctx, const ntc::ColumnSet& cols, const u64* coeffs, u64 coeff_stride, u64* lde,

@@ -220,38 +220,29 @@ static inline std::vector<u64> zfinal_host(u32 n_log, const std::vector<u64>& z,
     return f;
 }
 
-// The columns of one launch sequence of a partitioned LDE (sharded.inl): `run` columns from each of n_src sources; column i of
-// source q is physical column col0 + q * period + i of the LDE (dropped when >= limit).  pull: the first pass reads source q's
-// coefficients from column src_col0 + i of the matrix at src[q] (a peer's exchange window) and also stores them to `copy_out`.
+// The columns of one launch sequence of a partitioned LDE (sharded.inl); see PassParams.  `count` grid columns: a range of
+// physical columns from col0 (sel = 0) or the first `count` columns of source `src_rank` from group col0 / period on (sel = 1).
+// pull: the first pass reads every column from its owner's matrix src[q] (local columns src_col_stride apart) and also stores
+// it to `copy_out`.
 struct ColumnSet {
-    u32 run = 0, period = 0, col0 = 0, limit = 0, n_src = 0;
+    u32 run = 0, period = 0, col0 = 0, limit = 0, count = 0, sel = 0, src_rank = 0;
     bool pull = false;
     const u64* src[MAX_SRC] = {};
-    u32 src_col0 = 0;
     u64 src_col_stride = 0;
     u64* copy_out = nullptr;
     u64 copy_col_stride = 0;
 };
 
 // ztab / zfinal: the strided table (ztab_entries per block) and the tile-ordered last-pass table (zfinal_words per block)
-// cols (optional): see ColumnSet; `ncols` is then ignored (run * n_src grid columns) and `in` is only read when !cols->pull
+// cols (optional): see ColumnSet; `ncols` is then ignored (cols->count grid columns) and `in` is only read when !cols->pull
 static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out, u64 out_stride, u64* scratch, u32 n_log,
                              u32 ncols, u32 n_blk, u64 out_blk_stride, bool natural_out, const u64* ztab, const u64* zfinal,
                              u64 a_scale, bool use_tma, const ColumnSet* cols = nullptr) {
     if (cols) {
-        if (natural_out || cols->run == 0 || cols->n_src == 0 || cols->n_src > (u32)MAX_SRC) return false;
-        if (cols->pull && n_blk > (u32)MAX_LOOP_BLOCKS) return false;
-        // grid columns = the columns that exist: every source before the first short one is full and every source after it is
-        // empty (period >= run, sources in rank order), so they are a prefix of the (source, column) enumeration
-        ncols = 0;
-        bool short_seen = false;
-        for (u32 q = 0; q < cols->n_src; q++) {
-            const u64 first = (u64)cols->col0 + (u64)q * cols->period;
-            const u32 cnt = first >= cols->limit ? 0u : (u32)std::min<u64>(cols->run, cols->limit - first);
-            if (short_seen && cnt) return false;
-            if (cnt < cols->run) short_seen = true;
-            ncols += cnt;
-        }
+        if (natural_out || cols->run == 0 || cols->period == 0 || cols->period % cols->run || cols->count == 0) return false;
+        if (cols->pull && (n_blk > (u32)MAX_LOOP_BLOCKS || cols->period / cols->run > (u32)MAX_SRC || cols->sel)) return false;
+        if (!cols->sel && (u64)cols->col0 + cols->count > cols->limit) return false;      // (the persistent gather has no idle CTAs)
+        ncols = cols->count;
     }
     if (!covers(n_log) || ncols == 0 || n_blk == 0) return false;
     if (natural_out && (!scratch || n_blk != 1)) return false;
@@ -279,11 +270,12 @@ static inline bool make_plan(Plan* plan, const u64* in, u64 in_stride, u64* out,
         else kind = (pi == 0 && n_blk > 1 && n_blk <= (u32)MAX_LOOP_BLOCKS) ? KIND_STRIDED_LOOP : KIND_STRIDED;
         if (cols) {
             p.col_run = cols->run; p.col_period = cols->period; p.col0 = cols->col0; p.col_limit = cols->limit;
+            p.col_sel = cols->sel; p.col_src = cols->src_rank;
             if (pi == 0 && cols->pull) {
                 kind = KIND_PULL_LOOP;
-                p.in = nullptr; p.in_col_stride = cols->src_col_stride; p.src_col0 = cols->src_col0;
+                p.in = nullptr; p.in_col_stride = cols->src_col_stride;
                 p.copy_out = cols->copy_out; p.copy_col_stride = cols->copy_col_stride;
-                for (u32 q = 0; q < cols->n_src; q++) {
+                for (u32 q = 0; q < cols->period / cols->run; q++) {
                     p.src[q] = cols->src[q];
                     if ((uintptr_t)cols->src[q] & 15) p.use_tma = 0;
                 }

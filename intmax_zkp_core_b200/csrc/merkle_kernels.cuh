@@ -59,6 +59,18 @@ GL_FN void sponge_leaf(const u64* __restrict__ p, u64 col_stride, u32 leaf_len, 
     }
 }
 
+// columns [c_begin, c_end) of one leaf absorbed into the running state of its sponge (c_begin a multiple of the rate; a short
+// last chunk leaves the remaining rate words as the previous permutation left them: overwrite mode).  hash_no_pad of a leaf
+// = this over [0, leaf_len) in any number of pieces cut at multiples of the rate; the digest is words 0..3 at the end.
+GL_FN void sponge_absorb(const u64* __restrict__ p, u64 col_stride, u32 c_begin, u32 c_end, u64 (&s)[poseidon::WIDTH]) {
+    for (u32 c = c_begin; c < c_end; c += poseidon::RATE) {
+#pragma unroll
+        for (int i = 0; i < poseidon::RATE; i++)
+            if (c + i < c_end) s[i] = p[(u64)(c + i) * col_stride];
+        poseidon::permute(s);
+    }
+}
+
 #ifndef B200ZKP_HOST_EMU
 __device__ __forceinline__ void store_digest(u64* dst, const u64 (&s)[poseidon::WIDTH]) {
     ulonglong2* d = reinterpret_cast<ulonglong2*>(dst);   // digests are 32-byte aligned
@@ -82,6 +94,38 @@ leaf_hash_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride,
     } else {
         u64 subtree = row >> shape.sub_log;
         u64 m = row & (((u64)1 << shape.sub_log) - 1);
+        store_digest(digests + 4 * node_slot(shape, subtree, 0, m), s);
+    }
+}
+
+// Resumable form of leaf_hash_kernel for column-major leaves that arrive column group by column group (the partitioned
+// commitment with host inputs, sharded.inl): columns [c_begin, c_end) of every row are absorbed; between launches the 12-word
+// state of row r lives at state[w * state_stride + r] (word-major: coalesced).  c_begin == 0 starts from the zero state,
+// c_end == leaf_len (> 4: hash_or_noop hashes) writes the digest instead of the state.
+__global__ void __launch_bounds__(B200ZKP_HASH_THREADS, B200ZKP_HASH_MINBLOCKS)
+leaf_absorb_kernel(const u64* __restrict__ leaves, u64 col_stride, u32 leaf_len, u32 c_begin, u32 c_end, u64 n_rows, TreeShape shape,
+                   u64* __restrict__ state, u64 state_stride, u64* __restrict__ digests, u64* __restrict__ cap) {
+    const u64 row = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    u64 s[poseidon::WIDTH];
+    if (c_begin == 0) {
+#pragma unroll
+        for (int i = 0; i < poseidon::WIDTH; i++) s[i] = 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < poseidon::WIDTH; i++) s[i] = state[(u64)i * state_stride + row];
+    }
+    sponge_absorb(leaves + row, col_stride, c_begin, c_end, s);
+    if (c_end < leaf_len) {
+#pragma unroll
+        for (int i = 0; i < poseidon::WIDTH; i++) state[(u64)i * state_stride + row] = s[i];
+        return;
+    }
+    if (shape.sub_log == 0) {
+        store_digest(cap + 4 * row, s);
+    } else {
+        const u64 subtree = row >> shape.sub_log;
+        const u64 m = row & (((u64)1 << shape.sub_log) - 1);
         store_digest(digests + 4 * node_slot(shape, subtree, 0, m), s);
     }
 }

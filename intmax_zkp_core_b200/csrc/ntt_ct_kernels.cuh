@@ -65,24 +65,32 @@ struct PassParams {
     u64 ztab_blk_stride;      // final passes: the tile-ordered image of the last levels (see FinalSmem), block stride in words
     u64 a_scale;    // 0, or n^-1: multiplies the sum operand of the LAST level (its twiddles carry the same factor)
     u32 use_tma;
-    // column sets of a partitioned LDE (sharded.inl).  col_run = 0: grid column v is column v of in / out.  Otherwise v stands
-    // for column i = v % col_run of source q = v / col_run, which is physical column col0 + q * col_period + i of `out` (the
-    // CTA leaves when that is >= col_limit: the last source may hold fewer columns).
-    u32 col_run, col_period, col0, col_limit;
-    // pull pass (KIND_PULL_LOOP): source q's coefficients are column src_col0 + i of the matrix at src[q] (in_col_stride
-    // apart; a peer GPU's exchange window, read over NVLink), and the staged tile is also stored to column `physical` of
-    // copy_out, so that the all-gather of the coefficients happens tile by tile inside the transform
+    // column sets of a partitioned LDE (sharded.inl).  col_run = 0: grid column v is column v of in / out.  Otherwise the
+    // columns of the commitment are dealt to the ranks in groups: column c belongs to source q = (c % col_period) / col_run
+    // and is that source's local column (c / col_period) * col_run + c % col_run (col_period = col_run * number of ranks, a
+    // multiple of the sponge rate, so that every group of col_period columns can be hashed as soon as it is complete).
+    //   col_sel = 0: grid column v is physical column col0 + v (a range of the commitment's columns, all sources)
+    //   col_sel = 1: grid column v is the v-th column of source col_src only: physical col0 + (v / col_run) * col_period +
+    //                col_src * col_run + v % col_run  (coset transforms of one shard that has arrived)
+    // A CTA whose physical column is >= col_limit leaves (ragged last group).
+    u32 col_run, col_period, col0, col_limit, col_sel, col_src;
+    // pull pass (KIND_PULL_LOOP): source q's coefficients are its local columns of the matrix at src[q] (in_col_stride apart;
+    // a peer GPU's exchange window, read over NVLink), and the staged tile is also stored to the physical column of copy_out,
+    // so that the all-gather of the coefficients happens tile by tile inside the transform
     const u64* src[MAX_SRC];
-    u32 src_col0;
     u64* copy_out;
     u64 copy_col_stride;
 };
 
-// physical column of grid column v, or 0xFFFFFFFF when the CTA has nothing to do; q, i: source and column inside the source
+// physical column of grid column v, or 0xFFFFFFFF when the CTA has nothing to do; q, i: owning source and its local column
 GL_FN u32 map_column(const PassParams& p, u32 v, u32& q, u32& i) {
     if (p.col_run == 0) { q = 0; i = v; return v; }
-    q = v / p.col_run; i = v - q * p.col_run;
-    const u32 phys = p.col0 + q * p.col_period + i;
+    u32 phys;
+    if (p.col_sel) phys = p.col0 + (v / p.col_run) * p.col_period + p.col_src * p.col_run + v % p.col_run;
+    else phys = p.col0 + v;
+    const u32 in_grp = phys % p.col_period;
+    q = in_grp / p.col_run;
+    i = (phys / p.col_period) * p.col_run + in_grp % p.col_run;
     return phys < p.col_limit ? phys : 0xFFFFFFFFu;
 }
 
@@ -248,7 +256,7 @@ GL_FN void strided_body(const PassParams& p, const TMap* tm_in, const TMap* tm_o
     u32 src_q, src_i;
     const u32 col = map_column(p, LOOP ? vcol : vcol / p.n_blk, src_q, src_i);
     if (col == 0xFFFFFFFFu) return;                            // (CTA-uniform) a short last source
-    const u32 in_col = PULL ? p.src_col0 + src_i : col;
+    const u32 in_col = PULL ? src_i : col;
     const u32 blk_fixed = LOOP ? 0u : vcol % p.n_blk;
     const u32 tiles_per_a_log = p.C_log - T_log;
     const u32 a = tile_i >> tiles_per_a_log;
@@ -476,7 +484,7 @@ __device__ __forceinline__ void pull_decode(const PassParams& p, u32 bid, u32& c
     const u32 vcol = bid % p.ncols, tile_i = bid / p.ncols;
     u32 i;
     col = map_column(p, vcol, q, i);
-    in_col = p.src_col0 + i;
+    in_col = i;
     const u32 tiles_per_a_log = p.C_log - T_log;
     a = tile_i >> tiles_per_a_log;
     c0 = (tile_i & ((1u << tiles_per_a_log) - 1)) << T_log;

@@ -126,16 +126,28 @@ struct b200zkp_comm {
 };
 
 struct ShardRank {
-    u64 *coeffs_all = nullptr, *lde = nullptr, *digests = nullptr, *cap_local = nullptr, *cap = nullptr, *stage = nullptr;
-    size_t coeffs_b = 0, lde_b = 0, digests_b = 0, cap_local_b = 0, cap_b = 0, stage_b = 0;
+    u64 *coeffs_all = nullptr, *lde = nullptr, *digests = nullptr, *cap_local = nullptr, *cap = nullptr;
+    u64 *stage = nullptr;     // host inputs: upload staging, [kp][n]
+    u64 *gather = nullptr;    // NCCL exchange: the shards of every rank as received, [G][kp][n] (own shard at g * kp * n)
+    u64 *sponge = nullptr;    // host inputs: the 12-word sponge state of every local leaf between column chunks, [12][N_local]
+    size_t coeffs_b = 0, lde_b = 0, digests_b = 0, cap_local_b = 0, cap_b = 0, stage_b = 0, gather_b = 0, sponge_b = 0;
 };
 
+// Partition of the k columns over the G ranks: groups of L = max(8, G) columns (a multiple of the sponge rate, so a group can be
+// hashed as soon as it is complete), w = L / G consecutive columns of every group per rank.  Column c belongs to rank
+// (c % L) / w and is that rank's local column (c / L) * w + c % w; rank g's local column t is column (t / w) * L + g * w + t % w.
 struct b200zkp_sharded {
     b200zkp_comm* comm = nullptr;
     u32 n_log = 0, k = 0, rate_bits = 0, cap_height = 0;
-    u32 kp = 0, bpr = 0, cpr = 0, cap_height_local = 0;
+    u32 L = 0, w = 0, n_groups = 0;
+    u32 kp = 0, bpr = 0, cpr = 0, cap_height_local = 0;      // kp = n_groups * w: local columns of a rank at most
     u64 N_local = 0;
     std::vector<ShardRank> r;
+    u32 local_cols(u32 g) const {
+        const u32 full = k / L, rem = k % L;
+        return full * w + (rem > g * w ? std::min(w, rem - g * w) : 0u);
+    }
+    u32 global_col(u32 g, u32 t) const { return (t / w) * L + g * w + t % w; }
 };
 
 #define COMM_BAD(c, msg) do { (c)->err = (msg); return B200ZKP_ERR_BAD_ARG; } while (0)
@@ -563,6 +575,7 @@ static void sharded_release(b200zkp_sharded* sh) {
         ShardRank& s = sh->r[i];
         dev_release(ctx, s.coeffs_all, s.coeffs_b); dev_release(ctx, s.lde, s.lde_b); dev_release(ctx, s.digests, s.digests_b);
         dev_release(ctx, s.cap_local, s.cap_local_b); dev_release(ctx, s.cap, s.cap_b); dev_release(ctx, s.stage, s.stage_b);
+        dev_release(ctx, s.gather, s.gather_b); dev_release(ctx, s.sponge, s.sponge_b);
     }
     delete sh;
 }
@@ -581,7 +594,10 @@ extern "C" int b200zkp_sharded_create(b200zkp_comm* c, uint32_t n_log, uint32_t 
     b200zkp_sharded* sh = new (std::nothrow) b200zkp_sharded();
     if (!sh) return B200ZKP_ERR_OOM;
     sh->comm = c; sh->n_log = n_log; sh->k = k; sh->rate_bits = rate_bits; sh->cap_height = cap_height;
-    sh->kp = (k + G - 1) / G;
+    sh->L = std::max(8u, G);
+    sh->w = sh->L / G;
+    sh->n_groups = (k + sh->L - 1) / sh->L;
+    sh->kp = sh->n_groups * sh->w;
     sh->bpr = (1u << rate_bits) / G;
     sh->cpr = (1u << cap_height) / G;
     u32 g_log = 0;
@@ -594,7 +610,7 @@ extern "C" int b200zkp_sharded_create(b200zkp_comm* c, uint32_t n_log, uint32_t 
         b200zkp_ctx* ctx = c->ctx[i];
         Guard g(ctx);
         ShardRank& s = sh->r[i];
-        s.coeffs_b = (size_t)sh->kp * G * n * 8;
+        s.coeffs_b = (size_t)sh->kp * G * n * 8;             // >= k columns; the tail stays zero
         s.lde_b = (size_t)k * sh->N_local * 8;
         s.digests_b = (size_t)2 * (sh->N_local - ((u64)1 << sh->cap_height_local)) * 32;
         s.cap_local_b = (size_t)32 << sh->cap_height_local;
@@ -604,7 +620,6 @@ extern "C" int b200zkp_sharded_create(b200zkp_comm* c, uint32_t n_log, uint32_t 
         TRY(dev_alloc(ctx, s.digests_b, (void**)&s.digests));
         TRY(dev_alloc(ctx, s.cap_local_b, (void**)&s.cap_local));
         TRY(dev_alloc(ctx, s.cap_b, (void**)&s.cap));
-        // columns past k of the last shard are never written by a transform: they travel as zeros
         CUDA_TRY(ctx, cudaMemsetAsync(s.coeffs_all, 0, s.coeffs_b, ctx->stream));
         return 0;
     });
@@ -623,121 +638,22 @@ extern "C" void b200zkp_sharded_free(b200zkp_sharded* sh) {
 extern "C" int b200zkp_sharded_layout(const b200zkp_sharded* sh, int local, uint64_t lay[8]) {
     if (!sh || !lay || local < 0 || local >= sh->comm->n_local()) return B200ZKP_ERR_BAD_ARG;
     const u64 g = (u64)sh->comm->rank[local];
-    lay[0] = sh->kp;
-    lay[1] = std::min<u64>(sh->k, g * sh->kp);
-    lay[2] = std::min<u64>(sh->k, (g + 1) * sh->kp);
+    lay[0] = sh->local_cols((u32)g);
+    lay[1] = sh->L;
+    lay[2] = sh->w;
     lay[3] = g * sh->bpr; lay[4] = (g + 1) * sh->bpr;
     lay[5] = sh->N_local;
     lay[6] = g * sh->cpr; lay[7] = (g + 1) * sh->cpr;
     return 0;
 }
 
-// everything one rank does for one commit; asynchronous (returns after enqueueing).  NCCL form of the exchange.
-static int sharded_commit_rank_nccl(b200zkp_sharded* sh, int i, const u64* input, int on_device, int is_coeffs) {
-    b200zkp_comm* c = sh->comm;
-    b200zkp_ctx* ctx = c->ctx[i];
-    NcclApi& nc = nccl_api();
-    Guard guard(ctx);
-    ShardRank& s = sh->r[i];
-    const u32 G = (u32)c->world, g = (u32)c->rank[i];
-    const u64 n = (u64)1 << sh->n_log;
-    const u32 c0 = std::min(sh->k, g * sh->kp), c1 = std::min(sh->k, (g + 1) * sh->kp), kl = c1 - c0;
-    u64* mine = s.coeffs_all + (u64)g * sh->kp * n;
-    cudaStream_t main_s = ctx->stream, xs = c->xstream[i];
-    cudaEvent_t* ev = &c->ev[(size_t)i * (2 + G)];
-    if (kl && !input) BAD(ctx, "null input shard");
-
-    // ---- 1. this rank's columns -> coefficients (host input: chunked upload on the copy stream, overlapped)
-    if (kl) {
-        // scratch of the inverse transform: this rank's own columns of the (still unused) LDE shard; N_local >= n
-        u64* scratch = s.lde + (u64)c0 * sh->N_local;
-        if (on_device) {
-            if (is_coeffs) TRY(launch_canon_copy(ctx, input, mine, (u64)kl * n));
-            else TRY(dev_intt_locked(ctx, input, n, mine, n, scratch, sh->n_log, kl));
-        } else {
-            if (s.stage_b < (size_t)sh->kp * n * 8) {
-                dev_release(ctx, s.stage, s.stage_b);
-                s.stage = nullptr; s.stage_b = 0;
-                TRY(dev_alloc(ctx, (size_t)sh->kp * n * 8, (void**)&s.stage));
-                s.stage_b = (size_t)sh->kp * n * 8;
-            }
-            if (!ctx->stream2) {
-                int lo = 0, hi = 0;
-                CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-                CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
-            }
-            const u32 n_chunks = (kl >= 4 && (size_t)kl * n * 8 >= ((size_t)16 << 20)) ? 4 : 1;
-            const u32 per = (kl + n_chunks - 1) / n_chunks;
-            cudaEvent_t e_free;
-            TRY(get_sync_event(ctx, 0, &e_free));
-            CUDA_TRY(ctx, cudaEventRecord(e_free, main_s));                  // the staging buffer may still feed the previous step
-            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, e_free, 0));
-            std::vector<cudaEvent_t> up(n_chunks);
-            for (u32 q = 0; q < n_chunks; q++) {
-                u32 a = std::min(kl, q * per), b = std::min(kl, (q + 1) * per);
-                TRY(get_sync_event(ctx, 1 + q, &up[q]));
-                if (b > a) CUDA_TRY(ctx, cudaMemcpyAsync(s.stage + (u64)a * n, input + (u64)a * n, (size_t)(b - a) * n * 8, cudaMemcpyHostToDevice, ctx->stream2));
-                CUDA_TRY(ctx, cudaEventRecord(up[q], ctx->stream2));
-            }
-            for (u32 q = 0; q < n_chunks; q++) {
-                u32 a = std::min(kl, q * per), b = std::min(kl, (q + 1) * per);
-                CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, up[q], 0));
-                if (b == a) continue;
-                if (is_coeffs) TRY(launch_canon_copy(ctx, s.stage + (u64)a * n, mine + (u64)a * n, (u64)(b - a) * n));
-                else TRY(dev_intt_locked(ctx, s.stage + (u64)a * n, n, mine + (u64)a * n, n, scratch + (u64)a * sh->N_local, sh->n_log, b - a));
-            }
-        }
-    }
-
-    // ---- 2. exchange of the coefficient shards in point-to-point groups on the exchange stream, and the coset transforms
-    //         of every shard as soon as it is here (own shard first)
-    // coset transforms of the shards of ranks [src_lo, src_hi] (adjacent ranks hold adjacent columns: one launch sequence)
-    auto lde_shards = [&](u32 src_lo, u32 src_hi) -> int {
-        u32 a = std::min(sh->k, src_lo * sh->kp), b = std::min(sh->k, (src_hi + 1) * sh->kp);
-        if (b == a) return 0;
-        return dev_lde_locked(ctx, s.coeffs_all + (u64)a * n, n, s.lde + (u64)a * sh->N_local, sh->N_local, sh->n_log, b - a,
-                              sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr);
-    };
-    if (G > 1) {
-        CUDA_TRY(ctx, cudaEventRecord(ev[0], main_s));            // own coefficients ready; earlier readers of coeffs_all done
-        CUDA_TRY(ctx, cudaStreamWaitEvent(xs, ev[0], 0));
-    }
-    TRY(lde_shards(g, g));
-    if (G > 1) {
-        const u32 per_group = c->peers_per_group ? c->peers_per_group : (G - 1);
-        const size_t count = (size_t)sh->kp * n;
-        u32 gi = 0;
-        for (u32 d0 = 1; d0 < G; d0 += per_group, gi++) {
-            const u32 d1 = std::min(G, d0 + per_group);
-            NCCL_TRY(&ctx->err, nc.GroupStart());
-            for (u32 d = d0; d < d1; d++) {
-                const u32 to = (g + d) % G, from = (g + G - d) % G;
-                NCCL_TRY(&ctx->err, nc.Send(mine, count, ncclUint64, (int)to, c->nc[i], xs));
-                NCCL_TRY(&ctx->err, nc.Recv(s.coeffs_all + (u64)from * sh->kp * n, count, ncclUint64, (int)from, c->nc[i], xs));
-            }
-            NCCL_TRY(&ctx->err, nc.GroupEnd());
-            ctx->launches++;
-            CUDA_TRY(ctx, cudaEventRecord(ev[2 + gi], xs));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, ev[2 + gi], 0));
-            // sources g - d0, g - d0 - 1, ..., g - (d1 - 1) (mod G): descending ranks, split where the index wraps below 0
-            u32 hi = (g + G - d0) % G, lo = hi;
-            for (u32 d = d0 + 1; d <= d1; d++) {
-                const u32 src = (g + G - d) % G;
-                if (d < d1 && src + 1 == lo) { lo = src; continue; }
-                TRY(lde_shards(lo, hi));
-                hi = lo = src;
-            }
-        }
-    }
-
-    // ---- 3. this rank's leaves -> digests of its cap subtrees; 4. the cap
-    TRY(dev_merkle_locked(ctx, s.lde, /*row_stride=*/1, /*col_stride=*/sh->N_local, sh->k, sh->N_local, sh->cap_height_local,
-                          s.digests, s.cap_local));
-    if (G > 1) {
-        NCCL_TRY(&ctx->err, nc.AllGather(s.cap_local, s.cap, s.cap_local_b / 8, ncclUint64, c->nc[i], main_s));
-        ctx->launches++;
-    } else {
-        CUDA_TRY(ctx, cudaMemcpyAsync(s.cap, s.cap_local, s.cap_b, cudaMemcpyDeviceToDevice, main_s));
+extern "C" int b200zkp_sharded_columns(const b200zkp_sharded* sh, int local, uint32_t* cols, uint32_t capacity, uint32_t* n_cols) {
+    if (!sh || !n_cols || local < 0 || local >= sh->comm->n_local()) return B200ZKP_ERR_BAD_ARG;
+    const u32 g = (u32)sh->comm->rank[local], cnt = sh->local_cols(g);
+    *n_cols = cnt;
+    if (cols) {
+        if (capacity < cnt) return B200ZKP_ERR_BAD_ARG;
+        for (u32 t = 0; t < cnt; t++) cols[t] = sh->global_col(g, t);
     }
     return 0;
 }
@@ -785,53 +701,85 @@ static int peer_publish_done(b200zkp_comm* c, int i, u32 epoch) {
     return 0;
 }
 
-// Peer-memory form of the same commit (the default inside one NVLink domain).  The rank's columns are cut into the same
-// chunks on every rank; per chunk:  [upload ->] inverse transform into the rank's exchange window -> "ready" flag to every
-// peer -> wait for every peer's flag -> ONE launch sequence of coset transforms over that chunk's columns of ALL ranks, whose
-// first pass reads the coefficient tiles straight from the peers' windows over NVLink and also files them in the local
-// coefficient matrix (ntc::ct_pull_kernel).  With host inputs the upload of chunk j + 1 runs under the transforms of chunk j,
-// so only the leaf hashing waits for the last byte.
-static int sharded_commit_rank_peer(b200zkp_sharded* sh, int i, const u64* input, int on_device, int is_coeffs, u32 epoch) {
+// where this rank's input columns live: packed (local column t at base + t * n) or, for the one-call form on the whole
+// matrix, at their place in the k x n matrix (local column t = column global_col(g, t))
+struct ShardInput { const u64* base; bool full_matrix; };
+
+static int ensure_buffer(b200zkp_ctx* ctx, u64** buf, size_t* have, size_t want) {
+    if (*have >= want) return 0;
+    dev_release(ctx, *buf, *have);
+    *buf = nullptr; *have = 0;
+    TRY(dev_alloc(ctx, want, (void**)buf));
+    *have = want;
+    return 0;
+}
+
+// Everything one rank does for one commit; asynchronous (returns after enqueueing).
+//
+// The rank's columns are cut into the same chunks (whole column groups) on every rank; per chunk:
+//   [upload ->] inverse transform into the rank's shard buffer -> (peer form) "ready" flag to every peer, wait for every
+//   peer's flag -> gather + coset transforms of the chunk's columns of ALL ranks [-> absorb them into the leaf sponges].
+// Peer form (the default inside one NVLink domain): the shard buffer is the rank's exchange window and the gather happens
+// inside the first pass of the coset transforms, which reads the coefficient tiles straight from the owners' windows over NVLink
+// and files them in the local coefficient matrix on the way (ntc::ct_pull_kernel).  With host inputs the upload of chunk j + 1
+// runs under the transforms and the hashing of chunk j (resumable sponge), so only the first chunk's upload is exposed.
+// NCCL form (fallback): the shards travel by ncclSend / ncclRecv into a local gather buffer after the last inverse transform,
+// and the same kernels then read them from there.
+static int sharded_commit_rank(b200zkp_sharded* sh, int i, ShardInput in, int on_device, int is_coeffs, bool peer, u32 epoch) {
     b200zkp_comm* c = sh->comm;
     b200zkp_ctx* ctx = c->ctx[i];
     NcclApi& nc = nccl_api();
     Guard guard(ctx);
     ShardRank& s = sh->r[i];
-    PeerRank& pr = c->pr[i];
     const u32 G = (u32)c->world, g = (u32)c->rank[i];
     const u64 n = (u64)1 << sh->n_log;
-    const u32 kp = sh->kp;
-    const u32 c0 = std::min(sh->k, g * kp), c1 = std::min(sh->k, (g + 1) * kp), kl = c1 - c0;
-    cudaStream_t main_s = ctx->stream;
-    if (kl && !input) BAD(ctx, "null input shard");
-    if (!pr.win || pr.win_b < (size_t)kp * n * 8 || pr.peer_win.size() != G) BAD(ctx, "internal: exchange window missing");
-    // the gather inside the first pass wants tile rows of 128 bytes and more (first passes of <= 7 bits) unless the upload of
-    // host inputs hides the transfer anyway
-    const bool fused = ctx->ntt_ct && ntc::covers(sh->n_log) && sh->bpr <= (u32)ntc::MAX_LOOP_BLOCKS &&
-                       (!on_device || ntc::first_pass_bits(sh->n_log) <= 7 || getenv("B200ZKP_PEER_FUSED_ALWAYS"));
+    const u32 L = sh->L, w = sh->w, kp = sh->kp, k = sh->k, kl = sh->local_cols(g);
+    cudaStream_t main_s = ctx->stream, side_s = c->xstream[i];
+    if (kl && !in.base) BAD(ctx, "null input shard");
+    if (on_device && in.full_matrix) BAD(ctx, "internal: device inputs are packed shards");
+
+    // ---- the rank's shard buffer and where the shards of the others are read from
+    u64* own_out = nullptr;
+    const u64* src[ntc::MAX_SRC] = {};
+    const bool few = G <= (u32)ntc::MAX_SRC;
+    if (peer) {
+        PeerRank& pr = c->pr[i];
+        if (!few || !pr.win || pr.win_b < (size_t)kp * n * 8 || pr.peer_win.size() != G) BAD(ctx, "internal: exchange window missing");
+        own_out = pr.win;
+        for (u32 q = 0; q < G; q++) src[q] = pr.peer_win[q];
+    } else {
+        TRY(ensure_buffer(ctx, &s.gather, &s.gather_b, (size_t)G * kp * n * 8));
+        own_out = s.gather + (u64)g * kp * n;
+        if (few) for (u32 q = 0; q < G; q++) src[q] = s.gather + (u64)q * kp * n;
+    }
+    const bool covered = ctx->ntt_ct && ntc::covers(sh->n_log);
+    // the gather inside the first pass wants tile rows of 128 bytes and more over NVLink (first passes of <= 7 bits) unless the
+    // upload of host inputs hides the transfer anyway; from the local gather buffer it always pays
+    const bool fused = covered && few && sh->bpr <= (u32)ntc::MAX_LOOP_BLOCKS &&
+                       (!peer || !on_device || ntc::first_pass_bits(sh->n_log) <= 7 || getenv("B200ZKP_PEER_FUSED_ALWAYS"));
     // tables first: their builders synchronise the stream, and nothing of this commit may be waiting on a peer by then
-    if (ctx->ntt_ct && ntc::covers(sh->n_log)) {
+    if (covered) {
         b200zkp_ctx::ZTables z;
         TRY(get_ztab_lde(ctx, sh->n_log, sh->rate_bits, &z));
         if (!is_coeffs) TRY(get_ztab_inv(ctx, sh->n_log, &z));
     }
-    // chunks of the rank-local column range [0, kp): the same cut on every rank (host inputs: >= 16 MB per upload)
-    u32 C = 1;
+
+    // ---- chunks of whole column groups: the same cut on every rank (host inputs: >= chunk_bytes per upload)
+    u32 m = sh->n_groups;
     if (!on_device) {
-        const u32 cols_per = (u32)std::max<u64>(1, (c->chunk_bytes + n * 8 - 1) / (n * 8));
-        C = std::max(1u, std::min((u32)peer::MAX_CHUNKS, (kp + cols_per - 1) / cols_per));
+        m = (u32)std::max<u64>(1, (c->chunk_bytes + (u64)w * n * 8 - 1) / ((u64)w * n * 8));
+        while ((sh->n_groups + m - 1) / m > peer::MAX_CHUNKS) m++;
     }
-    const u32 per = (kp + C - 1) / C;
-    C = (kp + per - 1) / per;
+    const u32 C = (sh->n_groups + m - 1) / m;
+    merkle::TreeShape shape;
+    TRY(merkle_shape(ctx, sh->N_local, sh->cap_height_local, s.lde, s.digests, s.cap_local, &shape));
+    // host inputs in the peer form: the leaves are hashed chunk by chunk as their columns arrive
+    const bool resumable = peer && !on_device && C > 1 && k > 4 && sh->N_local > COOP_MAX_NODES && !getenv("B200ZKP_NO_RESUMABLE_SPONGE");
+    if (resumable) TRY(ensure_buffer(ctx, &s.sponge, &s.sponge_b, (size_t)poseidon::WIDTH * sh->N_local * 8));
 
     std::vector<cudaEvent_t> up(C, nullptr);
     if (!on_device && kl) {
-        if (s.stage_b < (size_t)kp * n * 8) {
-            dev_release(ctx, s.stage, s.stage_b);
-            s.stage = nullptr; s.stage_b = 0;
-            TRY(dev_alloc(ctx, (size_t)kp * n * 8, (void**)&s.stage));
-            s.stage_b = (size_t)kp * n * 8;
-        }
+        TRY(ensure_buffer(ctx, &s.stage, &s.stage_b, (size_t)kp * n * 8));
         if (!ctx->stream2) {
             int lo = 0, hi = 0;
             CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -842,85 +790,169 @@ static int sharded_commit_rank_peer(b200zkp_sharded* sh, int i, const u64* input
         CUDA_TRY(ctx, cudaEventRecord(e_free, main_s));                  // the staging buffer may still feed the previous step
         CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, e_free, 0));
         for (u32 j = 0; j < C; j++) {
-            const u32 a = std::min(kl, j * per), b = std::min(kl, (j + 1) * per);
+            const u32 t0 = std::min(kl, j * m * w), t1 = std::min(kl, (j + 1) * m * w);
             TRY(get_sync_event(ctx, 1 + j, &up[j]));
-            if (b > a) CUDA_TRY(ctx, cudaMemcpyAsync(s.stage + (u64)a * n, input + (u64)a * n, (size_t)(b - a) * n * 8, cudaMemcpyHostToDevice, ctx->stream2));
+            if (t1 > t0 && !in.full_matrix)
+                CUDA_TRY(ctx, cudaMemcpyAsync(s.stage + (u64)t0 * n, in.base + (u64)t0 * n, (size_t)(t1 - t0) * n * 8, cudaMemcpyHostToDevice, ctx->stream2));
+            if (t1 > t0 && in.full_matrix)
+                for (u32 t = t0; t < t1; t += w) {       // the w local columns of a group are neighbours in the matrix
+                    const u32 cnt = std::min(w, t1 - t);
+                    CUDA_TRY(ctx, cudaMemcpyAsync(s.stage + (u64)t * n, in.base + (u64)sh->global_col(g, t) * n, (size_t)cnt * n * 8, cudaMemcpyHostToDevice, ctx->stream2));
+                }
             CUDA_TRY(ctx, cudaEventRecord(up[j], ctx->stream2));
         }
     }
-    const u64* src = on_device ? input : s.stage;
-    u64* scratch = s.lde + (u64)c0 * sh->N_local;         // the rank's own columns of the LDE shard, not written before their chunk
-    cudaStream_t side_s = c->xstream[i];
-    u32 n_side = 0, n_copy = 0;
+    const u64* in_cols = on_device ? in.base : s.stage;
+    u32 n_ev = 0;
+    bool side_used = false;
     std::unique_ptr<StageTimer> lde_timer;                // device inputs: gather + coset transforms as one span of the main stream
-    // the window is free again once every peer has read the previous commit out of it
-    TRY(peer_wait_window_free(c, i, epoch));
-    for (u32 j = 0; j < C; j++) {
-        const u32 a = std::min(kp, j * per), b = std::min(kp, (j + 1) * per);
-        const u32 am = std::min(kl, a), bm = std::min(kl, b);
-        if (bm > am) {
-            if (!on_device) CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, up[j], 0));
-            if (is_coeffs) TRY(launch_canon_copy(ctx, src + (u64)am * n, pr.win + (u64)am * n, (u64)(bm - am) * n));
-            else TRY(dev_intt_locked(ctx, src + (u64)am * n, n, pr.win + (u64)am * n, n, scratch + (u64)am * sh->N_local, sh->n_log, bm - am));
-        }
-        TRY(peer_publish_and_wait_chunk(c, i, j, epoch));
+    auto next_event = [&](cudaEvent_t* e) -> int { return get_sync_event(ctx, 24 + (n_ev++ & 63), e); };
+    auto join_side = [&]() -> int {
+        if (!side_used) return 0;
+        cudaEvent_t e_join;
+        TRY(next_event(&e_join));
+        CUDA_TRY(ctx, cudaEventRecord(e_join, side_s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, e_join, 0));
+        side_used = false;
+        return 0;
+    };
+
+    // gather + coset transforms of the columns [pa, pb) (pa a multiple of L) of every rank, read from src[]
+    auto gather_lde = [&](u32 pa, u32 pb, bool split) -> int {
+        const u32 b0 = g * sh->bpr, b1 = (g + 1) * sh->bpr;
+        const u32 grp0 = pa / L, grp1 = (pb + L - 1) / L;
         if (fused) {
-            // device inputs arrive as one chunk: cut it into column groups, so that the gather pass of group t + 1 (NVLink
-            // bound, launched two CTAs per SM wide) runs beside the in-place passes of group t on the side stream
-            const u32 n_grp = on_device ? std::min(c->pull_groups, std::max(1u, (b - a) / 2)) : 1u;
-            const u32 gw = (b - a + n_grp - 1) / n_grp;
-            for (u32 ga = a; ga < b; ga += gw) {
-                const u32 gb = std::min(b, ga + gw);
+            // device inputs arrive as one chunk: cut it into column ranges, so that the gather pass of range t + 1 (NVLink
+            // bound, launched two CTAs per SM wide) runs beside the in-place passes of range t on the side stream
+            const u32 n_rng = split ? std::min(c->pull_groups, std::max(1u, (pb - pa) / 16)) : 1u;
+            const u32 rw = (pb - pa + n_rng - 1) / n_rng;
+            for (u32 ra = pa; ra < pb; ra += rw) {
+                const u32 rb = std::min(pb, ra + rw);
                 ntc::ColumnSet cs;
-                cs.run = gb - ga; cs.period = kp; cs.col0 = ga; cs.limit = sh->k; cs.n_src = G; cs.pull = true;
-                for (u32 q = 0; q < G; q++) cs.src[q] = pr.peer_win[q];
-                cs.src_col0 = ga; cs.src_col_stride = n; cs.copy_out = s.coeffs_all; cs.copy_col_stride = n;
+                cs.run = w; cs.period = L; cs.col0 = ra; cs.limit = k; cs.count = rb - ra; cs.sel = 0; cs.pull = true;
+                for (u32 q = 0; q < G; q++) cs.src[q] = src[q];
+                cs.src_col_stride = n; cs.copy_out = s.coeffs_all; cs.copy_col_stride = n;
                 cudaEvent_t e_first;
-                TRY(get_sync_event(ctx, 24 + (n_side++ & 31), &e_first));
+                TRY(next_event(&e_first));
                 if (!lde_timer && on_device) lde_timer.reset(new StageTimer(ctx, B200ZKP_STAGE_LDE));
-                int rc = dev_lde_cols_locked(ctx, cs, nullptr, n, s.lde, sh->N_local, sh->n_log, sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr,
-                                             side_s, e_first, /*pull_ctas_per_sm=*/2);
-                if (rc == B200ZKP_ERR_UNSUPPORTED) BAD(ctx, "internal: pull transform refused a covered shape");
+                int rc = dev_lde_cols_locked(ctx, cs, nullptr, n, s.lde, sh->N_local, sh->n_log, sh->rate_bits, b0, b1, side_s, e_first, /*pull_ctas_per_sm=*/2);
+                if (rc == B200ZKP_ERR_UNSUPPORTED) BAD(ctx, "internal: gather transform refused a covered shape");
                 TRY(rc);
+                side_used = true;
             }
-        } else {
-            // shapes the gather pass does not serve well (one-pass transforms, wide blow-ups, and first passes of 8 bits, whose
-            // tiles are rows of 64 bytes — too short for NVLink — when nothing else hides the transfer): the copy engine pulls
-            // shard after shard from the peers' windows on the side stream, own shard first, and the coset transforms of a
-            // shard run on the main stream while the next one is in flight
+            return 0;
+        }
+        // copies of rank q's columns of the range into the coefficient matrix: one run of <= w columns per group
+        auto copy_shard = [&](u32 q, cudaStream_t st) -> int {
+            if (!few && !peer) return 0;      // (more ranks than sources: see below)
+            for (u32 grp = grp0; grp < grp1; grp++) {
+                const u32 first = grp * L + q * w;
+                if (first >= k) break;
+                const u32 cnt = std::min(w, k - first);
+                CUDA_TRY(ctx, cudaMemcpyAsync(s.coeffs_all + (u64)first * n, src[q] + (u64)grp * w * n, (size_t)cnt * n * 8, cudaMemcpyDefault, st));
+            }
+            return 0;
+        };
+        if (covered && few && sh->bpr <= (u32)ntc::MAX_LOOP_BLOCKS) {
+            // first passes of 8 bits (tile rows of 64 bytes are too short for NVLink) with nothing to hide the transfer: the copy
+            // engine pulls shard after shard on the side stream, own shard first, and the coset transforms of a shard run on
+            // the main stream while the next one is in flight
             cudaEvent_t e_ready;
-            TRY(get_sync_event(ctx, 22, &e_ready));
+            TRY(next_event(&e_ready));
             CUDA_TRY(ctx, cudaEventRecord(e_ready, main_s));
             CUDA_TRY(ctx, cudaStreamWaitEvent(side_s, e_ready, 0));
             for (u32 d = 0; d < G; d++) {
                 const u32 q = (g + d) % G;
-                const u32 ca = std::min(sh->k, q * kp + a), cb = std::min(sh->k, q * kp + b);
-                if (cb == ca) continue;
+                const u32 cnt = std::min(sh->local_cols(q), grp1 * w) - std::min(sh->local_cols(q), grp0 * w);
+                if (!cnt) continue;
                 cudaEvent_t e_here;
-                TRY(get_sync_event(ctx, 24 + (n_copy++ & 31), &e_here));
-                CUDA_TRY(ctx, cudaMemcpyAsync(s.coeffs_all + (u64)ca * n, pr.peer_win[q] + (u64)a * n, (size_t)(cb - ca) * n * 8, cudaMemcpyDefault, side_s));
+                TRY(next_event(&e_here));
+                TRY(copy_shard(q, side_s));
                 CUDA_TRY(ctx, cudaEventRecord(e_here, side_s));
                 CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, e_here, 0));
-                TRY(dev_lde_locked(ctx, s.coeffs_all + (u64)ca * n, n, s.lde + (u64)ca * sh->N_local, sh->N_local, sh->n_log, cb - ca,
-                                   sh->rate_bits, g * sh->bpr, (g + 1) * sh->bpr));
+                ntc::ColumnSet cs;
+                cs.run = w; cs.period = L; cs.col0 = pa; cs.limit = k; cs.count = (grp1 - grp0) * w; cs.sel = 1; cs.src_rank = q; cs.pull = false;
+                int rc = dev_lde_cols_locked(ctx, cs, s.coeffs_all, n, s.lde, sh->N_local, sh->n_log, sh->rate_bits, b0, b1);
+                if (rc == B200ZKP_ERR_UNSUPPORTED) BAD(ctx, "internal: shard transform refused a covered shape");
+                TRY(rc);
+            }
+            return 0;
+        }
+        // one-pass transforms and wide blow-ups: plain copies, then the transforms of the whole range
+        for (u32 q = 0; q < G; q++) {
+            if (few || peer) { TRY(copy_shard(q, main_s)); continue; }
+            for (u32 grp = grp0; grp < grp1; grp++) {          // (NCCL form with more ranks than gather sources)
+                const u32 first = grp * L + q * w;
+                if (first >= k) break;
+                CUDA_TRY(ctx, cudaMemcpyAsync(s.coeffs_all + (u64)first * n, s.gather + ((u64)q * kp + (u64)grp * w) * n,
+                                              (size_t)std::min(w, k - first) * n * 8, cudaMemcpyDeviceToDevice, main_s));
             }
         }
-    }
-    if (n_side) {
-        // the in-place passes on the side stream join the main stream before the leaves are hashed
-        cudaEvent_t e_join;
-        TRY(get_sync_event(ctx, 23, &e_join));
-        CUDA_TRY(ctx, cudaEventRecord(e_join, side_s));
-        CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, e_join, 0));
-    }
-    lde_timer.reset();
-    // every window has been read by this rank
-    TRY(peer_publish_done(c, i, epoch));
+        return dev_lde_locked(ctx, s.coeffs_all + (u64)pa * n, n, s.lde + (u64)pa * sh->N_local, sh->N_local, sh->n_log, pb - pa,
+                              sh->rate_bits, b0, b1);
+    };
 
-    TRY(dev_merkle_locked(ctx, s.lde, /*row_stride=*/1, /*col_stride=*/sh->N_local, sh->k, sh->N_local, sh->cap_height_local,
-                          s.digests, s.cap_local));
-    NCCL_TRY(&ctx->err, nc.AllGather(s.cap_local, s.cap, s.cap_local_b / 8, ncclUint64, c->nc[i], main_s));
-    ctx->launches++;
+    // ---- the chunks
+    if (peer) TRY(peer_wait_window_free(c, i, epoch));   // every peer has read the previous commit out of the window
+    for (u32 j = 0; j < C; j++) {
+        const u32 grp0 = j * m, grp1 = std::min(sh->n_groups, (j + 1) * m);
+        const u32 t0 = std::min(kl, grp0 * w), t1 = std::min(kl, grp1 * w);
+        const u32 pa = grp0 * L, pb = std::min(k, grp1 * L);
+        if (t1 > t0) {
+            if (!on_device) CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, up[j], 0));
+            // scratch of the inverse transform: LDE columns of this very chunk, not written before its coset transforms
+            if (is_coeffs) TRY(launch_canon_copy(ctx, in_cols + (u64)t0 * n, own_out + (u64)t0 * n, (u64)(t1 - t0) * n));
+            else TRY(dev_intt_locked(ctx, in_cols + (u64)t0 * n, n, own_out + (u64)t0 * n, n, s.lde + (u64)pa * sh->N_local, sh->n_log, t1 - t0));
+        }
+        if (!peer) continue;
+        TRY(peer_publish_and_wait_chunk(c, i, j, epoch));
+        TRY(gather_lde(pa, pb, /*split=*/on_device != 0));
+        if (resumable) {
+            TRY(join_side());
+            StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
+            const unsigned threads = hash_block_threads(sh->N_local);
+            merkle::leaf_absorb_kernel<<<(unsigned)((sh->N_local + threads - 1) / threads), threads, 0, main_s>>>(
+                s.lde, sh->N_local, k, pa, pb, sh->N_local, shape, s.sponge, sh->N_local, s.digests, s.cap_local);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    if (peer) {
+        TRY(peer_publish_done(c, i, epoch));             // every window has been read by this rank
+    } else {
+        // NCCL form: the shards travel in point-to-point groups on the exchange stream, then everything is local
+        cudaEvent_t* ev = &c->ev[(size_t)i * (2 + G)];
+        CUDA_TRY(ctx, cudaEventRecord(ev[0], main_s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(side_s, ev[0], 0));
+        const u32 per_group = c->peers_per_group ? c->peers_per_group : (G - 1);
+        const size_t count = (size_t)kp * n;
+        for (u32 d0 = 1; d0 < G; d0 += per_group) {
+            const u32 d1 = std::min(G, d0 + per_group);
+            NCCL_TRY(&ctx->err, nc.GroupStart());
+            for (u32 d = d0; d < d1; d++) {
+                const u32 to = (g + d) % G, from = (g + G - d) % G;
+                NCCL_TRY(&ctx->err, nc.Send(own_out, count, ncclUint64, (int)to, c->nc[i], side_s));
+                NCCL_TRY(&ctx->err, nc.Recv(s.gather + (u64)from * kp * n, count, ncclUint64, (int)from, c->nc[i], side_s));
+            }
+            NCCL_TRY(&ctx->err, nc.GroupEnd());
+            ctx->launches++;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ev[1], side_s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, ev[1], 0));
+        TRY(gather_lde(0, k, /*split=*/true));
+    }
+    TRY(join_side());
+    lde_timer.reset();
+
+    // ---- the rank's leaves -> digests of its cap subtrees; the cap
+    if (resumable) TRY(launch_tree_levels(ctx, sh->N_local, shape, s.digests, s.cap_local));
+    else TRY(dev_merkle_locked(ctx, s.lde, /*row_stride=*/1, /*col_stride=*/sh->N_local, k, sh->N_local, sh->cap_height_local,
+                               s.digests, s.cap_local));
+    if (G > 1) {
+        NCCL_TRY(&ctx->err, nc.AllGather(s.cap_local, s.cap, s.cap_local_b / 8, ncclUint64, c->nc[i], main_s));
+        ctx->launches++;
+    } else {
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.cap, s.cap_local, s.cap_b, cudaMemcpyDeviceToDevice, main_s));
+    }
     return 0;
 }
 
@@ -935,26 +967,23 @@ static int peer_check_error(b200zkp_comm* c, int i) {
     return 0;
 }
 
-static int sharded_commit_locked(b200zkp_sharded* sh, const u64* const* inputs, int on_device, int is_coeffs, u64* cap_out) {
+static int sharded_commit_locked(b200zkp_sharded* sh, const u64* const* inputs, bool full_matrix, int on_device, int is_coeffs, u64* cap_out) {
     b200zkp_comm* c = sh->comm;
     if (!inputs) COMM_BAD(c, "null inputs");
-    const bool use_peer = c->peer_exchange() && c->world > 1;
+    bool use_peer = c->peer_exchange() && c->world > 1 && c->world <= (int)ntc::MAX_SRC;
     if (use_peer) {
         TRY(comm_ensure_window(c, (size_t)sh->kp * ((size_t)8 << sh->n_log)));        // (a no-op unless the exchange was switched on after create)
+        use_peer = c->peer_exchange();
     }
-    if (use_peer && c->peer_exchange()) {
-        const u32 epoch = ++c->epoch;
-        c->hb.reset(c->n_local());
-        int rc = for_each_rank(c, [&](int i) -> int {
-            const int r = sharded_commit_rank_peer(sh, i, inputs[i], on_device, is_coeffs, epoch);
-            if (r) c->hb.abort();          // the other rank threads must not wait for this one
-            return r;
-        });
-        if (c->one_process()) c->done_valid = rc == 0;
-        TRY(rc);
-    } else {
-        TRY(for_each_rank(c, [&](int i) -> int { return sharded_commit_rank_nccl(sh, i, inputs[i], on_device, is_coeffs); }));
-    }
+    const u32 epoch = use_peer ? ++c->epoch : 0;
+    c->hb.reset(c->n_local());
+    int rc = for_each_rank(c, [&](int i) -> int {
+        const int r = sharded_commit_rank(sh, i, ShardInput{inputs[i], full_matrix}, on_device, is_coeffs, use_peer, epoch);
+        if (r) c->hb.abort();          // the other rank threads must not wait for this one
+        return r;
+    });
+    if (use_peer && c->one_process()) c->done_valid = rc == 0;
+    TRY(rc);
     if (cap_out) {
         TRY(for_each_rank(c, [&](int i) -> int {
             b200zkp_ctx* ctx = c->ctx[i];
@@ -971,7 +1000,7 @@ extern "C" int b200zkp_sharded_commit(b200zkp_sharded* sh, const uint64_t* const
                                       uint64_t* cap_out) {
     if (!sh) return B200ZKP_ERR_BAD_ARG;
     std::lock_guard<std::mutex> lk(sh->comm->mu);
-    return sharded_commit_locked(sh, (const u64* const*)inputs, inputs_on_device, is_coeffs, (u64*)cap_out);
+    return sharded_commit_locked(sh, (const u64* const*)inputs, /*full_matrix=*/false, inputs_on_device, is_coeffs, (u64*)cap_out);
 }
 
 extern "C" int b200zkp_sharded_commit_from_values(b200zkp_comm* c, const uint64_t* values, uint32_t n_log, uint32_t k,
@@ -983,10 +1012,9 @@ extern "C" int b200zkp_sharded_commit_from_values(b200zkp_comm* c, const uint64_
     b200zkp_sharded* sh = nullptr;
     TRY(b200zkp_sharded_create(c, n_log, k, rate_bits, cap_height, &sh));
     std::lock_guard<std::mutex> lk(c->mu);
-    const u64 n = (u64)1 << n_log;
-    std::vector<const u64*> in(c->n_local());
-    for (int i = 0; i < c->n_local(); i++) in[i] = (const u64*)values + std::min<u64>(k, (u64)c->rank[i] * sh->kp) * n;
-    int rc = sharded_commit_locked(sh, in.data(), /*on_device=*/0, /*is_coeffs=*/0, (u64*)cap_out);
+    // every local rank picks its columns out of the one matrix
+    std::vector<const u64*> in(c->n_local(), (const u64*)values);
+    int rc = sharded_commit_locked(sh, in.data(), /*full_matrix=*/true, /*on_device=*/0, /*is_coeffs=*/0, (u64*)cap_out);
     if (!rc && !cap_out)   // the caller's host matrix must stay valid only for the duration of this call
         rc = for_each_rank(c, [&](int i) -> int { Guard g(c->ctx[i]); CUDA_TRY(c->ctx[i], cudaStreamSynchronize(c->ctx[i]->stream)); return 0; });
     if (rc) { sharded_release(sh); return rc; }

@@ -45,17 +45,23 @@ def torch_context(device_index: int) -> Context:
 
 def shard_layout(n_log: int, k: int, rate_bits: int, cap_height: int, rank: int, world: int) -> dict:
     """Pure partition arithmetic of the multi-GPU commitment (no torch, no device): which columns rank
-    `rank` inverse-transforms, which coset blocks / leaf range / cap entries it owns."""
+    `rank` inverse-transforms, which coset blocks / leaf range / cap entries it owns.
+    Columns are dealt in groups of L = max(8, world) — a whole number of sponge chunks, so a group can be hashed as soon as it is
+    complete — w = L / world consecutive columns of every group per rank: `cols` lists the rank's columns in increasing order,
+    and that is the order of the rows of the shard it hands to ShardedCommitment.run / run_from_host."""
     if world <= 0 or world & (world - 1) or world > (1 << rate_bits) or world > (1 << cap_height):
         raise ValueError("world size must be a power of two <= 2^rate_bits and <= 2^cap_height")
     if not 0 <= rank < world:
         raise ValueError("rank out of range")
     N = 1 << (n_log + rate_bits)
-    kp = (k + world - 1) // world
+    L = max(8, world)
+    w = L // world
+    kp = -(-k // L) * w
+    cols = [c for c in range(k) if (c % L) // w == rank]
     bpr = (1 << rate_bits) // world
     cpr = (1 << cap_height) // world
     return dict(
-        kp=kp, col_begin=min(k, rank * kp), col_end=min(k, (rank + 1) * kp),
+        kp=kp, group=L, per_group=w, cols=cols, n_cols=len(cols),
         block_begin=rank * bpr, block_end=(rank + 1) * bpr,
         N_local=N // world, leaf_begin=rank * (N // world), leaf_end=(rank + 1) * (N // world),
         cap_height_local=cap_height - log2_strict(world), cap_begin=rank * cpr, cap_end=(rank + 1) * cpr,
@@ -213,7 +219,7 @@ class ShardedCommitment:
             raise ValueError("one input per local rank")
         n = 1 << self.n_log
         for t, lay in zip(tensors, self.layouts):
-            kl = lay["col_end"] - lay["col_begin"]
+            kl = lay["n_cols"]
             if t is None:
                 if kl:
                     raise ValueError("missing input shard")

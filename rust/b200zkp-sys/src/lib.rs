@@ -108,6 +108,7 @@ extern "C" {
         out: *mut *mut b200zkp_sharded) -> c_int;
     pub fn b200zkp_sharded_free(sh: *mut b200zkp_sharded);
     pub fn b200zkp_sharded_layout(sh: *const b200zkp_sharded, local: c_int, lay: *mut u64) -> c_int;
+    pub fn b200zkp_sharded_columns(sh: *const b200zkp_sharded, local: c_int, cols: *mut u32, capacity: u32, n_cols: *mut u32) -> c_int;
     pub fn b200zkp_sharded_commit(sh: *mut b200zkp_sharded, inputs: *const *const u64, inputs_on_device: c_int, is_coeffs: c_int,
         cap_out: *mut u64) -> c_int;
     pub fn b200zkp_sharded_commit_from_values(comm: *mut b200zkp_comm, values: *const u64, n_log: u32, k: u32, rate_bits: u32,

@@ -143,11 +143,12 @@ int emu_ct_lde(const u64* coeffs, u64* lde, u32 n_log, u32 k, u32 rate_bits, u32
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
     return 1;
 }
-// partitioned LDE (sharded.inl): columns [ca, cb) of each of n_src sources (source q's coefficients: src[q], [kp][n]; its column i
-// is column q * kp + i of the commitment, dropped when >= k) gathered into coeffs_copy [k][n] and transformed for coset blocks
-// [b0, b1) into lde [k][(b1 - b0) * n]; pull = 0: the same column set read from coeffs_copy (already gathered)
-int emu_ct_lde_cols(const u64* const* src, u32 n_src, u32 kp, u32 k, u32 ca, u32 cb, int pull, u64* coeffs_copy, u64* lde, u32 n_log,
-                    u32 rate_bits, u32 b0, u32 b1) {
+// partitioned LDE (sharded.inl): the k columns are dealt to G ranks in groups of G * w (column c: rank (c % (G w)) / w, local
+// column (c / (G w)) * w + c % w; src[q] = rank q's local columns, [.][n]).  sel = 0: physical columns [col0, col0 + count);
+// sel = 1: the first `count` columns of rank src_rank from group col0 / (G w) on.  pull: gathered from src into coeffs_copy
+// [k][n] on the way; else read from coeffs_copy.  Coset blocks [b0, b1) into lde [k][(b1 - b0) * n].
+int emu_ct_lde_cols(const u64* const* src, u32 G, u32 w, u32 k, u32 col0, u32 count, u32 sel, u32 src_rank, int pull, u64* coeffs_copy,
+                    u64* lde, u32 n_log, u32 rate_bits, u32 b0, u32 b1) {
     u64 n = (u64)1 << n_log;
     if (!ntc::covers(n_log)) return 0;
     std::vector<u64> z, zf;
@@ -158,9 +159,9 @@ int emu_ct_lde_cols(const u64* const* src, u32 n_src, u32 kp, u32 k, u32 ca, u32
         zf.insert(zf.end(), fb.begin(), fb.end());
     }
     ntc::ColumnSet cs;
-    cs.run = cb - ca; cs.period = kp; cs.col0 = ca; cs.limit = k; cs.n_src = n_src; cs.pull = pull != 0;
-    for (u32 q = 0; q < n_src; q++) cs.src[q] = src[q];
-    cs.src_col0 = ca; cs.src_col_stride = n; cs.copy_out = coeffs_copy; cs.copy_col_stride = n;
+    cs.run = w; cs.period = G * w; cs.col0 = col0; cs.limit = k; cs.count = count; cs.sel = sel; cs.src_rank = src_rank; cs.pull = pull != 0;
+    for (u32 q = 0; q < G && q < (u32)ntc::MAX_SRC; q++) cs.src[q] = src[q];
+    cs.src_col_stride = n; cs.copy_out = coeffs_copy; cs.copy_col_stride = n;
     ntc::Plan plan;
     if (!ntc::make_plan(&plan, coeffs_copy, n, lde, (u64)(b1 - b0) * n, nullptr, n_log, 0, b1 - b0, n, false, z.data(), zf.data(), 0, false, &cs)) return 0;
     for (u32 pi = 0; pi < plan.n_passes; pi++) run_ct_pass(plan.pass[pi], plan.bits[pi], plan.kind[pi], plan.grid[pi]);
@@ -214,6 +215,20 @@ void emu_permute(u64* s) { u64 t[12]; memcpy(t, s, sizeof t); poseidon::permute(
 void emu_sponge(const u64* leaf, u64 col_stride, u32 len, u32 noop_short, u64* out4) {
     u64 s[12];
     merkle::sponge_leaf(leaf, col_stride, len, noop_short, s);
+    memcpy(out4, s, 32);
+}
+// the sponge of one leaf absorbed in pieces cut at `cuts` (multiples of the rate), the state carried between the pieces
+void emu_sponge_pieces(const u64* leaf, u64 col_stride, u32 len, const u32* cuts, u32 n_cuts, u64* out4) {
+    u64 s[12] = {0};
+    u32 begin = 0;
+    for (u32 i = 0; i <= n_cuts; i++) {
+        const u32 end = i < n_cuts ? cuts[i] : len;
+        u64 carried[12];
+        memcpy(carried, s, sizeof s);       // (what leaf_absorb_kernel stores and reloads)
+        memcpy(s, carried, sizeof s);
+        merkle::sponge_absorb(leaf, col_stride, begin, end, s);
+        begin = end;
+    }
     memcpy(out4, s, 32);
 }
 u64 emu_node_slot(u32 sub_log, u64 subtree, u32 layer, u64 m) {

@@ -34,14 +34,16 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     n, N = 1 << n_log, 1 << (n_log + r)
     lay = shard_layout(n_log, k, r, h, rank, world)
     values = O.synthetic_values(k, n, seed=2)
-    # 1. column shard of the inverse transform (zero-padded to kp columns)
+    # 1. column shard of the inverse transform (zero-padded to kp columns): the rank's columns, w of every group of L
     mine = np.zeros((lay["kp"], n), np.uint64)
-    for i, c in enumerate(range(lay["col_begin"], lay["col_end"])):
+    for i, c in enumerate(lay["cols"]):
         mine[i] = O.ifft(values[c])
-    # 2. all-gather of coefficients
+    # 2. all-gather of coefficients; column c is local column (c // L) * w + c % w of rank (c % L) // w
     gathered = torch.zeros((world * lay["kp"], n), dtype=torch.int64)
     dist.all_gather_into_tensor(gathered, torch.from_numpy(mine.view(np.int64)))
-    coeffs = gathered.numpy().view(np.uint64)[:k]
+    shards = gathered.numpy().view(np.uint64).reshape(world, lay["kp"], n)
+    L, w = lay["group"], lay["per_group"]
+    coeffs = np.stack([shards[(c % L) // w][(c // L) * w + c % w] for c in range(k)])
     # 3. this rank's coset blocks: block b = leaves [b*n, (b+1)*n) = size-n coset NTT in bit-reversed order
     perm_n = bitrev_perm(n_log)
     g2 = 1753635133440165772
@@ -83,7 +85,7 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_log,k,r,h", [(4, 5, 3, 4), (3, 7, 1, 1)])
+@pytest.mark.parametrize("n_log,k,r,h", [(4, 5, 3, 4), (3, 7, 1, 1), (3, 19, 1, 1)])
 def test_two_rank_partition_reproduces_commitment(n_log, k, r, h):
     world = 2
     port = _free_port()
@@ -102,8 +104,10 @@ def test_shard_layout_covers_everything():
     from intmax_zkp_core_b200.device import shard_layout
     for world in (1, 2, 4, 8):
         lays = [shard_layout(20, 135, 3, 4, g, world) for g in range(world)]
-        assert lays[0]["col_begin"] == 0 and lays[-1]["col_end"] == 135
-        assert all(a["col_end"] == b["col_begin"] for a, b in zip(lays, lays[1:]))
+        assert sorted(c for l in lays for c in l["cols"]) == list(range(135))
+        assert all(l["n_cols"] <= l["kp"] and l["group"] % 8 == 0 for l in lays)
+        # every group of `group` columns holds `per_group` consecutive columns of every rank
+        assert all(l["cols"][:l["per_group"]] == list(range(g * l["per_group"], (g + 1) * l["per_group"])) for g, l in enumerate(lays))
         assert sum(l["N_local"] for l in lays) == 1 << 23
         assert [l["block_begin"] for l in lays] == [g * (8 // world) for g in range(world)]
         assert all(l["cap_end"] - l["cap_begin"] == 16 // world for l in lays)

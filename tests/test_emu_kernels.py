@@ -66,6 +66,19 @@ def test_sponge_body(emu, oracle):
     assert (out == oracle.hash_or_noop(m[:, 2])).all()
 
 
+def test_sponge_in_pieces(emu, oracle):
+    """merkle::sponge_absorb (the resumable leaf hash of the partitioned commitment): any cut at multiples of the rate gives
+    hash_no_pad of the whole leaf, ragged tail included"""
+    rng = np.random.default_rng(14)
+    u32p = C.POINTER(C.c_uint32)
+    for L, cuts in ((135, [8, 16, 64, 128]), (135, [128]), (135, list(range(8, 135, 8))), (20, [16]), (16, [8]), (9, [8]), (24, [])):
+        x = rng.integers(0, P, size=L, dtype=np.uint64)
+        out = np.zeros(4, np.uint64)
+        cu = np.array(cuts + [0], np.uint32)
+        emu.emu_sponge_pieces(ptr(x), 1, L, cu.ctypes.data_as(u32p), len(cuts), ptr(out))
+        assert (out == oracle.hash_no_pad(x)).all(), (L, cuts)
+
+
 def test_digest_slots_match_recursive_layout(emu, oracle):
     """node_slot (index formula used by the kernels) == where plonky2's recursive fill puts each digest."""
     rng = np.random.default_rng(13)
@@ -124,38 +137,57 @@ def test_ct_pass_bodies(emu, oracle, n_log):
             assert (lde[c] == oracle.coset_lde(v[c], r)[perm][b0 * n:b1 * n]).all(), (r, b0, b1)
 
 
-@pytest.mark.parametrize("n_log,k,G,chunks", [(11, 7, 2, 1), (12, 7, 4, 2), (13, 5, 2, 2), (11, 9, 8, 1)])
-def test_ct_pull_pass_bodies(emu, oracle, n_log, k, G, chunks):
-    """partitioned LDE (sharded.inl): the first pass gathers column chunks from per-rank coefficient windows (KIND_PULL_LOOP,
-    stepped on the host with the plain-load staging), later passes walk the same column set in place; rank g keeps coset
-    blocks [g * 2^r / G, (g + 1) * 2^r / G)"""
+def owned_columns(k, G, g):
+    """partition of the columns over G ranks (sharded.inl): groups of L = max(8, G) columns, w = L / G of each group per rank"""
+    L = max(8, G)
+    w = L // G
+    return [c for c in range(k) if (c % L) // w == g]
+
+
+@pytest.mark.parametrize("n_log,k,G", [(11, 7, 2), (12, 21, 4), (13, 11, 2), (11, 19, 8)])
+def test_ct_pull_pass_bodies(emu, oracle, n_log, k, G):
+    """partitioned LDE (sharded.inl): the first pass gathers the columns of a group range from per-rank coefficient windows
+    (KIND_PULL_LOOP, stepped on the host with the plain-load staging), later passes walk the same columns in place; rank g keeps
+    coset blocks [g * 2^r / G, (g + 1) * 2^r / G).  Also: the columns of one source only (the shard-by-shard pipeline)."""
     rng = np.random.default_rng(300 + n_log)
     n, r = 1 << n_log, 3
-    kp = -(-k // G)
+    L = max(8, G)
+    w = L // G
+    kp = -(-k // L) * w
     c = rng.integers(0, 2**64, size=(k, n), dtype=np.uint64)
     win = [np.zeros((kp, n), np.uint64) for _ in range(G)]
     for q in range(G):
-        lo, hi = min(k, q * kp), min(k, (q + 1) * kp)
-        win[q][:hi - lo] = c[lo:hi]
-    srcs = (u64p * G)(*[ptr(w) for w in win])
+        cols = owned_columns(k, G, q)
+        win[q][:len(cols)] = c[cols]
+    srcs = (u64p * G)(*[ptr(x) for x in win])
     bpr = (1 << r) // G
     for g in (0, G - 1):
         b0, b1 = g * bpr, (g + 1) * bpr
-        copy = np.zeros((k, n), np.uint64)
-        lde = np.zeros((k, (b1 - b0) * n), np.uint64)
-        per = -(-kp // chunks)
-        for j in range(chunks):
-            ca, cb = min(kp, j * per), min(kp, (j + 1) * per)
-            if cb > ca:
-                assert emu.emu_ct_lde_cols(srcs, G, kp, k, ca, cb, 1, ptr(copy), ptr(lde), n_log, r, b0, b1) == 1
-        assert (copy == c).all()
-        want = np.zeros_like(lde)
+        want = np.zeros((k, (b1 - b0) * n), np.uint64)
         assert emu.emu_ct_lde(ptr(c), ptr(want), n_log, k, r, b0, b1) == 1
+        # group by group (the host-input pipeline), gathering
+        copy = np.zeros((k, n), np.uint64)
+        lde = np.zeros_like(want)
+        for col0 in range(0, k, L):
+            cnt = min(L, k - col0)
+            assert emu.emu_ct_lde_cols(srcs, G, w, k, col0, cnt, 0, 0, 1, ptr(copy), ptr(lde), n_log, r, b0, b1) == 1
+        assert (copy == c).all()
         assert (lde == want).all()
-        # the same column sets without the gather (coefficients already local)
-        lde2 = np.zeros_like(lde)
-        assert emu.emu_ct_lde_cols(srcs, G, kp, k, 0, kp, 0, ptr(copy), ptr(lde2), n_log, r, b0, b1) == 1
-        assert (lde2 == want).all()
+        # an arbitrary column range in one go (device inputs), gathering
+        copy2 = np.zeros((k, n), np.uint64)
+        lde2 = np.zeros_like(want)
+        cut = min(k, 5)
+        assert emu.emu_ct_lde_cols(srcs, G, w, k, 0, cut, 0, 0, 1, ptr(copy2), ptr(lde2), n_log, r, b0, b1) == 1
+        if k > cut:
+            assert emu.emu_ct_lde_cols(srcs, G, w, k, cut, k - cut, 0, 0, 1, ptr(copy2), ptr(lde2), n_log, r, b0, b1) == 1
+        assert (copy2 == c).all() and (lde2 == want).all()
+        # shard by shard from the gathered matrix (no gather): the columns of one source at a time
+        lde3 = np.zeros_like(want)
+        for q in range(G):
+            cnt = len(owned_columns(k, G, q))
+            if cnt:
+                assert emu.emu_ct_lde_cols(srcs, G, w, k, 0, -(-cnt // w) * w, 1, q, 0, ptr(copy), ptr(lde3), n_log, r, b0, b1) == 1
+        assert (lde3 == want).all()
 
 
 def test_ntt_hostile_columns(emu, oracle):

@@ -69,7 +69,7 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     ctx = D.torch_context(rank)
     comm = D.Comm.from_torch_distributed(ctx)
     lay = D.shard_layout(n_log, k, r, h, rank, world)
-    mine = np.ascontiguousarray(v[lay["col_begin"]:lay["col_end"]])
+    mine = np.ascontiguousarray(v[lay["cols"]])
     sh = D.ShardedCommitment(comm, n_log, k, r, h)
     # device-resident input (asynchronous), twice: the second commit reuses every buffer
     dv = torch.from_numpy(mine.view(np.int64)).to(dev) if mine.size else None
@@ -84,7 +84,7 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     ok &= _check_rank(O, sh, 0, lay, ref, n_log, k, r, h)
     ok &= _check_rows(O, sh, ref, n_log, r, h)
     # from_coeffs form
-    cf = np.ascontiguousarray(ref["coeffs"][lay["col_begin"]:lay["col_end"]])
+    cf = np.ascontiguousarray(ref["coeffs"][lay["cols"]])
     sh.run(torch.from_numpy(cf.view(np.int64)).to(dev) if cf.size else None, is_coeffs=True)
     ok &= _check_rank(O, sh, 0, lay, ref, n_log, k, r, h)
     # other data through the same buffers and exchange windows (a stale read of a peer's window would show here), in both
@@ -92,7 +92,7 @@ def _worker(rank, world, port, n_log, k, r, h, q):
     peer = comm.peer_exchange
     v2 = O.synthetic_values(k, n, seed=4)
     ref2 = O.commit(v2, r, h)
-    mine2 = np.ascontiguousarray(v2[lay["col_begin"]:lay["col_end"]])
+    mine2 = np.ascontiguousarray(v2[lay["cols"]])
     dv2 = torch.from_numpy(mine2.view(np.int64)).to(dev) if mine2.size else None
     hv2 = torch.from_numpy(mine2.view(np.int64)).pin_memory() if mine2.size else None
     for form in ((True, False) if peer else (False,)):
@@ -153,14 +153,12 @@ def test_one_process_drives_all_gpus(oracle, n_log, k, r, h, monkeypatch):
     ref = O.commit(v, r, h)
     sh = D.ShardedCommitment(comm, n_log, k, r, h)
     lays = sh.layouts
-    host = [torch.from_numpy(np.ascontiguousarray(v[l["col_begin"]:l["col_end"]]).view(np.int64)).pin_memory()
-            if l["col_end"] > l["col_begin"] else None for l in lays]
+    host = [torch.from_numpy(np.ascontiguousarray(v[l["cols"]]).view(np.int64)).pin_memory() if l["n_cols"] else None for l in lays]
     cap_host = torch.zeros((1 << h, 4), dtype=torch.int64).pin_memory()
     assert comm.peer_exchange, "peer access between the GPUs of one box"
     v2 = O.synthetic_values(k, n, seed=6)
     ref2 = O.commit(v2, r, h)
-    host2 = [torch.from_numpy(np.ascontiguousarray(v2[l["col_begin"]:l["col_end"]]).view(np.int64)).pin_memory()
-             if l["col_end"] > l["col_begin"] else None for l in lays]
+    host2 = [torch.from_numpy(np.ascontiguousarray(v2[l["cols"]]).view(np.int64)).pin_memory() if l["n_cols"] else None for l in lays]
     for groups in (None, 2, 0, 1):          # None: peer-memory exchange; else the NCCL exchange with that group size
         comm.set_peer_exchange(groups is None)
         assert comm.peer_exchange == (groups is None)
