@@ -104,7 +104,8 @@ struct b200zkp_comm {
     std::vector<int> rank;             // global rank of local rank i
     std::vector<b200zkp_ctx*> ctx;     // (not owned)
     std::vector<ncclComm_t> nc;
-    std::vector<cudaStream_t> xstream; // exchange stream per local rank (NCCL point-to-point groups)
+    std::vector<cudaStream_t> xstream; // side stream per local rank: NCCL point-to-point groups; in-place passes beside the gather pass
+    std::vector<cudaStream_t> hstream; // hash stream per local rank: sponge absorption of a column chunk beside the transforms of the next
     std::vector<cudaEvent_t> ev;       // per local rank: [2 + world] events (coefficients ready, buffers free, one per group)
     uint32_t peers_per_group = 2;
     bool peer_ok = false;              // peer memory reaches every rank from every rank (decided collectively at init)
@@ -460,6 +461,9 @@ static int comm_finish_init(b200zkp_comm* c) {
             (void)cudaGetLastError(); c->err = "cannot create the exchange stream"; return B200ZKP_ERR_CUDA;
         }
         c->xstream.push_back(s);
+        cudaStream_t hs = nullptr;
+        if (cudaStreamCreateWithFlags(&hs, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); c->err = "cannot create the hash stream"; return B200ZKP_ERR_CUDA; }
+        c->hstream.push_back(hs);
         for (int e = 0; e < 2 + c->world; e++) {
             cudaEvent_t ev = nullptr;
             if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); c->err = "cannot create an event"; return B200ZKP_ERR_CUDA; }
@@ -534,6 +538,7 @@ extern "C" void b200zkp_comm_destroy(b200zkp_comm* c) {
     }
     for (size_t i = 0; i < c->nc.size(); i++) if (c->nc[i]) nccl_api().CommDestroy(c->nc[i]);
     for (int i = 0; i < (int)c->xstream.size(); i++) { cudaSetDevice(c->ctx[i]->device); cudaStreamDestroy(c->xstream[i]); }
+    for (int i = 0; i < (int)c->hstream.size(); i++) { cudaSetDevice(c->ctx[i]->device); cudaStreamSynchronize(c->hstream[i]); cudaStreamDestroy(c->hstream[i]); }
     for (size_t e = 0; e < c->ev.size(); e++) {
         cudaSetDevice(c->ctx[e / (2 + c->world)]->device);
         cudaEventDestroy(c->ev[e]);
@@ -572,6 +577,7 @@ static void sharded_release(b200zkp_sharded* sh) {
         Guard g(ctx);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(sh->comm->xstream[i]);
+        cudaStreamSynchronize(sh->comm->hstream[i]);
         ShardRank& s = sh->r[i];
         dev_release(ctx, s.coeffs_all, s.coeffs_b); dev_release(ctx, s.lde, s.lde_b); dev_release(ctx, s.digests, s.digests_b);
         dev_release(ctx, s.cap_local, s.cap_local_b); dev_release(ctx, s.cap, s.cap_b); dev_release(ctx, s.stage, s.stage_b);
@@ -734,7 +740,7 @@ static int sharded_commit_rank(b200zkp_sharded* sh, int i, ShardInput in, int on
     const u32 G = (u32)c->world, g = (u32)c->rank[i];
     const u64 n = (u64)1 << sh->n_log;
     const u32 L = sh->L, w = sh->w, kp = sh->kp, k = sh->k, kl = sh->local_cols(g);
-    cudaStream_t main_s = ctx->stream, side_s = c->xstream[i];
+    cudaStream_t main_s = ctx->stream, side_s = c->xstream[i], hash_s = c->hstream[i];
     if (kl && !in.base) BAD(ctx, "null input shard");
     if (on_device && in.full_matrix) BAD(ctx, "internal: device inputs are packed shards");
 
@@ -908,13 +914,23 @@ static int sharded_commit_rank(b200zkp_sharded* sh, int i, ShardInput in, int on
         TRY(peer_publish_and_wait_chunk(c, i, j, epoch));
         TRY(gather_lde(pa, pb, /*split=*/on_device != 0));
         if (resumable) {
-            TRY(join_side());
-            StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
+            // the chunk's columns are absorbed on the hash stream as soon as their last pass is through; the main stream goes on
+            // with the next chunk (its gather pass waits on NVLink more than it computes: the two kernels share the SMs)
+            cudaEvent_t e_lde;
+            TRY(next_event(&e_lde));
+            CUDA_TRY(ctx, cudaEventRecord(e_lde, side_used ? side_s : main_s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(hash_s, e_lde, 0));
             const unsigned threads = hash_block_threads(sh->N_local);
-            merkle::leaf_absorb_kernel<<<(unsigned)((sh->N_local + threads - 1) / threads), threads, 0, main_s>>>(
+            merkle::leaf_absorb_kernel<<<(unsigned)((sh->N_local + threads - 1) / threads), threads, 0, hash_s>>>(
                 s.lde, sh->N_local, k, pa, pb, sh->N_local, shape, s.sponge, sh->N_local, s.digests, s.cap_local);
             LAUNCH_CHECK(ctx);
         }
+    }
+    if (resumable) {
+        cudaEvent_t e_hash;
+        TRY(next_event(&e_hash));
+        CUDA_TRY(ctx, cudaEventRecord(e_hash, hash_s));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, e_hash, 0));
     }
     if (peer) {
         TRY(peer_publish_done(c, i, epoch));             // every window has been read by this rank
