@@ -1,6 +1,8 @@
 // One commitment partitioned over several GPUs behind the C ABI (include/b200zkp.h, "partitioned over several GPUs").
 // Included at the end of b200zkp.cu (uses its static stage functions).  Product code: NCCL is the only library on this
-// path and it only moves the coefficient shards and the 512-byte cap; every transform and hash is this repo's kernels.
+// path and in the default (peer-memory) form it only moves the 512-byte cap and the handshakes of the set-up; the coefficient
+// shards cross NVLink inside this repo's own first-pass kernel (ntc::ct_pull_kernel), every transform and hash is this
+// repo's kernels.  The NCCL point-to-point form of the exchange is the fallback.
 //
 // Replaces nothing in plonky2 (the CPU prover is one process on one memory): it is north_star's multi-GPU form of
 // PolynomialBatch::from_values, reached from the same prove() call sites
