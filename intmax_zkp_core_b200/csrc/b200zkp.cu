@@ -59,6 +59,7 @@ struct b200zkp_ctx {
     bool ntt_tma = true;                                // B200ZKP_NTT_TMA=0: the new passes stage their tiles with plain loads
     u32 ct_smem_set = 0;                                // kernels whose dynamic shared memory limit has been raised on this device
     u32 sm_count = 0;                                   // (queried on first use)
+    u64 coop_level_nodes = 2048;                        // tree levels of at most this many parents use the latency form (B200ZKP_COOP_LEVEL_NODES)
     // mailbox: 64 KB of mapped pinned host memory the small host-buffer calls (single hashes, the Fiat-Shamir transcript)
     // read and write directly from the kernel: no cudaMemcpy on those paths, one launch + one stream synchronise per call
     void* mailbox = nullptr;
@@ -550,6 +551,7 @@ extern "C" int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out) {
     }
     if (const char* e = getenv("B200ZKP_NTT_CT")) ctx->ntt_ct = atoi(e) != 0;
     if (const char* e = getenv("B200ZKP_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
+    if (const char* e = getenv("B200ZKP_COOP_LEVEL_NODES")) { const long v = atol(e); if (v >= 0 && v <= (1 << 20)) ctx->coop_level_nodes = (u64)v; }
     size_t mem_free = 0, mem_total = 0;
     if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total) ctx->pool_max_bytes = mem_total / 8;
     else (void)cudaGetLastError();
@@ -812,7 +814,7 @@ static int launch_tree_levels(b200zkp_ctx* ctx, u64 n_leaves, const merkle::Tree
             break;
         }
         u64 n_parents = n_leaves >> (layer + 1);
-        if (n_parents <= COOP_MAX_NODES) {
+        if (n_parents <= ctx->coop_level_nodes) {
             // too few nodes to fill the GPU: one node per 16 lanes, ~4x less latency per level
             merkle::merkle_level_coop_kernel<<<(unsigned)((n_parents * 16 + 127) / 128), 128, 0, ctx->stream>>>(
                 digests, cap, shape, layer, n_parents, ctx->round_add);
