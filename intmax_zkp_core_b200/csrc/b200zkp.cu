@@ -59,6 +59,7 @@ struct b200zkp_ctx {
     bool ntt_tma = true;                                // B200ZKP_NTT_TMA=0: the new passes stage their tiles with plain loads
     u32 ct_smem_set = 0;                                // kernels whose dynamic shared memory limit has been raised on this device
     u32 sm_count = 0;                                   // (queried on first use)
+    u64 coop_leaf_rows = 2048;                          // leaf sponges: the same switch (B200ZKP_COOP_LEAF_ROWS)
     u64 coop_level_nodes = 2048;                        // tree levels of at most this many parents use the latency form (B200ZKP_COOP_LEVEL_NODES)
     // mailbox: 64 KB of mapped pinned host memory the small host-buffer calls (single hashes, the Fiat-Shamir transcript)
     // read and write directly from the kernel: no cudaMemcpy on those paths, one launch + one stream synchronise per call
@@ -551,6 +552,7 @@ extern "C" int b200zkp_ctx_create(int device, void* stream, b200zkp_ctx** out) {
     }
     if (const char* e = getenv("B200ZKP_NTT_CT")) ctx->ntt_ct = atoi(e) != 0;
     if (const char* e = getenv("B200ZKP_NTT_TMA")) ctx->ntt_tma = atoi(e) != 0;
+    if (const char* e = getenv("B200ZKP_COOP_LEAF_ROWS")) { const long v = atol(e); if (v >= 0 && v <= (1 << 24)) ctx->coop_leaf_rows = (u64)v; }
     if (const char* e = getenv("B200ZKP_COOP_LEVEL_NODES")) { const long v = atol(e); if (v >= 0 && v <= (1 << 20)) ctx->coop_level_nodes = (u64)v; }
     size_t mem_free = 0, mem_total = 0;
     if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total) ctx->pool_max_bytes = mem_total / 8;
@@ -785,7 +787,7 @@ static int launch_leaf_hash(b200zkp_ctx* ctx, const u64* leaves, u64 row_stride,
                             u64 n_rows, const merkle::TreeShape& shape, u64* digests, u64* cap) {
     if (!n_rows) return 0;
     StageTimer tm(ctx, B200ZKP_STAGE_LEAF_HASH);
-    if (n_rows <= COOP_MAX_NODES) {
+    if (n_rows <= ctx->coop_leaf_rows) {
         merkle::leaf_hash_coop_kernel<<<(unsigned)((n_rows * 16 + 127) / 128), 128, 0, ctx->stream>>>(
             leaves, row_stride, col_stride, leaf_len, row0, n_rows, shape, digests, cap, 1u, ctx->round_add);
         LAUNCH_CHECK(ctx);
