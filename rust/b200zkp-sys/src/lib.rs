@@ -12,6 +12,21 @@ use std::os::raw::{c_char, c_int, c_void};
 
 pub const B200ZKP_COMM_ID_BYTES: usize = 128;
 pub const B200ZKP_MAX_GATES: usize = 16;
+/// gate kinds of `b200zkp_vanishing_desc::gate_kind` (include/b200zkp.h B200ZKP_GATE_*); parameters in `gate_params`
+pub const B200ZKP_GATE_NOOP: u32 = 0;
+pub const B200ZKP_GATE_CONSTANT: u32 = 1;
+pub const B200ZKP_GATE_PUBLIC_INPUT: u32 = 2;
+pub const B200ZKP_GATE_ARITHMETIC: u32 = 3;
+pub const B200ZKP_GATE_POSEIDON: u32 = 4;
+pub const B200ZKP_GATE_ARITHMETIC_EXTENSION: u32 = 5;
+pub const B200ZKP_GATE_MUL_EXTENSION: u32 = 6;
+pub const B200ZKP_GATE_BASE_SUM: u32 = 7; // { B, num_limbs }
+pub const B200ZKP_GATE_REDUCING: u32 = 8; // { num_coeffs }
+pub const B200ZKP_GATE_REDUCING_EXTENSION: u32 = 9; // { num_coeffs }
+pub const B200ZKP_GATE_RANDOM_ACCESS: u32 = 10; // { bits, num_copies, num_extra_constants }
+pub const B200ZKP_GATE_EXPONENTIATION: u32 = 11; // { num_power_bits }
+pub const B200ZKP_GATE_POSEIDON_MDS: u32 = 12;
+
 /// include/b200zkp.h `b200zkp_vanishing_desc` (row N1b: what compute_quotient_polys reads of CommonCircuitData)
 #[repr(C)]
 pub struct b200zkp_vanishing_desc {
