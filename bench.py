@@ -466,6 +466,49 @@ def leaf_mix():
     return m
 
 
+def ntt_roofline_block(lde_ms, intt_ms, lde_cells, intt_cells, n_log, hbm_peak):
+    """The transforms against both roofs.  They are bound by the ALU pipe, not by HBM (a butterfly of two 8-byte elements is ~28
+    integer instructions, 20 of them on the ALU pipe; log2(n) / 2 butterflies per element and transform): `alu_pipe_busy` is
+    ncu's pipe utilisation of the slowest LDE pass of the tracked capture (the integer roof of a pass is 100 %), the HBM figures
+    are algorithmic bytes over the live stage times."""
+    m = ntt_mix()
+    blk = {"bound": "int (ALU pipe)",
+           "lde": {"ms": lde_ms, "algorithmic_gbs": (72 * lde_cells) / (lde_ms * 1e-3) / 1e9 if lde_ms else None,
+                   "butterflies_per_s": lde_cells * 8 * n_log / 2 / (lde_ms * 1e-3) if lde_ms else None},
+           "intt": {"ms": intt_ms, "algorithmic_gbs": (16 * intt_cells) / (intt_ms * 1e-3) / 1e9 if intt_ms else None},
+           "hbm_peak_gbs": hbm_peak}
+    if blk["lde"]["algorithmic_gbs"]:
+        blk["lde"]["hbm_frac"] = blk["lde"]["algorithmic_gbs"] / hbm_peak
+    if m:
+        lde = [l for l in m["launches"] if l["ms"] and l["ms"] > 2.0] or m["launches"]
+        blk["profile"] = {"file": "profiles/ntt_mix.json", "stale": m["stale"], "source_key": m["source_key"],
+                          "lde_passes": [{k: l[k] for k in ("kernel", "ms", "dram_gbs", "alu_pipe_pct", "fmaheavy_pipe_pct", "issue_pct", "registers")} for l in lde],
+                          "alu_pipe_busy": max(l["alu_pipe_pct"] for l in lde) / 100.0,
+                          "dram_frac_of_measured_peak": max(l["dram_gbs"] for l in lde) / hbm_peak}
+    return blk
+
+
+def ntt_source_key():
+    h = hashlib.sha256()
+    for name in ("goldilocks.cuh", "ntt_ct_kernels.cuh"):
+        with open(os.path.join(ROOT, "intmax_zkp_core_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def ntt_mix():
+    """per-pass ncu figures of the transform kernels (profiles/ntt_mix.json, tools/ncu_ntt.py), keyed by the hash of the kernel
+    sources they were captured from; `stale` when the sources have changed since"""
+    p = os.path.join(ROOT, "profiles", "ntt_mix.json")
+    try:
+        with open(p) as f:
+            m = json.load(f)
+    except Exception:
+        return None
+    m["stale"] = m.get("source_key") != ntt_source_key()
+    return m
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import ctypes as C
@@ -656,6 +699,7 @@ def run_b200(args):
             "ntt_hbm": {"lde_algorithmic_gbs": (72 * lde_cells) / (lde_ms * 1e-3) / 1e9 if lde_ms else None,
                         "intt_algorithmic_gbs": (16 * (n * lay["n_cols"])) / (intt_ms * 1e-3) / 1e9 if intt_ms else None,
                         "peak": peak, "note": "SURVEY.md 8d stage bytes: LDE 72 B/cell, iNTT 16 B/cell (rank 0's share at N > 1)"},
+            "ntt_roofline": ntt_roofline_block(lde_ms, intt_ms, lde_cells, n * lay["n_cols"], n_log, peak),
             "stages_ms_per_step": {s: v[0] / args.steps for s, v in stages.items()},
             "poseidon_perms_per_s": perms / (ms_step * 1e-3),
             "cap_checksum": cap_checksum,
