@@ -87,3 +87,23 @@ def test_host_mirror_argument_errors():
     with pytest.raises(ValueError):
         z.PolynomialBatch.from_values(np.zeros((3, 8), np.uint64), 1, False, 5, ctx=object())
     assert z.HashOut.from_hex(z.HashOut([1, 2, 3, 2**63]).to_hex()) == z.HashOut([1, 2, 3, 2**63])
+
+
+def test_bench_profile_blocks_are_keyed_to_the_kernel_sources():
+    """bench.py's roofline blocks read ncu figures from profiles/*.json; each carries the hash of the kernel sources it was
+    captured from and is reported `stale` when they changed.  The committed profiles must load, and the staleness test must
+    react to a different key."""
+    import json
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    for fn, key in ((bench.leaf_mix, bench.kernel_source_key), (bench.ntt_mix, bench.ntt_source_key)):
+        m = fn()
+        assert m is not None and isinstance(m["stale"], bool) and len(key()) == 16
+        assert m["stale"] == (m["source_key"] != key())
+    blk = bench.ntt_roofline_block(18.8, 2.54, 135 << 20, 135 << 20, 20, 6550.1)
+    assert blk["bound"].startswith("int") and 0.05 < blk["lde"]["hbm_frac"] < 0.2
+    assert abs(blk["lde"]["butterflies_per_s"] - (135 << 20) * 8 * 10 / 18.8e-3) < 1e3
+    json.dumps(blk)
+    if "profile" in blk:
+        assert 0.5 < blk["profile"]["alu_pipe_busy"] <= 1.0 and len(blk["profile"]["lde_passes"]) == 3
