@@ -3,8 +3,22 @@
 //! the public signatures of PolynomialBatch::from_values / from_coeffs stay as they are; only the bodies
 //! call the C ABI.  `copy-back` mode materialises plonky2's own fields so the rest of prove() is untouched.
 use b200zkp_sys as sys;
-use plonky2_field::types::Field;
+use plonky2_field::fft::FftRootTable;
 use plonky2_field::polynomial::{PolynomialCoeffs, PolynomialValues};
+use plonky2_field::types::Field;
+use plonky2_util::log2_strict;
+
+use crate::fri::oracle::{PolynomialBatch, SALT_SIZE};
+use crate::hash::hash_types::{HashOut, RichField};
+use crate::hash::merkle_tree::{MerkleCap, MerkleTree};
+use crate::plonk::config::GenericConfig;
+use crate::util::timing::TimingTree;
+use plonky2_field::extension::Extendable;
+
+/// four canonical words of the library's digest layout -> plonky2's HashOut (PoseidonGoldilocksConfig: Hasher::Hash = HashOut<F>)
+fn hash_out_from_u64s<F: RichField>(w: &[u64]) -> HashOut<F> {
+    HashOut { elements: [F::from_canonical_u64(w[0]), F::from_canonical_u64(w[1]), F::from_canonical_u64(w[2]), F::from_canonical_u64(w[3])] }
+}
 
 thread_local! { static CTX: *mut sys::b200zkp_ctx = unsafe {
     let mut c = std::ptr::null_mut();

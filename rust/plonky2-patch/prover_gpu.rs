@@ -3,6 +3,16 @@
 // INTEGRATION.md; the same C ABI calls are exercised from Python (intmax_zkp_core_b200/prover.py) and C++
 // (host/prover_api.hpp), which is what the parity tests run.
 use b200zkp_sys as sys;
+use plonky2_field::extension::Extendable;
+use plonky2_field::polynomial::{PolynomialCoeffs, PolynomialValues};
+use plonky2_field::types::Field;
+use plonky2_util::log2_strict;
+
+use crate::fri::oracle::CTX;            // the thread-local b200zkp_ctx of oracle_gpu.rs (made pub(crate) there)
+use crate::hash::hash_types::RichField;
+use crate::iop::witness::MatrixWitness;
+use crate::plonk::circuit_data::{CommonCircuitData, ProverOnlyCircuitData};
+use crate::plonk::config::GenericConfig;
 
 /// all_wires_permutation_partial_products + the `pop()` / `concat()` that moves every Z to the front: returns the
 /// `zs_partial_products` batch of prove() (Z of every challenge, then the partial products challenge by challenge).
