@@ -702,6 +702,7 @@ def run_b200(args):
             "ntt_roofline": ntt_roofline_block(lde_ms, intt_ms, lde_cells, n * lay["n_cols"], n_log, peak),
             "stages_ms_per_step": {s: v[0] / args.steps for s, v in stages.items()},
             "poseidon_perms_per_s": perms / (ms_step * 1e-3),
+            "lde_cells_per_s": value * (1 << RATE_BITS),          # the same throughput counted in LDE cells
             "cap_checksum": cap_checksum,
         }
         if world > 1:
